@@ -1,0 +1,164 @@
+/*
+ * pk_capi.h -- C ABI of libpkb200.so, the B200-native (sm_100a) replacement for the
+ * Monte-Carlo hot path of lizmoscow/polar-codes-with-bch-kernel.
+ *
+ * Every entry point names the reference interface it replaces (file:line under the
+ * reference tree).  Plain pointers and sizes only; no exceptions cross the boundary:
+ * every function returns PK_OK (0) or a negative pk_status and leaves a message in
+ * pk_last_error().  There is NO CPU fallback: without a CUDA device every compute
+ * call fails with PK_ERR_CUDA.
+ *
+ * Conventions (identical to the reference):
+ *   - bits are one byte each (0/1), polynomial index == array index == power of x
+ *     (headers/bchCoder.h:10-48);
+ *   - a frame is n bytes (codeword / hard decisions) or n doubles (channel output y);
+ *   - batches are row-major [B][n], caller-owned.
+ *   Pointers named d_* must be device pointers on the handle's device, all others host.
+ */
+#ifndef PK_CAPI_H
+#define PK_CAPI_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PK_OK = 0,
+    PK_ERR_ARG = -1,         /* the reference throws "Invalid values of arguments" (src/main.cpp:55-57) */
+    PK_ERR_UNSUPPORTED = -2, /* no sm_100a kernel instantiated for this (m,t) */
+    PK_ERR_CUDA = -3,        /* CUDA runtime error / no device */
+    PK_ERR_ALLOC = -4
+} pk_status;
+
+/* per-frame flags in pk_frame_rec.flags */
+#define PK_FLAG_EARLY_RETURN 0x01 /* left through `if (l < calcRightSide()) return;` (KanekoKernelProcessor.cpp:380) */
+#define PK_FLAG_NO_DECISION 0x02  /* no trial ever succeeded: the reference leaves `res` untouched */
+#define PK_FLAG_SORT_TIE 0x04     /* equal |alpha| keys met: std::sort's tie order is unspecified for n > 16 */
+#define PK_FLAG_FRAME_ERROR 0x08  /* generation mode: decided != transmitted (dataForPlot.cpp:66) */
+#define PK_FLAG_TRUNCATED 0x10    /* stopped by the max_trials safety cap (never set with the default cap) */
+
+/* One record per decoded frame (16 bytes). The reference's three operation counters
+ * (KanekoKernelProcessor.cpp:367-369,386-404) are reconstructed as
+ *   decodingCount   = trials
+ *   comparisonCount = (trials - early) * (n + 6) + extra_cmp
+ *   summCount       = (trials - early) * (n + 1) + extra_sum        early = flags & 1 */
+typedef struct {
+    uint32_t trials;
+    uint32_t extra_cmp;
+    uint32_t extra_sum;
+    uint16_t bit_errors; /* generation mode only (dataForPlot.cpp:69-73) */
+    uint8_t flags;
+    uint8_t reserved;
+} pk_frame_rec;
+
+/* Totals of one SNR point / one batch: what fun() accumulates (dataForPlot.cpp:20,66-87). */
+typedef struct {
+    uint64_t frames;
+    uint64_t frame_errors;
+    uint64_t bit_errors;
+    uint64_t trials; /* decodingCount   */
+    uint64_t cmp;    /* comparisonCount */
+    uint64_t sum;    /* summCount       */
+    uint64_t max_trials_seen;
+    uint64_t flags_or;
+} pk_point_result;
+
+typedef struct pk_code pk_code;     /* field tables + g(x) + device tables  */
+typedef struct pk_kaneko pk_kaneko; /* decoder instance: stream + workspaces */
+
+const char *pk_last_error(void);
+int pk_device_count(void);
+
+/* ---- code construction: replaces src/main.cpp:59-95 (tables, g(x) = lcm of minimal
+ * polynomials via findMinimalPolynomial/lcm, src/bchCoder.cpp:25,217).  m in [3,8],
+ * 0 < t < 2^(m-1).  `device` is the CUDA ordinal the tables are uploaded to. */
+int pk_code_create(int m, int t, int device, pk_code **out);
+/* Host tables only, no CUDA (introspection / CPU tests); compute calls on it return PK_ERR_CUDA. */
+int pk_code_create_host(int m, int t, pk_code **out);
+void pk_code_destroy(pk_code *code);
+/* (n,k,d) banner values of main.cpp:93-97 and g(x) (gsize = n-k+1 bytes; g_out may be NULL) */
+int pk_code_info(const pk_code *code, int *n, int *k, int *d, int *gsize, uint8_t *g_out);
+/* antilogarithms[n], logarithms[n+1] exactly as main.cpp:63-78 builds them (log[0] = LONG_MAX) */
+int pk_code_tables(const pk_code *code, uint64_t *antilog_out, uint64_t *log_out);
+/* 1 if the algebraic decoder runs from the shared-memory coset table (n-k <= 16, t*m <= 15);
+ * pk_code_set_lut(code, 0) forces the Berlekamp-Massey + Chien kernels instead (call before
+ * pk_kaneko_create). */
+int pk_code_uses_lut(const pk_code *code);
+int pk_code_set_lut(pk_code *code, int enable);
+/* The coset table itself: entry r = up to t error positions (m bits each, n = none) of the
+ * algebraic decoder's answer for syndrome r(x) = word mod g, 0xFFFF = decoding failure. */
+int pk_code_coset_table(const pk_code *code, uint16_t *out /*[2^(n-k)] or NULL*/, long *nentries);
+
+/* ---- encoder: multiplyPolynomials(info,k,g,gSize,res) (src/bchCoder.cpp:120-132) */
+int pk_encode_batch(pk_code *code, const uint8_t *info /*[B][k]*/, long B, uint8_t *cw /*[B][n]*/);
+
+/* ---- algebraic decoder: Decoder::findSyndromPoly + Decoder::decode
+ * (src/Decoder.cpp:184-207,298-321).  answers[f] is written only when ok[f] == 1. */
+int pk_bch_decode_batch(pk_code *code, const uint8_t *words /*[B][n]*/, long B,
+                        uint8_t *answers /*[B][n]*/, uint8_t *ok /*[B]*/);
+
+/* ---- Kaneko decoder: KanekoKernelProcessor(pw,n,t,k,antilog,log,snr) ctor
+ * (src/KanekoKernelProcessor.cpp:17-26); llr_snr_db is the ctor's signalToNoiseRatio
+ * (main.cpp:176 passes 0.5).  J < 0: HEAD semantics T = j (line 393); J >= 0: capped
+ * T = min(j,J) (line 392, the *_e*.csv runs).  max_trials <= 0: the reference bound. */
+int pk_kaneko_create(pk_code *code, double llr_snr_db, long J, long max_trials, pk_kaneko **out);
+void pk_kaneko_destroy(pk_kaneko *dec);
+/* tuning / introspection */
+int pk_kaneko_set_frames_per_grab(pk_kaneko *dec, int frames);
+int pk_kaneko_launch_geometry(const pk_kaneko *dec, int *grid, int *block, long *smem_bytes);
+
+/* Replay mode, host buffers: decode(answer, word, res) for B frames
+ * (src/KanekoKernelProcessor.cpp:335-407).  H2D of y and D2H of the results happen
+ * inside the call (chunked, double-buffered).  decided rows of frames flagged
+ * PK_FLAG_NO_DECISION come back zero-filled (the reference leaves the caller's stale bytes;
+ * it takes 2^15-1 .. 2^31-1 consecutive failed trials to get there).  recs / totals may be NULL. */
+int pk_kaneko_decode_batch(pk_kaneko *dec, const double *y /*[B][n]*/, long B, uint8_t *decided /*[B][n]*/,
+                           uint32_t *trials /*[B] or NULL*/, pk_frame_rec *recs /*[B] or NULL*/,
+                           pk_point_result *totals /*or NULL*/);
+
+/* Replay mode, device-resident buffers, asynchronous on `stream` (a cudaStream_t, NULL =
+ * the handle's own stream).  d_totals (8 x u64, pk_point_result layout) is ACCUMULATED
+ * into, the caller zeroes it. */
+int pk_kaneko_decode_batch_dev(pk_kaneko *dec, const double *d_y, long B, uint8_t *d_decided,
+                               uint32_t *d_trials /*or NULL*/, pk_frame_rec *d_recs /*or NULL*/,
+                               uint64_t *d_totals /*or NULL*/, void *stream);
+
+/* Generation mode: the body of fun()'s while loop (src/dataForPlot.cpp:43-74) for frames
+ * [first_frame, first_frame + nframes) of SNR point `snr_index` at ebn0_db, fully on the
+ * device: Philox4x32-10 info bits + AWGN (counter = (frame, snr_index, draw), key = seed)
+ * -> encode -> Kaneko decode -> compare.  Results do not depend on how the frame range
+ * is split over calls or GPUs.  d_recs (nframes records) may be NULL.  Asynchronous on
+ * `stream`; d_totals is accumulated into. */
+int pk_kaneko_run_frames_dev(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t seed,
+                             uint64_t first_frame, long nframes, pk_frame_rec *d_recs /*or NULL*/,
+                             uint64_t *d_totals, void *stream);
+
+/* Same, synchronous, host-side result (adds into *totals). recs (host, nframes) may be NULL. */
+int pk_kaneko_run_frames(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame,
+                         long nframes, pk_frame_rec *recs /*or NULL*/, pk_point_result *totals);
+
+/* The frames generation mode would draw, written out (host buffers; any may be NULL):
+ * generateRandomPoly + multiplyPolynomials + addNoise (dataForPlot.cpp:45-48) on the Philox stream. */
+int pk_generate_frames(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame,
+                       long nframes, uint8_t *info /*[B][k]*/, uint8_t *cw /*[B][n]*/, double *y /*[B][n]*/);
+
+/* One whole SNR point with fun()'s stop rule `count < p && countErr < e`
+ * (dataForPlot.cpp:43), evaluated in frame order on the per-frame records so the result
+ * equals a sequential run over the same Philox frames.  Frames [rank, world) are
+ * interleaved in blocks of `chunk`; the caller reduces *out across ranks when world > 1
+ * and e is unlimited (e <= 0).  With world == 1 the stop rule is exact. */
+int pk_kaneko_run_point(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t seed, long p, long e,
+                        pk_point_result *out);
+
+/* n x n nested-BCH polarisation kernel, makeMatrix (src/bchCoder.cpp:317-345); row-major bytes. */
+int pk_make_kernel_matrix(const pk_code *code, uint8_t *out /*[n][n]*/);
+
+/* Introspection for bench.py: kernels launched by this library since load / reset. */
+uint64_t pk_launch_count(void);
+void pk_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PK_CAPI_H */

@@ -1,0 +1,245 @@
+"""ctypes binding of libpkb200.so (include/pk_capi.h).
+
+Thin plumbing for tests, bench.py and the multi-GPU sweep: it passes numpy host buffers or
+torch device pointers straight through the C ABI.  There is no Python implementation of any
+algorithm here and no fallback: if the shared library is missing the import fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpkb200.so")
+
+PK_FLAG_EARLY_RETURN = 0x01
+PK_FLAG_NO_DECISION = 0x02
+PK_FLAG_SORT_TIE = 0x04
+PK_FLAG_FRAME_ERROR = 0x08
+PK_FLAG_TRUNCATED = 0x10
+
+#: numpy view of pk_frame_rec (16 bytes)
+FRAME_REC = np.dtype(
+    [("trials", "<u4"), ("extra_cmp", "<u4"), ("extra_sum", "<u4"), ("bit_errors", "<u2"), ("flags", "u1"), ("reserved", "u1")]
+)
+#: field order of pk_point_result (8 x u64)
+POINT_FIELDS = ("frames", "frame_errors", "bit_errors", "trials", "cmp", "sum", "max_trials_seen", "flags_or")
+
+#: every symbol include/pk_capi.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = (
+    "pk_last_error pk_device_count pk_code_create pk_code_create_host pk_code_destroy pk_code_info pk_code_tables "
+    "pk_code_uses_lut pk_code_set_lut pk_code_coset_table pk_encode_batch pk_bch_decode_batch pk_kaneko_create "
+    "pk_kaneko_destroy pk_kaneko_set_frames_per_grab pk_kaneko_launch_geometry pk_kaneko_decode_batch "
+    "pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames "
+    "pk_kaneko_run_point pk_make_kernel_matrix pk_launch_count pk_launch_count_reset"
+).split()
+
+
+class PkError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"libpkb200 status {status}: {msg}")
+        self.status = status
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make -C {_HERE}` (or __graft_entry__.build()); "
+            "there is no CPU fallback for the CUDA path"
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, i, l, d, u64 = C.c_void_p, C.c_int, C.c_long, C.c_double, C.c_uint64
+    pp = C.POINTER(C.c_void_p)
+    ip = C.POINTER(C.c_int)
+    lib.pk_last_error.restype = C.c_char_p
+    lib.pk_device_count.restype = i
+    lib.pk_code_create.argtypes = [i, i, i, pp]
+    lib.pk_code_create_host.argtypes = [i, i, pp]
+    lib.pk_code_destroy.argtypes = [vp]
+    lib.pk_code_destroy.restype = None
+    lib.pk_code_info.argtypes = [vp, ip, ip, ip, ip, vp]
+    lib.pk_code_tables.argtypes = [vp, vp, vp]
+    lib.pk_code_uses_lut.argtypes = [vp]
+    lib.pk_code_set_lut.argtypes = [vp, i]
+    lib.pk_code_coset_table.argtypes = [vp, vp, C.POINTER(l)]
+    lib.pk_encode_batch.argtypes = [vp, vp, l, vp]
+    lib.pk_bch_decode_batch.argtypes = [vp, vp, l, vp, vp]
+    lib.pk_kaneko_create.argtypes = [vp, d, l, l, pp]
+    lib.pk_kaneko_destroy.argtypes = [vp]
+    lib.pk_kaneko_destroy.restype = None
+    lib.pk_kaneko_set_frames_per_grab.argtypes = [vp, i]
+    lib.pk_kaneko_launch_geometry.argtypes = [vp, ip, ip, C.POINTER(l)]
+    lib.pk_kaneko_decode_batch.argtypes = [vp, vp, l, vp, vp, vp, vp]
+    lib.pk_kaneko_decode_batch_dev.argtypes = [vp, vp, l, vp, vp, vp, vp, vp]
+    lib.pk_kaneko_run_frames_dev.argtypes = [vp, d, i, u64, u64, l, vp, vp, vp]
+    lib.pk_kaneko_run_frames.argtypes = [vp, d, i, u64, u64, l, vp, vp]
+    lib.pk_generate_frames.argtypes = [vp, d, i, u64, u64, l, vp, vp, vp]
+    lib.pk_kaneko_run_point.argtypes = [vp, d, i, u64, l, l, vp]
+    lib.pk_make_kernel_matrix.argtypes = [vp, vp]
+    lib.pk_launch_count.restype = u64
+    lib.pk_launch_count_reset.restype = None
+    return lib
+
+
+lib = _load()
+
+
+def _check(rc):
+    if rc != 0:
+        raise PkError(rc, lib.pk_last_error().decode(errors="replace"))
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def launch_count():
+    return int(lib.pk_launch_count())
+
+
+def launch_count_reset():
+    lib.pk_launch_count_reset()
+
+
+class Code:
+    """pk_code handle: BCH code (m, t) with its tables; device=None builds host tables only."""
+
+    def __init__(self, m, t, device=0):
+        h = C.c_void_p()
+        if device is None:
+            _check(lib.pk_code_create_host(m, t, C.byref(h)))
+        else:
+            _check(lib.pk_code_create(m, t, int(device), C.byref(h)))
+        self.h = h
+        self.m, self.t, self.device = m, t, device
+        n, k, d, gs = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        g = np.zeros(1 << m, np.uint8)
+        _check(lib.pk_code_info(h, C.byref(n), C.byref(k), C.byref(d), C.byref(gs), _np_ptr(g)))
+        self.n, self.k, self.d = n.value, k.value, d.value
+        self.g = g[: gs.value].copy()
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.pk_code_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def tables(self):
+        alog = np.zeros(self.n, np.uint64)
+        log = np.zeros(self.n + 1, np.uint64)
+        _check(lib.pk_code_tables(self.h, _np_ptr(alog), _np_ptr(log)))
+        return alog, log
+
+    @property
+    def uses_lut(self):
+        return bool(lib.pk_code_uses_lut(self.h))
+
+    def set_lut(self, enable):
+        _check(lib.pk_code_set_lut(self.h, int(bool(enable))))
+
+    def coset_table(self):
+        cnt = C.c_long()
+        _check(lib.pk_code_coset_table(self.h, None, C.byref(cnt)))
+        out = np.zeros(cnt.value, np.uint16)
+        if cnt.value:
+            _check(lib.pk_code_coset_table(self.h, _np_ptr(out), C.byref(cnt)))
+        return out
+
+    def kernel_matrix(self):
+        out = np.zeros((self.n, self.n), np.uint8)
+        _check(lib.pk_make_kernel_matrix(self.h, _np_ptr(out)))
+        return out
+
+    def encode(self, info):
+        info = np.ascontiguousarray(info, np.uint8)
+        assert info.ndim == 2 and info.shape[1] == self.k
+        cw = np.zeros((info.shape[0], self.n), np.uint8)
+        _check(lib.pk_encode_batch(self.h, _np_ptr(info), info.shape[0], _np_ptr(cw)))
+        return cw
+
+    def bch_decode(self, words, answers=None):
+        words = np.ascontiguousarray(words, np.uint8)
+        assert words.ndim == 2 and words.shape[1] == self.n
+        B = words.shape[0]
+        if answers is None:
+            answers = np.zeros((B, self.n), np.uint8)
+        ok = np.zeros(B, np.uint8)
+        _check(lib.pk_bch_decode_batch(self.h, _np_ptr(words), B, _np_ptr(answers), _np_ptr(ok)))
+        return answers, ok
+
+
+class Kaneko:
+    """pk_kaneko handle (KanekoKernelProcessor): J < 0 = HEAD semantics, J >= 0 = capped variant."""
+
+    def __init__(self, code, J=-1, llr_snr_db=0.5, max_trials=0):
+        self.code = code
+        h = C.c_void_p()
+        _check(lib.pk_kaneko_create(code.h, float(llr_snr_db), int(J), int(max_trials), C.byref(h)))
+        self.h = h
+        self.J = J
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.pk_kaneko_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_frames_per_grab(self, g):
+        _check(lib.pk_kaneko_set_frames_per_grab(self.h, int(g)))
+
+    def geometry(self):
+        g, b, s = C.c_int(), C.c_int(), C.c_long()
+        _check(lib.pk_kaneko_launch_geometry(self.h, C.byref(g), C.byref(b), C.byref(s)))
+        return g.value, b.value, s.value
+
+    # ---- replay mode, host buffers (H2D / D2H inside the call)
+    def decode(self, y, decided=None, want_recs=True):
+        y = np.ascontiguousarray(y, np.float64)
+        assert y.ndim == 2 and y.shape[1] == self.code.n
+        B = y.shape[0]
+        if decided is None:
+            decided = np.zeros((B, self.code.n), np.uint8)
+        trials = np.zeros(B, np.uint32)
+        recs = np.zeros(B, FRAME_REC) if want_recs else None
+        tot = np.zeros(8, np.uint64)
+        _check(lib.pk_kaneko_decode_batch(self.h, _np_ptr(y), B, _np_ptr(decided), _np_ptr(trials), _np_ptr(recs), _np_ptr(tot)))
+        return decided, trials, recs, dict(zip(POINT_FIELDS, (int(v) for v in tot)))
+
+    def decode_ptr(self, y_ptr, B, decided_ptr, trials_ptr=None, recs_ptr=None, totals_ptr=None):
+        """Host pointers given as ints (e.g. pinned torch tensors' data_ptr())."""
+        _check(lib.pk_kaneko_decode_batch(self.h, y_ptr, B, decided_ptr, trials_ptr, recs_ptr, totals_ptr))
+
+    # ---- replay mode, device pointers (ints), asynchronous on `stream`
+    def decode_dev(self, d_y, B, d_decided, d_trials=None, d_recs=None, d_totals=None, stream=None):
+        _check(lib.pk_kaneko_decode_batch_dev(self.h, d_y, B, d_decided, d_trials, d_recs, d_totals, stream))
+
+    # ---- generation mode
+    def run_frames_dev(self, ebn0_db, snr_index, seed, first_frame, nframes, d_totals, d_recs=None, stream=None):
+        _check(lib.pk_kaneko_run_frames_dev(self.h, float(ebn0_db), int(snr_index), int(seed), int(first_frame), int(nframes), d_recs, d_totals, stream))
+
+    def run_frames(self, ebn0_db, snr_index, seed, first_frame, nframes, want_recs=False):
+        recs = np.zeros(nframes, FRAME_REC) if want_recs else None
+        tot = np.zeros(8, np.uint64)
+        _check(lib.pk_kaneko_run_frames(self.h, float(ebn0_db), int(snr_index), int(seed), int(first_frame), int(nframes), _np_ptr(recs), _np_ptr(tot)))
+        return dict(zip(POINT_FIELDS, (int(v) for v in tot))), recs
+
+    def generate_frames(self, ebn0_db, snr_index, seed, first_frame, nframes):
+        info = np.zeros((nframes, self.code.k), np.uint8)
+        cw = np.zeros((nframes, self.code.n), np.uint8)
+        y = np.zeros((nframes, self.code.n), np.float64)
+        _check(lib.pk_generate_frames(self.h, float(ebn0_db), int(snr_index), int(seed), int(first_frame), int(nframes), _np_ptr(info), _np_ptr(cw), _np_ptr(y)))
+        return info, cw, y
+
+    def run_point(self, ebn0_db, snr_index, seed, p, e):
+        tot = np.zeros(8, np.uint64)
+        _check(lib.pk_kaneko_run_point(self.h, float(ebn0_db), int(snr_index), int(seed), int(p), int(e), _np_ptr(tot)))
+        return dict(zip(POINT_FIELDS, (int(v) for v in tot)))
+
+
+def counters_from_recs(recs, n):
+    """(decodingCount, comparisonCount, summCount) per frame from pk_frame_rec records."""
+    tr = recs["trials"].astype(np.uint64)
+    run = tr - (recs["flags"] & PK_FLAG_EARLY_RETURN).astype(np.uint64)
+    return tr, run * np.uint64(n + 6) + recs["extra_cmp"], run * np.uint64(n + 1) + recs["extra_sum"]

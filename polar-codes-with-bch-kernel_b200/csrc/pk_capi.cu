@@ -1,0 +1,507 @@
+// pk_capi.cu -- the C ABI (include/pk_capi.h) over the sm_100a kernels.
+// No CPU fallback lives here: every compute entry point launches CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pk_capi.h"
+#include "pk_code.h"
+#include "pk_kernels.h"
+
+unsigned long long g_pk_launches = 0;
+
+namespace {
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define PK_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(PK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+template <class Tp>
+int upload(pk_code *c, const std::vector<Tp> &h, const Tp **dptr) {
+    *dptr = nullptr;
+    if (h.empty()) return PK_OK;
+    void *d = nullptr;
+    PK_CUDA(cudaMalloc(&d, h.size() * sizeof(Tp)));
+    c->dev_allocs.push_back(d);
+    PK_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+    *dptr = static_cast<const Tp *>(d);
+    return PK_OK;
+}
+}  // namespace
+
+struct pk_kaneko {
+    pk_code *code = nullptr;
+    PkKanekoParams kp{};
+    PkLaunchGeom geom{};
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    unsigned long long *d_queue = nullptr;    // [4]
+    unsigned long long *d_totals = nullptr;   // [8]
+    unsigned long long *h_totals = nullptr;   // pinned [8]
+    // host-batch pipeline, one set per stream
+    long chunk = 0;
+    double *d_y[2] = {nullptr, nullptr};
+    uint8_t *d_dec[2] = {nullptr, nullptr};
+    uint32_t *d_tr[2] = {nullptr, nullptr};
+    pk_frame_rec *d_rec[2] = {nullptr, nullptr};
+    // generation-mode scratch (run_point)
+    pk_frame_rec *d_grec = nullptr;
+    pk_frame_rec *h_grec = nullptr;
+    long grec_cap = 0;
+};
+
+extern "C" {
+
+const char *pk_last_error(void) { return g_err.c_str(); }
+
+int pk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+uint64_t pk_launch_count(void) { return g_pk_launches; }
+void pk_launch_count_reset(void) { g_pk_launches = 0; }
+
+// ------------------------------------------------------------------ code
+int pk_code_create(int m, int t, int device, pk_code **out) {
+    if (!out) return fail(PK_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    pk_code *c = new (std::nothrow) pk_code;
+    if (!c) return fail(PK_ERR_ALLOC, "out of memory");
+    std::string msg = pk_code_build_host(*c, m, t);
+    if (!msg.empty()) {
+        delete c;
+        return fail(PK_ERR_ARG, msg);
+    }
+    c->device = device;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        delete c;
+        return fail(PK_ERR_CUDA, "no CUDA device: libpkb200 has no CPU path");
+    }
+    if (device < 0 || device >= ndev) {
+        delete c;
+        return fail(PK_ERR_ARG, "bad device ordinal");
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(PK_ERR_CUDA, cudaGetErrorString(e));
+    }
+    int rc;
+    if ((rc = upload(c, c->mul, &c->dev.mul)) || (rc = upload(c, c->xoff, &c->dev.xoff)) ||
+        (rc = upload(c, c->hcol, &c->dev.hcol)) || (rc = upload(c, c->rcol, &c->dev.rcol)) ||
+        (rc = upload(c, c->lut, &c->dev.lut)) || (rc = upload(c, c->gmask, &c->dev.gmask))) {
+        pk_code_destroy(c);
+        return rc;
+    }
+    c->dev.k = c->k;
+    c->dev.nk = c->nk;
+    *out = c;
+    return PK_OK;
+}
+
+// Host tables only (device = -1): lets CPU-only tooling and tests inspect g(x), the field
+// tables, the kernel matrix and the coset table.  Every compute call on such a handle fails.
+int pk_code_create_host(int m, int t, pk_code **out) {
+    if (!out) return fail(PK_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    pk_code *c = new (std::nothrow) pk_code;
+    if (!c) return fail(PK_ERR_ALLOC, "out of memory");
+    std::string msg = pk_code_build_host(*c, m, t);
+    if (!msg.empty()) {
+        delete c;
+        return fail(PK_ERR_ARG, msg);
+    }
+    c->device = -1;
+    *out = c;
+    return PK_OK;
+}
+
+void pk_code_destroy(pk_code *c) {
+    if (!c) return;
+    if (c->device >= 0) {
+        cudaSetDevice(c->device);
+        for (void *p : c->dev_allocs) cudaFree(p);
+    }
+    delete c;
+}
+
+int pk_code_coset_table(const pk_code *c, uint16_t *out, long *nentries) {
+    if (!c) return fail(PK_ERR_ARG, "code is NULL");
+    if (nentries) *nentries = (long)c->lut.size();
+    if (out && !c->lut.empty()) std::memcpy(out, c->lut.data(), c->lut.size() * sizeof(uint16_t));
+    return PK_OK;
+}
+
+int pk_code_info(const pk_code *c, int *n, int *k, int *d, int *gsize, uint8_t *g_out) {
+    if (!c) return fail(PK_ERR_ARG, "code is NULL");
+    if (n) *n = c->n;
+    if (k) *k = c->k;
+    if (d) *d = 2 * c->t + 1;   // main.cpp:94
+    if (gsize) *gsize = c->gsize;
+    if (g_out) std::memcpy(g_out, c->g.data(), c->g.size());
+    return PK_OK;
+}
+
+int pk_code_tables(const pk_code *c, uint64_t *antilog_out, uint64_t *log_out) {
+    if (!c) return fail(PK_ERR_ARG, "code is NULL");
+    if (antilog_out)
+        for (int i = 0; i < c->n; ++i) antilog_out[i] = c->alog[i];
+    if (log_out) {
+        log_out[0] = (uint64_t)LONG_MAX;   // main.cpp:68
+        for (int i = 1; i <= c->n; ++i) log_out[i] = c->log[i];
+    }
+    return PK_OK;
+}
+
+int pk_code_uses_lut(const pk_code *c) { return c && c->use_lut ? 1 : 0; }
+
+int pk_code_set_lut(pk_code *c, int enable) {
+    if (!c) return fail(PK_ERR_ARG, "code is NULL");
+    if (enable && c->lut.empty()) return fail(PK_ERR_UNSUPPORTED, "no coset table for this code (needs n-k <= 16, t*m <= 15)");
+    c->use_lut = enable != 0;
+    return PK_OK;
+}
+
+int pk_make_kernel_matrix(const pk_code *c, uint8_t *out) {
+    if (!c || !out) return fail(PK_ERR_ARG, "NULL argument");
+    pk_code_kernel_matrix(*c, out);
+    return PK_OK;
+}
+
+static int need_kernels(const pk_code *c) {
+    if (!c) return fail(PK_ERR_ARG, "code is NULL");
+    if (c->device < 0) return fail(PK_ERR_CUDA, "host-only code handle: libpkb200 has no CPU compute path");
+    if (!c->ks)
+        return fail(PK_ERR_UNSUPPORTED, "no sm_100a kernel instantiated for (m=" + std::to_string(c->m) +
+                                            ", t=" + std::to_string(c->t) + "); see csrc/pk_inst_m*.cu");
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------ encoder / algebraic decoder
+int pk_encode_batch(pk_code *c, const uint8_t *info, long B, uint8_t *cw) {
+    int rc = need_kernels(c);
+    if (rc) return rc;
+    if (B < 0 || (B && (!info || !cw))) return fail(PK_ERR_ARG, "bad buffers");
+    if (!B) return PK_OK;
+    PK_CUDA(cudaSetDevice(c->device));
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    PK_CUDA(cudaMalloc(&d_in, (size_t)B * c->k));
+    cudaError_t e = cudaMalloc(&d_out, (size_t)B * c->n);
+    if (e != cudaSuccess) { cudaFree(d_in); return fail(PK_ERR_CUDA, cudaGetErrorString(e)); }
+    e = cudaMemcpy(d_in, info, (size_t)B * c->k, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = c->ks->launch_encode(c->dev, d_in, B, d_out, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(cw, d_out, (size_t)B * c->n, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(PK_ERR_CUDA, cudaGetErrorString(e));
+    return PK_OK;
+}
+
+int pk_bch_decode_batch(pk_code *c, const uint8_t *words, long B, uint8_t *answers, uint8_t *ok) {
+    int rc = need_kernels(c);
+    if (rc) return rc;
+    if (B < 0 || (B && (!words || !answers || !ok))) return fail(PK_ERR_ARG, "bad buffers");
+    if (!B) return PK_OK;
+    PK_CUDA(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    PK_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    PkLaunchGeom g;
+    PK_CUDA(c->ks->geom_bdd(prop.multiProcessorCount, &g));
+    uint8_t *d_w = nullptr, *d_a = nullptr, *d_ok = nullptr;
+    PK_CUDA(cudaMalloc(&d_w, (size_t)B * c->n));
+    cudaError_t e = cudaMalloc(&d_a, (size_t)B * c->n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_ok, (size_t)B);
+    if (e == cudaSuccess) e = cudaMemcpy(d_w, words, (size_t)B * c->n, cudaMemcpyHostToDevice);
+    // rows of failed words keep the caller's bytes, like Decoder::decode (Decoder.cpp:300-307)
+    if (e == cudaSuccess) e = cudaMemcpy(d_a, answers, (size_t)B * c->n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = c->ks->launch_bdd(g, c->dev, d_w, B, d_a, d_ok, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(answers, d_a, (size_t)B * c->n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ok, d_ok, (size_t)B, cudaMemcpyDeviceToHost);
+    cudaFree(d_w);
+    cudaFree(d_a);
+    cudaFree(d_ok);
+    if (e != cudaSuccess) return fail(PK_ERR_CUDA, cudaGetErrorString(e));
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------ Kaneko handle
+int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_kaneko **out) {
+    if (!out) return fail(PK_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int rc = need_kernels(c);
+    if (rc) return rc;
+    if (llr_snr_db < 0) return fail(PK_ERR_ARG, "Invalid values of arguments");   // main.cpp:55
+    PK_CUDA(cudaSetDevice(c->device));
+    pk_kaneko *d = new (std::nothrow) pk_kaneko;
+    if (!d) return fail(PK_ERR_ALLOC, "out of memory");
+    d->code = c;
+    {   // sd = sqrt(1 / (pow(10, snr/10) * 2 * k / n)); alpha = 2*y / pow(sd, 2)
+        // (KanekoKernelProcessor.cpp:20,337) -- same expression, same operand types.
+        long k = c->k, n = c->n;
+        double sd = sqrt(1 / (pow(10, llr_snr_db / 10) * 2 * k / n));
+        d->kp.llr_den = pow(sd, 2);
+    }
+    d->kp.J = (J < 0 || J >= c->n) ? -1 : (int)J;
+    d->kp.max_trials = (max_trials <= 0 || max_trials > 0x7FFFFFFFL) ? 0x7FFFFFFFu : (uint32_t)max_trials;
+    d->kp.frames_per_grab = 2;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, c->device);
+    if (e == cudaSuccess) e = c->ks->geom_kaneko(c->use_lut, c->nk, prop.multiProcessorCount, &d->geom);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream[0], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream[1], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_queue, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_totals, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&d->h_totals, 8 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        pk_kaneko_destroy(d);
+        return fail(PK_ERR_CUDA, std::string("pk_kaneko_create: ") + cudaGetErrorString(e));
+    }
+    *out = d;
+    return PK_OK;
+}
+
+void pk_kaneko_destroy(pk_kaneko *d) {
+    if (!d) return;
+    cudaSetDevice(d->code->device);
+    for (int s = 0; s < 2; ++s) {
+        if (d->stream[s]) { cudaStreamSynchronize(d->stream[s]); cudaStreamDestroy(d->stream[s]); }
+        cudaFree(d->d_y[s]); cudaFree(d->d_dec[s]); cudaFree(d->d_tr[s]); cudaFree(d->d_rec[s]);
+    }
+    cudaFree(d->d_queue);
+    cudaFree(d->d_totals);
+    cudaFree(d->d_grec);
+    if (d->h_totals) cudaFreeHost(d->h_totals);
+    if (d->h_grec) cudaFreeHost(d->h_grec);
+    delete d;
+}
+
+int pk_kaneko_set_frames_per_grab(pk_kaneko *d, int g) {
+    if (!d || g < 1) return fail(PK_ERR_ARG, "bad argument");
+    d->kp.frames_per_grab = g;
+    return PK_OK;
+}
+
+int pk_kaneko_launch_geometry(const pk_kaneko *d, int *grid, int *block, long *smem) {
+    if (!d) return fail(PK_ERR_ARG, "NULL");
+    if (grid) *grid = d->geom.grid;
+    if (block) *block = d->geom.block;
+    if (smem) *smem = (long)d->geom.smem;
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------ replay mode
+int pk_kaneko_decode_batch_dev(pk_kaneko *d, const double *d_y, long B, uint8_t *d_decided, uint32_t *d_trials,
+                               pk_frame_rec *d_recs, uint64_t *d_totals, void *stream) {
+    if (!d || B < 0 || (B && (!d_y || !d_decided))) return fail(PK_ERR_ARG, "bad arguments");
+    if (!B) return PK_OK;
+    PK_CUDA(cudaSetDevice(d->code->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream[0];
+    PK_CUDA(d->code->ks->launch_replay(d->code->use_lut, d->geom, d->code->dev, d->kp, d_y, B, d_decided, d_trials,
+                                       d_recs, (unsigned long long *)d_totals, (unsigned int *)d->d_queue, st));
+    return PK_OK;
+}
+
+static int ensure_pipeline(pk_kaneko *d) {
+    if (d->chunk) return PK_OK;
+    const int n = d->code->n;
+    long chunk = (32L << 20) / (8L * n);
+    chunk = std::max(1024L, chunk / 1024 * 1024);
+    for (int s = 0; s < 2; ++s) {
+        PK_CUDA(cudaMalloc(&d->d_y[s], (size_t)chunk * n * sizeof(double)));
+        PK_CUDA(cudaMalloc(&d->d_dec[s], (size_t)chunk * n));
+        PK_CUDA(cudaMalloc(&d->d_tr[s], (size_t)chunk * sizeof(uint32_t)));
+        PK_CUDA(cudaMalloc(&d->d_rec[s], (size_t)chunk * sizeof(pk_frame_rec)));
+    }
+    d->chunk = chunk;
+    return PK_OK;
+}
+
+int pk_kaneko_decode_batch(pk_kaneko *d, const double *y, long B, uint8_t *decided, uint32_t *trials,
+                           pk_frame_rec *recs, pk_point_result *totals) {
+    if (!d || B < 0 || (B && (!y || !decided))) return fail(PK_ERR_ARG, "bad arguments");
+    if (totals) std::memset(totals, 0, sizeof(*totals));
+    if (!B) return PK_OK;
+    PK_CUDA(cudaSetDevice(d->code->device));
+    int rc = ensure_pipeline(d);
+    if (rc) return rc;
+    const int n = d->code->n;
+    PK_CUDA(cudaMemsetAsync(d->d_totals, 0, 8 * sizeof(unsigned long long), d->stream[0]));
+    PK_CUDA(cudaStreamSynchronize(d->stream[0]));
+    // chunked, double-buffered: H2D(y) -> kernel -> D2H(results) on alternating streams
+    int s = 0;
+    for (long off = 0; off < B; off += d->chunk, s ^= 1) {
+        const long nb = std::min(d->chunk, B - off);
+        cudaStream_t st = d->stream[s];
+        PK_CUDA(cudaMemcpyAsync(d->d_y[s], y + off * n, (size_t)nb * n * sizeof(double), cudaMemcpyHostToDevice, st));
+        // undecided rows (PK_FLAG_NO_DECISION) come back zero-filled
+        PK_CUDA(cudaMemsetAsync(d->d_dec[s], 0, (size_t)nb * n, st));
+        PK_CUDA(d->code->ks->launch_replay(d->code->use_lut, d->geom, d->code->dev, d->kp, d->d_y[s], nb, d->d_dec[s],
+                                           trials ? d->d_tr[s] : nullptr, recs ? d->d_rec[s] : nullptr, d->d_totals,
+                                           (unsigned int *)(d->d_queue + s), st));
+        PK_CUDA(cudaMemcpyAsync(decided + off * n, d->d_dec[s], (size_t)nb * n, cudaMemcpyDeviceToHost, st));
+        if (trials)
+            PK_CUDA(cudaMemcpyAsync(trials + off, d->d_tr[s], (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (recs)
+            PK_CUDA(cudaMemcpyAsync(recs + off, d->d_rec[s], (size_t)nb * sizeof(pk_frame_rec), cudaMemcpyDeviceToHost, st));
+    }
+    PK_CUDA(cudaStreamSynchronize(d->stream[0]));
+    PK_CUDA(cudaStreamSynchronize(d->stream[1]));
+    if (totals) {
+        PK_CUDA(cudaMemcpy(d->h_totals, d->d_totals, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        std::memcpy(totals, d->h_totals, sizeof(*totals));
+    }
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------ generation mode
+static double channel_sigma(const pk_code *c, double ebn0_db) {
+    long k = c->k, n = c->n;
+    return sqrt(1 / (pow(10, ebn0_db / 10) * 2 * k / n));   // dataForPlot.cpp:45
+}
+
+int pk_kaneko_run_frames_dev(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame,
+                             long nframes, pk_frame_rec *d_recs, uint64_t *d_totals, void *stream) {
+    if (!d || nframes < 0) return fail(PK_ERR_ARG, "bad arguments");
+    if (!nframes) return PK_OK;
+    PK_CUDA(cudaSetDevice(d->code->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream[0];
+    PkGenParams gp;
+    gp.sigma = channel_sigma(d->code, ebn0_db);
+    gp.seed = seed;
+    gp.first_frame = first_frame;
+    gp.snr_index = (uint32_t)snr_index;
+    PK_CUDA(d->code->ks->launch_generate(d->code->use_lut, d->geom, d->code->dev, d->kp, gp, nframes, d_recs,
+                                         (unsigned long long *)d_totals, (unsigned int *)d->d_queue, nullptr, nullptr,
+                                         nullptr, 0, st));
+    return PK_OK;
+}
+
+static int ensure_grec(pk_kaneko *d, long cap) {
+    if (cap <= d->grec_cap) return PK_OK;
+    cudaFree(d->d_grec);
+    if (d->h_grec) cudaFreeHost(d->h_grec);
+    d->d_grec = nullptr; d->h_grec = nullptr; d->grec_cap = 0;
+    PK_CUDA(cudaMalloc(&d->d_grec, (size_t)cap * sizeof(pk_frame_rec)));
+    PK_CUDA(cudaMallocHost(&d->h_grec, (size_t)cap * sizeof(pk_frame_rec)));
+    d->grec_cap = cap;
+    return PK_OK;
+}
+
+int pk_kaneko_run_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame,
+                         long nframes, pk_frame_rec *recs, pk_point_result *totals) {
+    if (!d || nframes < 0 || !totals) return fail(PK_ERR_ARG, "bad arguments");
+    if (!nframes) return PK_OK;
+    PK_CUDA(cudaSetDevice(d->code->device));
+    cudaStream_t st = d->stream[0];
+    const long step = recs ? (1L << 20) : nframes;
+    if (recs) {
+        int rc = ensure_grec(d, std::min(step, nframes));
+        if (rc) return rc;
+    }
+    PK_CUDA(cudaMemsetAsync(d->d_totals, 0, 8 * sizeof(unsigned long long), st));
+    for (long off = 0; off < nframes; off += step) {
+        const long nb = std::min(step, nframes - off);
+        int rc = pk_kaneko_run_frames_dev(d, ebn0_db, snr_index, seed, first_frame + (uint64_t)off, nb,
+                                          recs ? d->d_grec : nullptr, (uint64_t *)d->d_totals, st);
+        if (rc) return rc;
+        if (recs) {
+            PK_CUDA(cudaMemcpyAsync(d->h_grec, d->d_grec, (size_t)nb * sizeof(pk_frame_rec), cudaMemcpyDeviceToHost, st));
+            PK_CUDA(cudaStreamSynchronize(st));
+            std::memcpy(recs + off, d->h_grec, (size_t)nb * sizeof(pk_frame_rec));
+        }
+    }
+    PK_CUDA(cudaMemcpyAsync(d->h_totals, d->d_totals, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    PK_CUDA(cudaStreamSynchronize(st));
+    uint64_t *t = reinterpret_cast<uint64_t *>(totals);
+    for (int i = 0; i < 6; ++i) t[i] += d->h_totals[i];
+    t[6] = std::max<uint64_t>(t[6], d->h_totals[6]);
+    t[7] |= d->h_totals[7];
+    return PK_OK;
+}
+
+int pk_generate_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
+                       uint8_t *info, uint8_t *cw, double *y) {
+    if (!d || nframes < 0) return fail(PK_ERR_ARG, "bad arguments");
+    if (!nframes) return PK_OK;
+    const pk_code *c = d->code;
+    PK_CUDA(cudaSetDevice(c->device));
+    uint8_t *d_info = nullptr, *d_cw = nullptr;
+    double *d_y = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (info) e = cudaMalloc(&d_info, (size_t)nframes * c->k);
+    if (e == cudaSuccess && cw) e = cudaMalloc(&d_cw, (size_t)nframes * c->n);
+    if (e == cudaSuccess && y) e = cudaMalloc(&d_y, (size_t)nframes * c->n * sizeof(double));
+    if (e == cudaSuccess) {
+        PkGenParams gp;
+        gp.sigma = channel_sigma(c, ebn0_db);
+        gp.seed = seed;
+        gp.first_frame = first_frame;
+        gp.snr_index = (uint32_t)snr_index;
+        e = c->ks->launch_generate(c->use_lut, d->geom, c->dev, d->kp, gp, nframes, nullptr, nullptr,
+                                   (unsigned int *)d->d_queue, d_info, d_cw, d_y, 1, d->stream[0]);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream[0]);
+    if (e == cudaSuccess && info) e = cudaMemcpy(info, d_info, (size_t)nframes * c->k, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && cw) e = cudaMemcpy(cw, d_cw, (size_t)nframes * c->n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && y) e = cudaMemcpy(y, d_y, (size_t)nframes * c->n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_info);
+    cudaFree(d_cw);
+    cudaFree(d_y);
+    if (e != cudaSuccess) return fail(PK_ERR_CUDA, cudaGetErrorString(e));
+    return PK_OK;
+}
+
+// One SNR point with fun()'s stop rule (dataForPlot.cpp:43): frames are decoded in growing
+// chunks; the per-frame records are then scanned IN FRAME ORDER and the scan stops at the
+// frame where `count < p && countErr < e` first fails, so the totals equal a sequential run.
+int pk_kaneko_run_point(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t seed, long p, long e,
+                        pk_point_result *out) {
+    if (!d || !out || p <= 0) return fail(PK_ERR_ARG, "Invalid values of arguments");
+    std::memset(out, 0, sizeof(*out));
+    if (e <= 0) return pk_kaneko_run_frames(d, ebn0_db, snr_index, seed, 0, p, nullptr, out);
+    const int n = d->code->n;
+    long done = 0, chunk = 4096;
+    std::vector<pk_frame_rec> recs;
+    while (done < p && (long)out->frame_errors < e) {
+        const long nb = std::min(chunk, p - done);
+        recs.resize((size_t)nb);
+        pk_point_result scratch;
+        std::memset(&scratch, 0, sizeof scratch);
+        int rc = pk_kaneko_run_frames(d, ebn0_db, snr_index, seed, (uint64_t)done, nb, recs.data(), &scratch);
+        if (rc) return rc;
+        for (long f = 0; f < nb && (long)out->frame_errors < e; ++f) {
+            const pk_frame_rec &r = recs[(size_t)f];
+            const uint64_t run = (uint64_t)r.trials - ((r.flags & PK_FLAG_EARLY_RETURN) ? 1 : 0);
+            out->frames += 1;
+            out->frame_errors += (r.flags & PK_FLAG_FRAME_ERROR) ? 1 : 0;
+            out->bit_errors += r.bit_errors;
+            out->trials += r.trials;
+            out->cmp += run * (uint64_t)(n + 6) + r.extra_cmp;
+            out->sum += run * (uint64_t)(n + 1) + r.extra_sum;
+            out->max_trials_seen = std::max<uint64_t>(out->max_trials_seen, r.trials);
+            out->flags_or |= r.flags;
+        }
+        done += nb;
+        chunk = std::min(chunk * 2, 1L << 20);
+    }
+    return PK_OK;
+}
+
+}  // extern "C"
