@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- decoded frames/s of the Kaneko/BCH hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): BCH(31,16,7) with the HEAD (uncapped) test-pattern rule
+and BCH(63,30,13) with the J=15 cap, every Eb/N0 point of the reference grid 0..5 dB step 0.5,
+the same number of frames per point and code.  One "step" = one pass of the decoder over that
+whole batch (2 codes x 11 points = 22 kernel launches).  Inputs are channel outputs y (f64)
+drawn once by the device-side Philox generator.
+
+  value  : frames/s with y resident in HBM, timed with CUDA events on the launching stream
+  e2e    : frames/s through pk_kaneko_decode_batch (the C-ABI call a reference-side binding
+           makes) with pinned HOST buffers: H2D of y and D2H of decisions + trial counts inside
+           the timed region
+  --impl reference : the compiled reference (oracle/_ref) on all host cores, same codes/grid
+
+Multi-GPU: frames are independent, so each rank decodes its own frames (weak scaling); the
+only collective is one all-reduce of the per-point counters (what the sweep driver does per
+SNR point), plus the max-over-ranks of the timings.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CODES = [  # (m, t, J, label)
+    (5, 3, -1, "BCH(31,16,7) uncapped"),
+    (6, 6, 15, "BCH(63,30,13) J=15"),
+]
+SNRS = [0.5 * i for i in range(11)]
+METRIC = "decoded frames/s (BCH(31,16,7) uncapped + BCH(63,30,13) J=15, Eb/N0 grid 0..5 dB)"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-point", type=int, default=1 << 14, help="frames per (code, SNR point) per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=12, help="frames per (code, point) for the single-core CPU baseline")
+    ap.add_argument("--ref-frames", type=int, default=3, help="--impl reference: frames per (code, point) per process per step")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--detail", action="store_true", help="print per-code / per-SNR numbers to stderr")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def _ref_worker(args):
+    """One process: the compiled reference decodes its own frames (reference RNG, own seed)."""
+    widx, nframes, steps = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+
+    out = []
+    refs = []
+    for (m, t, J, _) in CODES:
+        r = oracle_py.Reference(m, t, J)
+        r.seed(1000 + widx)
+        refs.append(r)
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        trials = 0
+        for r in refs:
+            for s in SNRS:
+                _, cw, y = r.gen_frames(s, nframes)
+                _, tr, _, _ = r.kaneko_decode(y, answer=cw)
+                trials += int(tr.sum())
+        out.append((time.perf_counter() - t0, trials))
+    return out
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+
+    if not (oracle_py.ref_available(False) and oracle_py.ref_available(True)):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return 0
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nf = a.ref_frames
+    total_steps = a.warmup + a.steps
+    with mp.get_context("spawn").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_ref_worker, [(w, nf, total_steps) for w in range(cores)])
+        wall = time.perf_counter() - t0
+    # per step: all processes run concurrently; step time = the slowest process
+    step_t = [max(res[w][s][0] for w in range(cores)) for s in range(total_steps)][a.warmup:]
+    trials = sum(res[w][s][1] for w in range(cores) for s in range(a.warmup, total_steps))
+    frames_per_step = cores * nf * len(SNRS) * len(CODES)
+    tsum = float(sum(step_t))
+    value = frames_per_step * a.steps / tsum
+    sample = f"{nf} frames x {len(SNRS)} SNR points x {len(CODES)} codes per process per step, {cores} processes (reference RNG, distinct seeds)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * tsum / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8 GF(2^m) + f64 metrics", "data": "synthetic (reference generator: minstd_rand0 AWGN)",
+        "config": {"workload": "BASELINE configs[1]: BCH(31,16,7) uncapped + BCH(63,30,13) J=15 (patched cap), Eb/N0 0..5 dB step 0.5, equal frames per point and code",
+                   "frames_per_point_per_process": nf, "processes": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "trials_per_s": trials / tsum, "wall_s": wall,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    import pkb200
+    pk = pkb200.pk
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = a.frames_per_point
+    # a real (non-default) stream: its handle goes through the C ABI, and every torch op and
+    # CUDA event below is issued on the same stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+    assert sp != 0
+
+    # ---- handles + device-resident inputs (drawn once by the Philox generator)
+    codes, kans, ys, decs, trs, tots = [], [], [], [], [], []
+    for (m, t, J, _) in CODES:
+        c = pk.Code(m, t, device=local)
+        k = pk.Kaneko(c, J=J)
+        codes.append(c); kans.append(k)
+        y = torch.empty((len(SNRS), B, c.n), dtype=torch.float64, device=dev)
+        for si, s in enumerate(SNRS):
+            k.generate_frames_dev(s, si, a.seed, rank * B, B, y[si].data_ptr(), stream=sp)
+        ys.append(y)
+        decs.append(torch.zeros((len(SNRS), B, c.n), dtype=torch.uint8, device=dev))
+        trs.append(torch.zeros((len(SNRS), B), dtype=torch.int32, device=dev))
+        tots.append(torch.zeros((len(SNRS), 8), dtype=torch.int64, device=dev))
+    torch.cuda.synchronize()
+
+    def device_step(events=None):
+        for ci, k in enumerate(kans):
+            for si in range(len(SNRS)):
+                if events is not None:
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                k.decode_dev(ys[ci][si].data_ptr(), B, decs[ci][si].data_ptr(), trs[ci][si].data_ptr(), None,
+                             tots[ci][si].data_ptr(), sp)
+                if events is not None:
+                    e1.record(stream)
+                    events.append((ci, si, e0, e1))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then K timed steps (CUDA events on the launching stream)
+    for _ in range(a.warmup):
+        device_step()
+    for tt in tots:
+        tt.zero_()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    pk.launch_count_reset()
+    events = []
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(a.steps):
+        device_step(events)
+    ev1.record(stream)
+    barrier()
+    launches = pk.launch_count()
+    dev_ms = ev0.elapsed_time(ev1)
+    per_launch = {}
+    for ci, si, e0, e1 in events:
+        per_launch.setdefault((ci, si), []).append(e0.elapsed_time(e1))
+
+    # ---- the one collective of the path: per-point counters summed over ranks
+    tot_all = torch.stack(tots).clone()
+    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_all[..., :6], op=dist.ReduceOp.SUM)
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    dev_ms = float(t_ms.item())
+    frames_per_step = world * B * len(SNRS) * len(CODES)
+    value = frames_per_step * a.steps / (dev_ms * 1e-3)
+    tot_np = tot_all.cpu().numpy()
+    trials_total = int(tot_np[..., 3].sum())
+
+    # ---- end to end through the C ABI with pinned host buffers
+    h_y = [y.cpu().pin_memory() for y in ys]
+    h_dec = [torch.zeros(d.shape, dtype=torch.uint8).pin_memory() for d in decs]
+    h_tr = [torch.zeros(t_.shape, dtype=torch.int32).pin_memory() for t_ in trs]
+
+    def e2e_step():
+        for ci, k in enumerate(kans):
+            for si in range(len(SNRS)):
+                k.decode_ptr(h_y[ci][si].data_ptr(), B, h_dec[ci][si].data_ptr(), h_tr[ci][si].data_ptr())
+
+    e2e_step()  # allocates the pipeline workspaces
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = frames_per_step * a.steps / e2e_s
+    h2d = sum(B * len(SNRS) * c.n * 8 for c in codes)
+    d2h = sum(B * len(SNRS) * (c.n + 4) for c in codes)
+    # same answers both ways
+    for ci in range(len(CODES)):
+        assert torch.equal(h_dec[ci], decs[ci].cpu()) and torch.equal(h_tr[ci], trs[ci].cpu()), "e2e != device-resident results"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (largest share of the step)
+    share = {key: float(np.mean(v)) for key, v in per_launch.items()}
+    step_ms = sum(share.values())
+    by_code = [sum(v for (ci, _), v in share.items() if ci == c) for c in range(len(CODES))]
+    dom = int(np.argmax(by_code))
+    dom_code = codes[dom]
+    dom_ms = by_code[dom] / len(SNRS)   # average launch duration of that kernel
+    bytes_per_frame = 9 * dom_code.n + 4   # 8n in + n out + 4 (trial count)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_per_frame * B / (dom_ms * 1e-3) / 1e9
+    dom_trials = int(tot_np[dom, :, 3].sum()) // max(1, world)
+    kname = f"k_replay<{dom_code.m},{dom_code.t},{'LUT' if dom_code.uses_lut else 'BM+Chien'}>"
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+        "kernel": kname, "avg_launch_ms": dom_ms, "share_of_step": by_code[dom] / step_ms,
+        "note": "search kernel: neither HBM- nor tensor-bound (SURVEY 8d); the binding roofs are warp-instruction issue and the shared-memory LSU -- see issue_slot",
+        "issue_slot": {
+            "trials_per_s": dom_trials / (by_code[dom] * a.steps * 1e-3),
+            "algorithmic_gf_macs_per_trial": 2 * dom_code.t * 2 + 2 * dom_code.t ** 2 + dom_code.n * dom_code.t,
+            "peak_warp_inst_per_s": 148 * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6,
+            "warp_inst_per_trial": None,   # filled from profiles/*.md (ncu sm__inst_executed / trials)
+        },
+    }
+
+    # ---- single-core CPU baseline on a bounded sample of the same inputs (+ parity check)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+
+    cpu = None
+    nb = min(a.cpu_sample, B)
+    if nb > 0:
+        kind = "reference" if (oracle_py.ref_available(False) and oracle_py.ref_available(True)) else "port"
+        t_cpu, n_cpu, tr_cpu = 0.0, 0, 0
+        for ci, (m, t, J, _) in enumerate(CODES):
+            eng = oracle_py.Reference(m, t, J) if kind == "reference" else oracle_py.Oracle(m, t, J)
+            for si in range(len(SNRS)):
+                ysample = h_y[ci][si, :nb].numpy()
+                t0 = time.perf_counter()
+                d_cpu, tr, _, _ = eng.kaneko_decode(ysample)
+                t_cpu += time.perf_counter() - t0
+                n_cpu += nb
+                tr_cpu += int(tr.sum())
+                assert np.array_equal(d_cpu, h_dec[ci][si, :nb].numpy()), "GPU decisions differ from the CPU reference"
+                assert np.array_equal(tr.astype(np.int32), h_tr[ci][si, :nb].numpy()), "GPU trial counts differ"
+        cpu = {"value": n_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"first {nb} frames of every (code, SNR point) of this run's inputs ({n_cpu} frames, {t_cpu:.1f} s); decisions and trial counts checked equal to the GPU's",
+               "trials_per_s": tr_cpu / t_cpu}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 GF(2^m) + f64 metrics", "data": "synthetic (Philox4x32-10 info bits + AWGN drawn on the device)",
+        "config": {"workload": "BASELINE configs[1]: BCH(31,16,7) uncapped + BCH(63,30,13) J=15, Eb/N0 0..5 dB step 0.5 (11 points), replay mode",
+                   "frames_per_point_per_gpu": B, "frames_per_step": frames_per_step,
+                   "l2_policy": f"inputs larger than L2: {h2d / 1e6:.0f} MB of y per step per GPU, every launch reads a distinct buffer"},
+        "info_mbit_per_s": sum((B * len(SNRS) * world * c.k) for c in codes) * a.steps / (dev_ms * 1e-3) / 1e6,
+        "trials_per_s": trials_total / (dev_ms * 1e-3),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "pk_kaneko_decode_batch (pinned host y -> host decisions + trial counts)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "per_code_ms_per_step": {CODES[c][3]: by_code[c] for c in range(len(CODES))},
+    }
+    if a.detail:
+        for ci in range(len(CODES)):
+            for si, s in enumerate(SNRS):
+                ms = share[(ci, si)]
+                trp = int(tot_np[ci, si, 3]) / a.steps / max(1, world) / B
+                print(f"# {CODES[ci][3]:24s} {s:3.1f} dB  {ms:9.3f} ms/launch  {B / ms * 1e3:12.0f} frames/s  {trp:10.1f} trials/frame  {trp * B / ms * 1e3:14.0f} trials/s", file=sys.stderr)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    sys.exit(run_reference(args) if args.impl == "reference" else run_b200(args))

@@ -143,6 +143,10 @@ int pk_kaneko_run_frames(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t
 int pk_generate_frames(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame,
                        long nframes, uint8_t *info /*[B][k]*/, uint8_t *cw /*[B][n]*/, double *y /*[B][n]*/);
 
+/* Same, into device buffers (any may be NULL), asynchronous on `stream`. */
+int pk_generate_frames_dev(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame,
+                           long nframes, uint8_t *d_info, uint8_t *d_cw, double *d_y, void *stream);
+
 /* One whole SNR point with fun()'s stop rule `count < p && countErr < e`
  * (dataForPlot.cpp:43), evaluated in frame order on the per-frame records so the result
  * equals a sequential run over the same Philox frames.  Frames [rank, world) are

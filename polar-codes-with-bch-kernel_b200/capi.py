@@ -30,7 +30,7 @@ SYMBOLS = (
     "pk_last_error pk_device_count pk_code_create pk_code_create_host pk_code_destroy pk_code_info pk_code_tables "
     "pk_code_uses_lut pk_code_set_lut pk_code_coset_table pk_encode_batch pk_bch_decode_batch pk_kaneko_create "
     "pk_kaneko_destroy pk_kaneko_set_frames_per_grab pk_kaneko_launch_geometry pk_kaneko_decode_batch "
-    "pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames "
+    "pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames pk_generate_frames_dev "
     "pk_kaneko_run_point pk_make_kernel_matrix pk_launch_count pk_launch_count_reset"
 ).split()
 
@@ -74,6 +74,7 @@ def _load():
     lib.pk_kaneko_run_frames_dev.argtypes = [vp, d, i, u64, u64, l, vp, vp, vp]
     lib.pk_kaneko_run_frames.argtypes = [vp, d, i, u64, u64, l, vp, vp]
     lib.pk_generate_frames.argtypes = [vp, d, i, u64, u64, l, vp, vp, vp]
+    lib.pk_generate_frames_dev.argtypes = [vp, d, i, u64, u64, l, vp, vp, vp, vp]
     lib.pk_kaneko_run_point.argtypes = [vp, d, i, u64, l, l, vp]
     lib.pk_make_kernel_matrix.argtypes = [vp, vp]
     lib.pk_launch_count.restype = u64
@@ -119,7 +120,7 @@ class Code:
         self.g = g[: gs.value].copy()
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:  # lib is None during interpreter shutdown
             lib.pk_code_destroy(self.h)
             self.h = None
 
@@ -180,7 +181,7 @@ class Kaneko:
         self.J = J
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib.pk_kaneko_destroy(self.h)
             self.h = None
 
@@ -231,6 +232,9 @@ class Kaneko:
         y = np.zeros((nframes, self.code.n), np.float64)
         _check(lib.pk_generate_frames(self.h, float(ebn0_db), int(snr_index), int(seed), int(first_frame), int(nframes), _np_ptr(info), _np_ptr(cw), _np_ptr(y)))
         return info, cw, y
+
+    def generate_frames_dev(self, ebn0_db, snr_index, seed, first_frame, nframes, d_y, d_cw=None, d_info=None, stream=None):
+        _check(lib.pk_generate_frames_dev(self.h, float(ebn0_db), int(snr_index), int(seed), int(first_frame), int(nframes), d_info, d_cw, d_y, stream))
 
     def run_point(self, ebn0_db, snr_index, seed, p, e):
         tot = np.zeros(8, np.uint64)

@@ -46,7 +46,7 @@ int upload(pk_code *c, const std::vector<Tp> &h, const Tp **dptr) {
 struct pk_kaneko {
     pk_code *code = nullptr;
     PkKanekoParams kp{};
-    PkLaunchGeom geom{};
+    PkLaunchGeom geom2[2]{};   // [0] replay kernel, [1] generation kernel
     cudaStream_t stream[2] = {nullptr, nullptr};
     unsigned long long *d_queue = nullptr;    // [4]
     unsigned long long *d_totals = nullptr;   // [8]
@@ -263,7 +263,7 @@ int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_
     d->kp.frames_per_grab = 2;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, c->device);
-    if (e == cudaSuccess) e = c->ks->geom_kaneko(c->use_lut, c->nk, prop.multiProcessorCount, &d->geom);
+    if (e == cudaSuccess) e = c->ks->geom_kaneko(c->use_lut, c->nk, prop.multiProcessorCount, d->geom2);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream[0], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream[1], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&d->d_queue, 4 * sizeof(unsigned long long));
@@ -300,9 +300,9 @@ int pk_kaneko_set_frames_per_grab(pk_kaneko *d, int g) {
 
 int pk_kaneko_launch_geometry(const pk_kaneko *d, int *grid, int *block, long *smem) {
     if (!d) return fail(PK_ERR_ARG, "NULL");
-    if (grid) *grid = d->geom.grid;
-    if (block) *block = d->geom.block;
-    if (smem) *smem = (long)d->geom.smem;
+    if (grid) *grid = d->geom2[0].grid;
+    if (block) *block = d->geom2[0].block;
+    if (smem) *smem = (long)d->geom2[0].smem;
     return PK_OK;
 }
 
@@ -313,7 +313,7 @@ int pk_kaneko_decode_batch_dev(pk_kaneko *d, const double *d_y, long B, uint8_t 
     if (!B) return PK_OK;
     PK_CUDA(cudaSetDevice(d->code->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream[0];
-    PK_CUDA(d->code->ks->launch_replay(d->code->use_lut, d->geom, d->code->dev, d->kp, d_y, B, d_decided, d_trials,
+    PK_CUDA(d->code->ks->launch_replay(d->code->use_lut, d->geom2[0], d->code->dev, d->kp, d_y, B, d_decided, d_trials,
                                        d_recs, (unsigned long long *)d_totals, (unsigned int *)d->d_queue, st));
     return PK_OK;
 }
@@ -352,7 +352,7 @@ int pk_kaneko_decode_batch(pk_kaneko *d, const double *y, long B, uint8_t *decid
         PK_CUDA(cudaMemcpyAsync(d->d_y[s], y + off * n, (size_t)nb * n * sizeof(double), cudaMemcpyHostToDevice, st));
         // undecided rows (PK_FLAG_NO_DECISION) come back zero-filled
         PK_CUDA(cudaMemsetAsync(d->d_dec[s], 0, (size_t)nb * n, st));
-        PK_CUDA(d->code->ks->launch_replay(d->code->use_lut, d->geom, d->code->dev, d->kp, d->d_y[s], nb, d->d_dec[s],
+        PK_CUDA(d->code->ks->launch_replay(d->code->use_lut, d->geom2[0], d->code->dev, d->kp, d->d_y[s], nb, d->d_dec[s],
                                            trials ? d->d_tr[s] : nullptr, recs ? d->d_rec[s] : nullptr, d->d_totals,
                                            (unsigned int *)(d->d_queue + s), st));
         PK_CUDA(cudaMemcpyAsync(decided + off * n, d->d_dec[s], (size_t)nb * n, cudaMemcpyDeviceToHost, st));
@@ -387,7 +387,7 @@ int pk_kaneko_run_frames_dev(pk_kaneko *d, double ebn0_db, int snr_index, uint64
     gp.seed = seed;
     gp.first_frame = first_frame;
     gp.snr_index = (uint32_t)snr_index;
-    PK_CUDA(d->code->ks->launch_generate(d->code->use_lut, d->geom, d->code->dev, d->kp, gp, nframes, d_recs,
+    PK_CUDA(d->code->ks->launch_generate(d->code->use_lut, d->geom2[1], d->code->dev, d->kp, gp, nframes, d_recs,
                                          (unsigned long long *)d_totals, (unsigned int *)d->d_queue, nullptr, nullptr,
                                          nullptr, 0, st));
     return PK_OK;
@@ -436,6 +436,23 @@ int pk_kaneko_run_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t s
     return PK_OK;
 }
 
+int pk_generate_frames_dev(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame,
+                           long nframes, uint8_t *d_info, uint8_t *d_cw, double *d_y, void *stream) {
+    if (!d || nframes < 0) return fail(PK_ERR_ARG, "bad arguments");
+    if (!nframes) return PK_OK;
+    const pk_code *c = d->code;
+    PK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream[0];
+    PkGenParams gp;
+    gp.sigma = channel_sigma(c, ebn0_db);
+    gp.seed = seed;
+    gp.first_frame = first_frame;
+    gp.snr_index = (uint32_t)snr_index;
+    PK_CUDA(c->ks->launch_generate(c->use_lut, d->geom2[1], c->dev, d->kp, gp, nframes, nullptr, nullptr,
+                                   (unsigned int *)d->d_queue, d_info, d_cw, d_y, 1, st));
+    return PK_OK;
+}
+
 int pk_generate_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
                        uint8_t *info, uint8_t *cw, double *y) {
     if (!d || nframes < 0) return fail(PK_ERR_ARG, "bad arguments");
@@ -454,7 +471,7 @@ int pk_generate_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t see
         gp.seed = seed;
         gp.first_frame = first_frame;
         gp.snr_index = (uint32_t)snr_index;
-        e = c->ks->launch_generate(c->use_lut, d->geom, c->dev, d->kp, gp, nframes, nullptr, nullptr,
+        e = c->ks->launch_generate(c->use_lut, d->geom2[1], c->dev, d->kp, gp, nframes, nullptr, nullptr,
                                    (unsigned int *)d->d_queue, d_info, d_cw, d_y, 1, d->stream[0]);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream[0]);

@@ -707,11 +707,12 @@ struct PkLaunch {
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_generate<M, T, LUT>, PK_WARPS * 32, smem);
         if (e != cudaSuccess) return e;
-        int per_sm = per_sm_a < per_sm_b ? per_sm_a : per_sm_b;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        out->grid = sm_count * per_sm;    // persistent: every resident slot of every SM
-        out->block = PK_WARPS * 32;
-        out->smem = smem;
+        if (per_sm_a < 1 || per_sm_b < 1) return cudaErrorLaunchOutOfResources;
+        // persistent grids: every resident slot of every SM; out[0] = replay, out[1] = generate
+        out[0].grid = sm_count * per_sm_a;
+        out[1].grid = sm_count * per_sm_b;
+        out[0].block = out[1].block = PK_WARPS * 32;
+        out[0].smem = out[1].smem = smem;
         return cudaSuccess;
     }
     // coset-table kernels exist only where the u16 entry (t positions of m bits + flag) fits

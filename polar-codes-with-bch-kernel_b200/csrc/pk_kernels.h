@@ -33,7 +33,7 @@ struct PkKernelSet {
     // host instance of the algebraic decoder (coset-table construction)
     bool (*host_alg_decode)(const uint32_t *, const uint8_t *, const uint16_t *, uint32_t *);
     // geometry (queries the device once; sets the dynamic shared-memory attribute)
-    cudaError_t (*geom_kaneko)(bool lut, int nk, int sm_count, PkLaunchGeom *out);
+    cudaError_t (*geom_kaneko)(bool lut, int nk, int sm_count, PkLaunchGeom *out /*[2]: replay, generate*/);
     cudaError_t (*geom_bdd)(int sm_count, PkLaunchGeom *out);
     // Kaneko decode of B frames from y (replay mode).  queue: device u32 zeroed by the callee.
     cudaError_t (*launch_replay)(bool lut, const PkLaunchGeom &g, const PkDevTables &tb, const PkKanekoParams &kp,

@@ -1,0 +1,56 @@
+// kaneko_processor.hpp -- class KanekoKernelProcessor with the reference's public interface
+// (headers/KanekoKernelProcessor.h:47-68) on top of the C ABI.  Besides the per-word
+// decode() of the reference it exposes the batched entry points the Monte-Carlo driver uses.
+#pragma once
+#include <cstdint>
+
+#include "bch_decoder.hpp"
+#include "pk_capi.h"
+
+class KanekoKernelProcessor {
+public:
+    // J = cap on the test-pattern exponent (reference: compile-time constant 15 that HEAD ignores,
+    // KanekoKernelProcessor.h:35, .cpp:392-393); J < 0 keeps HEAD behaviour.
+    KanekoKernelProcessor(long pw, long n, long t, long k, unsigned long *antilogarithms, unsigned long *logarithms,
+                          double signalToNoiseRatio, long J = -1);
+    virtual ~KanekoKernelProcessor();
+    KanekoKernelProcessor(const KanekoKernelProcessor &) = delete;
+    KanekoKernelProcessor &operator=(const KanekoKernelProcessor &) = delete;
+
+    // decode(answer, word, res): the flavour fun() uses (KanekoKernelProcessor.cpp:335-407).
+    void decode(const unsigned char *answer, const double *word, unsigned char *res);
+    // The 2-argument (file mode, :212-276) and 1-argument (DEBUG, :161-210) flavours follow
+    // different -- in the DEBUG case undefined -- rules and have no device implementation yet:
+    // they throw instead of silently answering with other semantics.
+    void decode(const double *word, unsigned char *res);
+    void decode(unsigned char *res);
+    void set(const double *word) const;
+    double calcL(const unsigned char *word) const;   // :79-87, against the last word given to set()/decode()
+
+    long getN() const { return decoder.getN(); }
+    long getT() const { return decoder.getT(); }
+    long getK() const { return decoder.getK(); }
+    unsigned long getComparisonCount() const { return comparisonCount; }
+    unsigned long getSummCount() const { return summCount; }
+    unsigned long getDecodingCount() const { return decodingCount; }
+    void setDecodingCount(unsigned long c = 0) { decodingCount = c; }
+    void setComparisonCount(unsigned long c = 0) { comparisonCount = c; }
+    void setSummCount(unsigned long c = 0) { summCount = c; }
+
+    // ---- batched extensions (what the sm_100a path is for)
+    // replay: B frames of channel output -> decisions; counters accumulate like B decode() calls
+    void decodeBatch(const double *words, long B, unsigned char *res, uint32_t *trials = nullptr);
+    // generation mode: one SNR point with fun()'s stop rule, frames drawn on the device
+    pk_point_result runPoint(double ebn0_db, int snr_index, uint64_t seed, long p, long e);
+    pk_kaneko *handle() const { return kan_; }
+
+private:
+    Decoder decoder;
+    long n_, t_;
+    double sd;
+    pk_kaneko *kan_;
+    mutable double *alpha_;
+    mutable unsigned char *yH_;
+    unsigned long comparisonCount{0}, summCount{0}, decodingCount{0};
+    void account(const pk_point_result &r);
+};
