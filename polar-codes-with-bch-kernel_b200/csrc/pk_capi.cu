@@ -46,9 +46,13 @@ int upload(pk_code *c, const std::vector<Tp> &h, const Tp **dptr) {
 struct pk_kaneko {
     pk_code *code = nullptr;
     PkKanekoParams kp{};
-    PkLaunchGeom geom2[2]{};   // [0] replay kernel, [1] generation kernel
+    PkLaunchGeom geom4[4]{};   // replay phase A/B, generation phase A/B
     cudaStream_t stream[2] = {nullptr, nullptr};
-    unsigned long long *d_queue = nullptr;    // [4]
+    // one control block + parked-frame list per concurrent launch slot:
+    // slots 0/1 = the handle's two pipeline streams, slot 2 = caller-supplied streams
+    PkPhaseCtl *d_ctl = nullptr;              // [3]
+    PkLongRec *d_longs[3] = {nullptr, nullptr, nullptr};
+    long long_cap = 1L << 18;                 // frames per launch pair (and capacity of a list)
     unsigned long long *d_totals = nullptr;   // [8]
     unsigned long long *h_totals = nullptr;   // pinned [8]
     // host-batch pipeline, one set per stream
@@ -263,10 +267,10 @@ int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_
     d->kp.frames_per_grab = 2;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, c->device);
-    if (e == cudaSuccess) e = c->ks->geom_kaneko(c->use_lut, c->nk, prop.multiProcessorCount, d->geom2);
+    if (e == cudaSuccess) e = c->ks->geom_kaneko(c->use_lut, c->nk, prop.multiProcessorCount, d->geom4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream[0], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream[1], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&d->d_queue, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_ctl, 3 * sizeof(PkPhaseCtl));
     if (e == cudaSuccess) e = cudaMalloc(&d->d_totals, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&d->h_totals, 8 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
@@ -284,7 +288,8 @@ void pk_kaneko_destroy(pk_kaneko *d) {
         if (d->stream[s]) { cudaStreamSynchronize(d->stream[s]); cudaStreamDestroy(d->stream[s]); }
         cudaFree(d->d_y[s]); cudaFree(d->d_dec[s]); cudaFree(d->d_tr[s]); cudaFree(d->d_rec[s]);
     }
-    cudaFree(d->d_queue);
+    cudaFree(d->d_ctl);
+    for (int i = 0; i < 3; ++i) cudaFree(d->d_longs[i]);
     cudaFree(d->d_totals);
     cudaFree(d->d_grec);
     if (d->h_totals) cudaFreeHost(d->h_totals);
@@ -300,10 +305,51 @@ int pk_kaneko_set_frames_per_grab(pk_kaneko *d, int g) {
 
 int pk_kaneko_launch_geometry(const pk_kaneko *d, int *grid, int *block, long *smem) {
     if (!d) return fail(PK_ERR_ARG, "NULL");
-    if (grid) *grid = d->geom2[0].grid;
-    if (block) *block = d->geom2[0].block;
-    if (smem) *smem = (long)d->geom2[0].smem;
+    if (grid) *grid = d->geom4[0].grid;
+    if (block) *block = d->geom4[0].block;
+    if (smem) *smem = (long)d->geom4[0].smem;
     return PK_OK;
+}
+
+// ------------------------------------------------------------------ launch helpers
+// A batch is cut into launch pairs (phase A + phase B) of at most long_cap frames, so that every
+// frame that outlives phase A finds a slot in the parked-frame list.
+static int launch_pairs(pk_kaneko *d, int slot, bool gen, PkIo io, long B, cudaStream_t st) {
+    const pk_code *c = d->code;
+    const bool wide = d->geom4[gen ? 3 : 1].grid > 0;
+    if (wide && !d->d_longs[slot]) PK_CUDA(cudaMalloc(&d->d_longs[slot], (size_t)d->long_cap * sizeof(PkLongRec)));
+    for (long off = 0; off < B; off += d->long_cap) {
+        const long nb = std::min(d->long_cap, B - off);
+        PkIo part = io;
+        if (gen) {
+            part.gp.first_frame = io.gp.first_frame + (uint64_t)off;
+            if (io.d_info) part.d_info = io.d_info + off * c->k;
+            if (io.d_cw) part.d_cw = io.d_cw + off * c->n;
+            if (io.d_y) part.d_y = io.d_y + off * c->n;
+        } else {
+            part.y = io.y + off * c->n;
+            part.decided = io.decided + off * c->n;
+            if (io.trials) part.trials = io.trials + off;
+        }
+        if (io.recs) part.recs = io.recs + off;
+        PK_CUDA(c->ks->launch_kaneko(c->use_lut, gen, d->geom4, c->dev, d->kp, part, nb, d->d_ctl + slot,
+                                     d->d_longs[slot], wide ? d->long_cap : 0, st));
+    }
+    return PK_OK;
+}
+static int launch_replay(pk_kaneko *d, int slot, const double *d_y, long B, uint8_t *d_dec, uint32_t *d_tr,
+                         pk_frame_rec *d_recs, unsigned long long *d_totals, cudaStream_t st) {
+    PkIo io{};
+    io.y = d_y; io.decided = d_dec; io.trials = d_tr; io.recs = d_recs; io.totals = d_totals;
+    return launch_pairs(d, slot, false, io, B, st);
+}
+static int launch_gen(pk_kaneko *d, int slot, const PkGenParams &gp, long B, pk_frame_rec *d_recs,
+                      unsigned long long *d_totals, uint8_t *d_info, uint8_t *d_cw, double *d_y, int dump_only,
+                      cudaStream_t st) {
+    PkIo io{};
+    io.gp = gp; io.d_info = d_info; io.d_cw = d_cw; io.d_y = d_y; io.dump_only = dump_only;
+    io.recs = d_recs; io.totals = d_totals;
+    return launch_pairs(d, slot, true, io, B, st);
 }
 
 // ------------------------------------------------------------------ replay mode
@@ -313,9 +359,7 @@ int pk_kaneko_decode_batch_dev(pk_kaneko *d, const double *d_y, long B, uint8_t 
     if (!B) return PK_OK;
     PK_CUDA(cudaSetDevice(d->code->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream[0];
-    PK_CUDA(d->code->ks->launch_replay(d->code->use_lut, d->geom2[0], d->code->dev, d->kp, d_y, B, d_decided, d_trials,
-                                       d_recs, (unsigned long long *)d_totals, (unsigned int *)d->d_queue, st));
-    return PK_OK;
+    return launch_replay(d, stream ? 2 : 0, d_y, B, d_decided, d_trials, d_recs, (unsigned long long *)d_totals, st);
 }
 
 static int ensure_pipeline(pk_kaneko *d) {
@@ -352,9 +396,9 @@ int pk_kaneko_decode_batch(pk_kaneko *d, const double *y, long B, uint8_t *decid
         PK_CUDA(cudaMemcpyAsync(d->d_y[s], y + off * n, (size_t)nb * n * sizeof(double), cudaMemcpyHostToDevice, st));
         // undecided rows (PK_FLAG_NO_DECISION) come back zero-filled
         PK_CUDA(cudaMemsetAsync(d->d_dec[s], 0, (size_t)nb * n, st));
-        PK_CUDA(d->code->ks->launch_replay(d->code->use_lut, d->geom2[0], d->code->dev, d->kp, d->d_y[s], nb, d->d_dec[s],
-                                           trials ? d->d_tr[s] : nullptr, recs ? d->d_rec[s] : nullptr, d->d_totals,
-                                           (unsigned int *)(d->d_queue + s), st));
+        rc = launch_replay(d, s, d->d_y[s], nb, d->d_dec[s], trials ? d->d_tr[s] : nullptr, recs ? d->d_rec[s] : nullptr,
+                           d->d_totals, st);
+        if (rc) return rc;
         PK_CUDA(cudaMemcpyAsync(decided + off * n, d->d_dec[s], (size_t)nb * n, cudaMemcpyDeviceToHost, st));
         if (trials)
             PK_CUDA(cudaMemcpyAsync(trials + off, d->d_tr[s], (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -387,10 +431,7 @@ int pk_kaneko_run_frames_dev(pk_kaneko *d, double ebn0_db, int snr_index, uint64
     gp.seed = seed;
     gp.first_frame = first_frame;
     gp.snr_index = (uint32_t)snr_index;
-    PK_CUDA(d->code->ks->launch_generate(d->code->use_lut, d->geom2[1], d->code->dev, d->kp, gp, nframes, d_recs,
-                                         (unsigned long long *)d_totals, (unsigned int *)d->d_queue, nullptr, nullptr,
-                                         nullptr, 0, st));
-    return PK_OK;
+    return launch_gen(d, stream ? 2 : 0, gp, nframes, d_recs, (unsigned long long *)d_totals, nullptr, nullptr, nullptr, 0, st);
 }
 
 static int ensure_grec(pk_kaneko *d, long cap) {
@@ -448,9 +489,7 @@ int pk_generate_frames_dev(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t
     gp.seed = seed;
     gp.first_frame = first_frame;
     gp.snr_index = (uint32_t)snr_index;
-    PK_CUDA(c->ks->launch_generate(c->use_lut, d->geom2[1], c->dev, d->kp, gp, nframes, nullptr, nullptr,
-                                   (unsigned int *)d->d_queue, d_info, d_cw, d_y, 1, st));
-    return PK_OK;
+    return launch_gen(d, stream ? 2 : 0, gp, nframes, nullptr, nullptr, d_info, d_cw, d_y, 1, st);
 }
 
 int pk_generate_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
@@ -471,8 +510,7 @@ int pk_generate_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t see
         gp.seed = seed;
         gp.first_frame = first_frame;
         gp.snr_index = (uint32_t)snr_index;
-        e = c->ks->launch_generate(c->use_lut, d->geom2[1], c->dev, d->kp, gp, nframes, nullptr, nullptr,
-                                   (unsigned int *)d->d_queue, d_info, d_cw, d_y, 1, d->stream[0]);
+        if (launch_gen(d, 0, gp, nframes, nullptr, nullptr, d_info, d_cw, d_y, 1, d->stream[0]) != PK_OK) e = cudaErrorUnknown;
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream[0]);
     if (e == cudaSuccess && info) e = cudaMemcpy(info, d_info, (size_t)nframes * c->k, cudaMemcpyDeviceToHost);

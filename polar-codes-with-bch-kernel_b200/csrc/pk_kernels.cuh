@@ -1,33 +1,41 @@
 // pk_kernels.cuh -- sm_100a kernels of the Kaneko/BCH Monte-Carlo hot path.
 //
 // Mapping (reference file:line -> here):
-//   KanekoKernelProcessor::decode(answer,word,res)  src/KanekoKernelProcessor.cpp:335-407 -> KanekoWarp::decode
+//   KanekoKernelProcessor::decode(answer,word,res)  src/KanekoKernelProcessor.cpp:335-407 -> KanekoWarp
 //   calcError / alterSyndromPoly                    :36-51, src/Decoder.cpp:210-230       -> XOR of "augmented columns"
-//   Decoder::decode (euclid + Chien)                src/Decoder.cpp:233-321               -> pk_alg_decode / coset table
-//   calcM / calcL / calcRightSide / calcT           :54-126                               -> popc, ordered fp64 sums
-//   generateRandomPoly / multiplyPolynomials / addNoise  src/bchCoder.cpp:120-132,236-250 -> k_generate front end
-//   fun() per-frame bookkeeping                     src/dataForPlot.cpp:66-73             -> k_generate back end
+//   Decoder::decode (euclid + Chien)                src/Decoder.cpp:233-321               -> pk_alg_decode / pk_bs_decode / coset table
+//   calcM / calcL / calcRightSide / calcT           :54-126                               -> popc, ordered fp64 sums (KanekoWarp::commit)
+//   generateRandomPoly / multiplyPolynomials / addNoise  src/bchCoder.cpp:120-132,236-250 -> pk_load_frame<.., GEN = true>
+//   fun() per-frame bookkeeping                     src/dataForPlot.cpp:66-73             -> pk_emit
 //
-// Execution model: persistent CTAs, ONE WARP PER FRAME, frames pulled from an atomic queue
-// (per-frame work spans 1 .. 2^31 trials).  Inside a frame the 32 lanes evaluate 32
-// consecutive test patterns per step speculatively; improvements are then committed IN
-// PATTERN ORDER (ballot + shuffles), so the sequential semantics of the reference loop
-// -- l0, m0, the shrinking bound (1 << T) - 1 and all three operation counters -- are
-// reproduced exactly, and only trials the sequential loop would have run are counted.
-// Pattern i's word differs from yH by an XOR of per-position columns, so its syndromes
-// are S(yH) ^ (uniform part for i >> 5) ^ (per-lane part for i & 31): calcError and
-// alterSyndromPoly collapse into a handful of XORs.
+// Execution model.  Persistent CTAs, ONE WARP PER FRAME, frames pulled from an atomic queue
+// (per-frame work spans 1 .. 2^31 trials).
+//   Phase A (k_phase_a): "narrow" search -- the 32 lanes evaluate 32 consecutive test patterns
+//     per step (BM+Chien in registers or a coset-table lookup).  Almost every frame at medium
+//     and high SNR finishes here.  A frame still running after PK_LIMIT_A trials is parked in a
+//     long list with its search state.
+//   Phase B (k_phase_b): "wide" search of the parked frames, 1024 test patterns per warp step:
+//     lane l, bit q  <->  pattern base + 32 l + q.  For t*m > 15 codes the algebraic decoder
+//     runs BIT-SLICED (pk_bs.cuh: no table lookups, ~9 LOP3 per trial); coset-table codes do
+//     32 lookups per lane.  Candidates are rare and are committed one by one.
+// In both phases improvements are committed IN PATTERN ORDER, so the sequential semantics of
+// the reference loop -- l0, m0, the shrinking bound (1 << T) - 1 and all three operation
+// counters -- are reproduced exactly, and only trials the sequential loop would have run are
+// counted.  Pattern i's word differs from yH by an XOR of per-position columns, so its
+// syndromes are S(yH) ^ (XOR of the columns of i's set bits): calcError and alterSyndromPoly
+// collapse into a handful of XORs.
 #pragma once
 #include <cfloat>
 #include <cuda_runtime.h>
 
 #include "pk_alg.cuh"
+#include "pk_bs.cuh"
 #include "pk_kernels.h"
 
 #define PK_FULL 0xFFFFFFFFu
-#ifndef PK_WARPS
-#define PK_WARPS 8
-#endif
+#define PK_WARPS_A 8        // warps per CTA, phase A
+#define PK_WARPS_B 4        // warps per CTA, phase B (the bit-sliced decoder needs ~170 registers)
+#define PK_LIMIT_A 1024u    // trials a frame may spend in phase A before it is parked (multiple of 1024)
 
 // totals slots (pk_point_result layout)
 enum { PK_T_FRAMES = 0, PK_T_FERR, PK_T_BERR, PK_T_TRIALS, PK_T_CMP, PK_T_SUM, PK_T_MAXTR, PK_T_FLAGS };
@@ -58,6 +66,13 @@ __device__ __forceinline__ PkPhilox pk_philox(uint32_t c0, uint32_t c1, uint32_t
     return o;
 }
 
+// ------------------------------------------------------------------ compile-time switches per (M,T)
+template <int M, int T>
+struct PkTraits {
+    static constexpr bool LUT_OK = (T * M <= 15);                 // u16 coset-table entry fits
+    static constexpr bool BS_OK = ((T + 1) * M <= 56) && !LUT_OK; // bit-sliced decoder fits the register file
+};
+
 // ------------------------------------------------------------------ shared memory plan
 template <int M, int T, bool LUT>
 struct PkSmem {
@@ -72,15 +87,26 @@ struct PkSmem {
     static constexpr size_t COL_SZ = pk_align16((size_t)C::N * SW * 4);
     static constexpr size_t LUT_OFF = COL_OFF + COL_SZ;
     __host__ __device__ static constexpr size_t lut_sz(int nk) { return LUT ? ((size_t)2 << nk) : 0; }
-    // per warp
+    // per warp (common)
     static constexpr size_t W_ALPHA = 0;                              // double[NP]   |alpha| by position
     static constexpr size_t W_SKEY = W_ALPHA + (size_t)NP * 8;        // double[NP+2] |alpha| ascending
-    static constexpr size_t W_SIDX = W_SKEY + (size_t)(NP + 2) * 8;   // uint8 [NP]   position of rank r
+    static constexpr size_t W_PREF = W_SKEY + (size_t)(NP + 2) * 8;   // double[NP+2] prefix sums of skey
+    static constexpr size_t W_SIDX = W_PREF + (size_t)(NP + 2) * 8;   // uint8 [NP]   position of rank r
     static constexpr size_t W_U = W_SIDX + (size_t)NP;                // uint32[NW+1] info bits (generation)
-    static constexpr size_t W_SZ = pk_align16(W_U + (size_t)(C::NW + 1) * 4);
-    __host__ __device__ static constexpr size_t total(int nk, int warps) {
-        return LUT_OFF + pk_align16(lut_sz(nk)) + (size_t)warps * W_SZ;
-    }
+    static constexpr size_t W_SZ_A = pk_align16(W_U + (size_t)(C::NW + 1) * 4);
+    // per warp, phase B extras
+    static constexpr size_t W_CM = W_SZ_A;                                          // uint32[2T*M] planes / [32] deltas
+    static constexpr size_t W_CM_SZ = pk_align16((size_t)(LUT ? 32 : 2 * T * M) * 4);
+    static constexpr size_t W_PB = W_CM + W_CM_SZ;                                  // uint32[32][NW] one-hot XORs (LUT)
+    static constexpr size_t W_PB_SZ = LUT ? pk_align16((size_t)32 * C::NW * 4) : 0;
+    static constexpr size_t W_WL = W_PB + W_PB_SZ;                                  // double[32] in-word pattern reliabilities (LUT)
+    static constexpr size_t W_WL_SZ = LUT ? 256 : 0;
+    static constexpr size_t W_Z = W_WL + W_WL_SZ;                                   // uint32[N][33] root words (bit-sliced)
+    static constexpr size_t W_Z_SZ = LUT ? 0 : pk_align16((size_t)C::N * 33 * 4);
+    static constexpr size_t W_SZ_B = W_Z + W_Z_SZ;
+    __host__ __device__ static constexpr size_t tables(int nk) { return LUT_OFF + pk_align16(lut_sz(nk)); }
+    __host__ __device__ static constexpr size_t total_a(int nk) { return tables(nk) + (size_t)PK_WARPS_A * W_SZ_A; }
+    __host__ __device__ static constexpr size_t total_b(int nk) { return tables(nk) + (size_t)PK_WARPS_B * W_SZ_B; }
 };
 
 template <int NW>
@@ -98,43 +124,73 @@ struct KanekoWarp {
     typedef PkSmem<M, T, LUT> SM;
     static constexpr int N = C::N, NW = C::NW, SW = SM::SW, NA = SW + NW;
 
-    struct Result {
-        uint32_t YH[NW];    // hard decisions of the received word
-        uint32_t F[NW];     // best flip set: decided = YH ^ F
-        uint32_t trials, extra_cmp, extra_sum, flags;
+    struct Tables {      // CTA-shared tables
+        const uint8_t *mul;
+        const uint16_t *xoff;
+        const uint32_t *col;
+        const uint16_t *lut;
+    };
+    struct WarpMem {     // per-warp shared scratch
+        double *alpha, *skey, *pref;
+        uint8_t *sidx;
+        uint32_t *cm, *pb, *z;
+        double *wl;
+    };
+    struct Frame {       // per-frame registers
+        uint32_t YH[NW];   // hard decisions (uniform)
+        uint32_t S0[SW];   // syndromes / coset index of yH (uniform)
+        uint32_t aug[NA];  // lane b: column of the b-th least reliable position | its one-hot mask
+        uint32_t flags;
+    };
+    struct Search {      // the sequential state of the reference loop (uniform)
+        double l0;
+        int m0;
+        bool first_ok, have, early;
+        uint32_t bound, trials, tsteps, nimpr, flags;
+        uint32_t bestF[NW];
     };
 
-    // yv[w]: channel output of position lane + 32 w.  All lanes return the same Result.
-    __device__ static void decode(const uint8_t *s_mul, const uint16_t *s_xoff, const uint32_t *s_col,
-                                  const uint16_t *s_lut, double *w_alpha, double *w_skey, uint8_t *w_sidx,
-                                  const double (&yv)[NW], const PkKanekoParams &kp, Result &R) {
-        const int lane = threadIdx.x & 31;
-        uint32_t flags = 0;
+    __device__ static WarpMem warp_mem(unsigned char *wb) {
+        WarpMem w;
+        w.alpha = reinterpret_cast<double *>(wb + SM::W_ALPHA);
+        w.skey = reinterpret_cast<double *>(wb + SM::W_SKEY);
+        w.pref = reinterpret_cast<double *>(wb + SM::W_PREF);
+        w.sidx = wb + SM::W_SIDX;
+        w.cm = reinterpret_cast<uint32_t *>(wb + SM::W_CM);
+        w.pb = reinterpret_cast<uint32_t *>(wb + SM::W_PB);
+        w.z = reinterpret_cast<uint32_t *>(wb + SM::W_Z);
+        w.wl = reinterpret_cast<double *>(wb + SM::W_WL);
+        return w;
+    }
 
-        // ---- alpha_i = 2 y_i / sd0^2, yH_i = (alpha_i > 0), reliabilities (KanekoKernelProcessor.cpp:336-342)
+    // ---- per-frame set-up: alpha, yH, reliability order, syndrome of yH, lane columns
+    // (KanekoKernelProcessor.cpp:336-343,359).  yv[w]: channel output of position lane + 32 w.
+    __device__ static void setup(const Tables &tb, const WarpMem &wm, const double (&yv)[NW], const PkKanekoParams &kp,
+                                 Frame &f) {
+        const int lane = threadIdx.x & 31;
+        f.flags = 0;
         unsigned long long keyb[NW];
         bool hard[NW];
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             const int p = lane + 32 * w;
-            const double a = (2.0 * yv[w]) / kp.llr_den;
+            const double a = (2.0 * yv[w]) / kp.llr_den;      // alpha_i = 2 y_i / sd^2, IEEE divide
             const bool valid = p < N;
-            hard[w] = valid && !(a <= 0.0);
+            hard[w] = valid && !(a <= 0.0);                   // yH = (alpha <= 0) ? 0 : 1
             const double key = fabs(a);
             keyb[w] = (unsigned long long)__double_as_longlong(key);
-            if (valid) w_alpha[p] = key;
-            R.YH[w] = __ballot_sync(PK_FULL, hard[w]);
+            if (valid) wm.alpha[p] = key;
+            f.YH[w] = __ballot_sync(PK_FULL, hard[w]);
         }
         __syncwarp();
-
-        // ---- std::sort by |alpha| ascending (:343) as a rank sort; ties broken by position
-        // (== std::sort for n <= 16 where libstdc++ runs a plain insertion sort; flagged otherwise).
+        // std::sort by |alpha| ascending (:343) as a rank sort on the f64 bit patterns; ties broken by
+        // position (== std::sort for n <= 16, where libstdc++ runs a plain insertion sort; flagged otherwise).
         {
             int rank[NW];
             bool tie = false;
 #pragma unroll
             for (int w = 0; w < NW; ++w) rank[w] = 0;
-            const unsigned long long *ak = reinterpret_cast<const unsigned long long *>(w_alpha);
+            const unsigned long long *ak = reinterpret_cast<const unsigned long long *>(wm.alpha);
 #pragma unroll 4
             for (int q = 0; q < N; ++q) {
                 const unsigned long long kq = ak[q];
@@ -150,17 +206,22 @@ struct KanekoWarp {
             for (int w = 0; w < NW; ++w) {
                 const int p = lane + 32 * w;
                 if (p < N) {
-                    w_skey[rank[w]] = __longlong_as_double((long long)keyb[w]);
-                    w_sidx[rank[w]] = (uint8_t)p;
+                    wm.skey[rank[w]] = __longlong_as_double((long long)keyb[w]);
+                    wm.sidx[rank[w]] = (uint8_t)p;
                 }
             }
-            if (lane == 0) w_skey[N] = 0.0;  // the reference reads one past the end in calcT(n-t); value unused
-            if (__any_sync(PK_FULL, tie)) flags |= PK_FLAG_SORT_TIE;
+            if (lane == 0) wm.skey[N] = 0.0;  // the reference reads one past the end in calcT(n-t); value unused
+            if (__any_sync(PK_FULL, tie)) f.flags |= PK_FLAG_SORT_TIE;
         }
         __syncwarp();
-
-        // ---- syndrome of yH (Decoder::findSyndromPoly, Decoder.cpp:184-207): XOR of columns
-        uint32_t S0[SW];
+        // prefix sums of the sorted reliabilities: pref[m] <= l of ANY flip set of weight m (used only to
+        // skip exact l computations that cannot beat l0; never decides anything by itself)
+        if (lane == 0) {
+            double acc = 0.0;
+            wm.pref[0] = 0.0;
+            for (int r = 0; r < N; ++r) { acc += wm.skey[r]; wm.pref[r + 1] = acc; }
+        }
+        // syndrome of yH (Decoder::findSyndromPoly, Decoder.cpp:184-207): XOR of columns
         {
             uint32_t acc[SW];
 #pragma unroll
@@ -170,26 +231,134 @@ struct KanekoWarp {
                 const int p = lane + 32 * w;
                 if (hard[w]) {
 #pragma unroll
-                    for (int s = 0; s < SW; ++s) acc[s] ^= s_col[p * SW + s];
+                    for (int s = 0; s < SW; ++s) acc[s] ^= tb.col[p * SW + s];
                 }
             }
 #pragma unroll
-            for (int s = 0; s < SW; ++s) S0[s] = __reduce_xor_sync(PK_FULL, acc[s]);
+            for (int s = 0; s < SW; ++s) f.S0[s] = __reduce_xor_sync(PK_FULL, acc[s]);
         }
-
-        // ---- lane b keeps the augmented column of the b-th least reliable position
-        // (pattern bit b flips that position, calcError :36-51).  Bits >= 31 are never set
-        // because the bound never exceeds 2^31 - 1.
-        uint32_t aug[NA];
+        // lane b keeps the augmented column of the b-th least reliable position (pattern bit b flips that
+        // position, calcError :36-51).  Bits >= 31 never occur: the bound never exceeds 2^31 - 1.
 #pragma unroll
-        for (int a = 0; a < NA; ++a) aug[a] = 0;
+        for (int a = 0; a < NA; ++a) f.aug[a] = 0;
         if (lane < 31 && lane < N) {
-            const int p = w_sidx[lane];
+            const int p = wm.sidx[lane];
 #pragma unroll
-            for (int s = 0; s < SW; ++s) aug[s] = s_col[p * SW + s];
+            for (int s = 0; s < SW; ++s) f.aug[s] = tb.col[p * SW + s];
 #pragma unroll
-            for (int w = 0; w < NW; ++w) aug[SW + w] = ((p >> 5) == w) ? (1u << (p & 31)) : 0u;
+            for (int w = 0; w < NW; ++w) f.aug[SW + w] = ((p >> 5) == w) ? (1u << (p & 31)) : 0u;
         }
+        __syncwarp();
+    }
+
+    __device__ static void search_init(Search &s, const Frame &f) {
+        s.l0 = DBL_MAX;
+        s.m0 = 0;
+        s.first_ok = true; s.have = false; s.early = false;
+        s.bound = pk_pattern_bound(N);      // long T = n (:354)
+        s.trials = 0; s.tsteps = 0; s.nimpr = 0;
+        s.flags = f.flags;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s.bestF[w] = 0;
+    }
+
+    // Could a flip set of weight m still beat l0?  pref[m] is a lower bound of its l; the margin makes the
+    // skip exact under fp64 rounding of both sums (2 m ulp << 1e-9).
+    __device__ static __forceinline__ bool may_improve(const WarpMem &wm, int m, double l0) {
+        return wm.pref[m] * (1.0 - 1e-9) < l0;
+    }
+    // l = sum over the set bits of F of alpha, ascending position (calcL :69-77)
+    __device__ static __forceinline__ double calc_l(const WarpMem &wm, const uint32_t (&F)[NW]) {
+        double l = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            uint32_t fw = F[w];
+            while (fw) {
+                const int b = __ffs(fw) - 1;
+                fw &= fw - 1;
+                l += wm.alpha[32 * w + b];
+            }
+        }
+        return l;
+    }
+
+    // ---- an improvement found at trial `is` (l < l0): lines :374-398.  Uniform across the warp.
+    // Returns true when the search ends through `if (l < calcRightSide()) return;`.
+    __device__ static bool commit(Search &s, const WarpMem &wm, const PkKanekoParams &kp, double ls, int ms,
+                                  const uint32_t (&Fs)[NW], uint32_t is) {
+        const int lane = threadIdx.x & 31;
+        if (is == 0 || !s.first_ok) s.m0 = ms;   // :374
+        s.l0 = ls;
+        s.have = true;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s.bestF[w] = Fs[w];
+        {   // calcRightSide (:54-67)
+            const int border = (2 * T + 1) - (ms + s.m0) / 2;
+            double rs = 0.0;
+            int cnt = 0, j = 0;
+            while (cnt < border && j < N) {
+                const int p = wm.sidx[j];
+                if (!pk_getbit<NW>(Fs, p)) { rs += wm.skey[j]; ++cnt; }
+                ++j;
+            }
+            if (ls < rs) { s.early = true; s.trials = is + 1; return true; }   // :380-382
+        }
+        // while (l >= calcT(j) && j <= n-1-t) ++j   (:384-390, calcT :110-126); lanes try 32 j at a time
+        int jn;
+        {
+            const int border = T - (ms + s.m0) / 2;
+            double bs = 0.0;
+            int cnt = 0, k = 0;
+            while (cnt < border && k < N) {
+                const int p = wm.sidx[k];
+                if (!pk_getbit<NW>(Fs, p)) { bs += wm.skey[k]; ++cnt; }
+                ++k;
+            }
+            const int jmax = N - 1 - T;
+            jn = jmax + 1;
+            for (int c0 = 0; c0 <= jmax; c0 += 32) {
+                const int jj = c0 + lane;
+                const bool in = jj <= jmax;
+                double tj = bs;
+                if (in) {
+#pragma unroll
+                    for (int q = 0; q <= T; ++q) tj += wm.skey[jj + q];
+                }
+                const uint32_t stop = __ballot_sync(PK_FULL, in && !(ls >= tj));
+                if (stop) { jn = c0 + __ffs(stop) - 1; break; }
+            }
+        }
+        s.tsteps += (uint32_t)jn;
+        ++s.nimpr;
+        const int Tn = (kp.J >= 0 && jn > kp.J) ? kp.J : jn;   // :392-393
+        s.bound = pk_pattern_bound(Tn);
+        return false;
+    }
+
+    // coset-table entry -> located positions; returns the verdict
+    __device__ static __forceinline__ bool lut_positions(uint32_t e, uint32_t (&A)[NW]) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) A[w] = 0;
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            const uint32_t p = (e >> (j * M)) & (uint32_t)N;   // N = "none"
+            if constexpr (NW == 1) {
+                A[0] |= 1u << p;                               // p == N sets the unused top bit
+            } else {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) A[w] |= ((p >> 5) == (uint32_t)w) ? (1u << (p & 31)) : 0u;
+            }
+        }
+        A[NW - 1] &= ~(1u << (N & 31));                        // drop the "none" marker bit
+        return !(e & 0x8000u);
+    }
+
+    // ---- narrow search: 32 patterns per step starting at trial base0 (multiple of 32).  Returns true when
+    // the frame is finished, false when trial `limit` was reached and the frame must be parked (s holds the
+    // state, *next = the next trial to run).
+    __device__ static bool narrow(const Tables &tb, const WarpMem &wm, const PkKanekoParams &kp, const Frame &f,
+                                  Search &s, uint32_t base0, uint32_t limit, uint32_t *next) {
+        const int lane = threadIdx.x & 31;
         uint32_t Vl[NA], Vb[NA];
 #pragma unroll
         for (int a = 0; a < NA; ++a) { Vl[a] = 0; Vb[a] = 0; }
@@ -197,61 +366,33 @@ struct KanekoWarp {
         for (int b = 0; b < 5; ++b) {
 #pragma unroll
             for (int a = 0; a < NA; ++a) {
-                const uint32_t c = __shfl_sync(PK_FULL, aug[a], b);
+                const uint32_t c = __shfl_sync(PK_FULL, f.aug[a], b);
                 Vl[a] ^= ((lane >> b) & 1) ? c : 0u;
             }
         }
-
-        // ---- the test-pattern loop (:354-405)
-        uint32_t bound = pk_pattern_bound(N);   // long T = n
-        double l0 = DBL_MAX;
-        bool first_ok = true, have = false, early = false;
-        int m0 = 0;
-        uint32_t bestF[NW];
+        {
+            uint32_t hb = base0 >> 5;
+            while (hb) {
+                const int b = __ffs(hb) - 1;
+                hb &= hb - 1;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) bestF[w] = 0;
-        uint32_t trials = 0, tsteps = 0, nimpr = 0;
-
-        uint32_t step = 0;
-        for (uint32_t base = 0;; base += 32, ++step) {
-            if (base >= kp.max_trials) { trials = base; flags |= PK_FLAG_TRUNCATED; break; }
-            if (step) {   // uniform part of the pattern: bits 5.. of i
-                uint32_t diff = step ^ (step - 1);
-                while (diff) {
-                    const int b = __ffs(diff) - 1;
-                    diff &= diff - 1;
-#pragma unroll
-                    for (int a = 0; a < NA; ++a) Vb[a] ^= __shfl_sync(PK_FULL, aug[a], 5 + b);
-                }
+                for (int a = 0; a < NA; ++a) Vb[a] ^= __shfl_sync(PK_FULL, f.aug[a], 5 + b);
             }
+        }
+        for (uint32_t base = base0;; base += 32) {
+            if (base >= kp.max_trials) { s.trials = base; s.flags |= PK_FLAG_TRUNCATED; return true; }
+            if (base >= limit) { *next = base; return false; }
             const uint32_t i = base + lane;
-            bool active = i < bound;
-
             uint32_t Sx[SW], A[NW], F[NW];
 #pragma unroll
-            for (int s = 0; s < SW; ++s) Sx[s] = S0[s] ^ Vb[s] ^ Vl[s];
+            for (int q = 0; q < SW; ++q) Sx[q] = f.S0[q] ^ Vb[q] ^ Vl[q];
             bool succ;
             if constexpr (LUT) {
-                const uint32_t e = s_lut[Sx[0]];
-                succ = !(e & 0x8000u);
-#pragma unroll
-                for (int w = 0; w < NW; ++w) A[w] = 0;
-#pragma unroll
-                for (int j = 0; j < T; ++j) {
-                    const uint32_t p = (e >> (j * M)) & (uint32_t)N;   // N = "none"
-                    if constexpr (NW == 1) {
-                        A[0] |= 1u << p;                               // p == N sets the unused top bit
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < NW; ++w) A[w] |= ((p >> 5) == (uint32_t)w) ? (1u << (p & 31)) : 0u;
-                    }
-                }
-                A[NW - 1] &= ~(1u << (N & 31));                        // drop the "none" marker bit
+                succ = lut_positions(tb.lut[Sx[0]], A);
             } else {
-                succ = pk_alg_decode<M, T>(Sx, s_mul, s_xoff, A);
+                succ = pk_alg_decode<M, T>(Sx, tb.mul, tb.xoff, A);
             }
-            succ = succ && active;
-
+            succ = succ && (i < s.bound);
             // m = d_H(yH, x) (calcM :89-97), l = sum_{yH != x} alpha in index order (calcL :69-77)
             int m = 0;
 #pragma unroll
@@ -259,24 +400,14 @@ struct KanekoWarp {
                 F[w] = Vb[SW + w] ^ Vl[SW + w] ^ A[w];
                 m += __popc(F[w]);
             }
-            double l = 0.0;
-            if (succ) {
-#pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    uint32_t f = F[w];
-                    while (f) {
-                        const int b = __ffs(f) - 1;
-                        f &= f - 1;
-                        l += w_alpha[32 * w + b];
-                    }
-                }
-            }
-            if (base == 0) first_ok = __shfl_sync(PK_FULL, succ ? 1 : 0, 0) != 0;   // :371
+            double l = DBL_MAX;
+            if (succ && may_improve(wm, m, s.l0)) l = calc_l(wm, F);
+            if (base == 0) s.first_ok = __shfl_sync(PK_FULL, succ ? 1 : 0, 0) != 0;   // :371
 
-            // ---- in-order commit of improvements (:372-399)
+            // in-order commit of improvements (:372-399)
             bool impr_here = false;
             uint32_t last_is = 0;
-            uint32_t cand = __ballot_sync(PK_FULL, succ && (l < l0));
+            uint32_t cand = __ballot_sync(PK_FULL, succ && (l < s.l0));
             while (cand) {
                 const int src = __ffs(cand) - 1;
                 const double ls = __shfl_sync(PK_FULL, l, src);
@@ -284,92 +415,273 @@ struct KanekoWarp {
                 uint32_t Fs[NW];
 #pragma unroll
                 for (int w = 0; w < NW; ++w) Fs[w] = __shfl_sync(PK_FULL, F[w], src);
-                const uint32_t is = base + src;
-                if (is == 0 || !first_ok) m0 = ms;   // :374
-                l0 = ls;
-                have = true;
                 impr_here = true;
-                last_is = is;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) bestF[w] = Fs[w];
-
-                // calcRightSide (:54-67)
-                {
-                    const int border = (2 * T + 1) - (ms + m0) / 2;
-                    double rs = 0.0;
-                    int cnt = 0, j = 0;
-                    while (cnt < border && j < N) {
-                        const int p = w_sidx[j];
-                        if (!pk_getbit<NW>(Fs, p)) { rs += w_skey[j]; ++cnt; }
-                        ++j;
-                    }
-                    if (ls < rs) { early = true; trials = is + 1; break; }   // :380-382
-                }
-                // while (l >= calcT(j) && j <= n-1-t) ++j   (:384-390, calcT :110-126)
-                int jn;
-                {
-                    const int border = T - (ms + m0) / 2;
-                    double bs = 0.0;
-                    int cnt = 0, k = 0;
-                    while (cnt < border && k < N) {
-                        const int p = w_sidx[k];
-                        if (!pk_getbit<NW>(Fs, p)) { bs += w_skey[k]; ++cnt; }
-                        ++k;
-                    }
-                    const int jmax = N - 1 - T;
-                    jn = jmax + 1;
-                    for (int c0 = 0; c0 <= jmax; c0 += 32) {
-                        const int jj = c0 + lane;
-                        const bool in = jj <= jmax;
-                        double tj = bs;
-                        if (in) {
-#pragma unroll
-                            for (int q = 0; q <= T; ++q) tj += w_skey[jj + q];
-                        }
-                        const uint32_t stop = __ballot_sync(PK_FULL, in && !(ls >= tj));
-                        if (stop) { jn = c0 + __ffs(stop) - 1; break; }
-                    }
-                }
-                tsteps += (uint32_t)jn;
-                ++nimpr;
-                const int Tn = (kp.J >= 0 && jn > kp.J) ? kp.J : jn;   // :392-393
-                bound = pk_pattern_bound(Tn);
-                active = i < bound;
+                last_is = base + src;
+                if (commit(s, wm, kp, ls, ms, Fs, base + src)) return true;
                 const uint32_t later = (src == 31) ? 0u : (PK_FULL << (src + 1));
-                cand = __ballot_sync(PK_FULL, succ && active && (l < l0)) & later;
+                cand = __ballot_sync(PK_FULL, succ && (i < s.bound) && (l < s.l0)) & later;
             }
-            if (early) break;
-            if (bound <= base + 32) {   // the sequential loop ends inside this step
-                trials = bound;
-                if (impr_here && last_is + 1 > trials) trials = last_is + 1;
-                break;
+            if (s.bound <= base + 32) {   // the sequential loop ends inside this step
+                s.trials = s.bound;
+                if (impr_here && last_is + 1 > s.trials) s.trials = last_is + 1;
+                return true;
+            }
+            {   // uniform part of the next pattern block: bits 5.. of i
+                uint32_t diff = ((base + 32u) ^ base) >> 5;
+                while (diff) {
+                    const int b = __ffs(diff) - 1;
+                    diff &= diff - 1;
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) Vb[a] ^= __shfl_sync(PK_FULL, f.aug[a], 5 + b);
+                }
             }
         }
+    }
 
-        if (early) flags |= PK_FLAG_EARLY_RETURN;
-        if (!have) flags |= PK_FLAG_NO_DECISION;
+    // ---- wide search (phase B): 1024 patterns per step, pattern = base + 32*lane + bit.
+    // Resumes a parked search at trial `base0` (multiple of 1024, > 0).
+    __device__ static void wide(const Tables &tb, const WarpMem &wm, const PkKanekoParams &kp, const Frame &f,
+                                Search &s, uint32_t base0) {
+        const int lane = threadIdx.x & 31;
+        // pattern bits 0..4 = bit index in the word: their column contributions are per-frame constants
+        if constexpr (LUT) {
+            // cm[q] = coset-index delta of in-word pattern q; pb[q][w] = its one-hot XOR
+            uint32_t c = 0, ph[NW];
 #pragma unroll
-        for (int w = 0; w < NW; ++w) R.F[w] = bestF[w];
-        R.trials = trials;
-        R.extra_cmp = tsteps + nimpr;   // :386-397
-        R.extra_sum = tsteps;
-        R.flags = flags;
+            for (int w = 0; w < NW; ++w) ph[w] = 0;
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+                const uint32_t cc = __shfl_sync(PK_FULL, f.aug[0], b);
+                c ^= ((lane >> b) & 1) ? cc : 0u;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const uint32_t pp = __shfl_sync(PK_FULL, f.aug[SW + w], b);
+                    ph[w] ^= ((lane >> b) & 1) ? pp : 0u;
+                }
+            }
+            wm.cm[lane] = c;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) wm.pb[lane * NW + w] = ph[w];
+            // wl[q] = sum of the reliabilities flipped by in-word pattern q (for the approximate-l filter)
+            double ws = 0.0;
+#pragma unroll
+            for (int b = 0; b < 5; ++b)
+                if (b < N && ((lane >> b) & 1)) ws += wm.skey[b];
+            wm.wl[lane] = ws;
+        } else {
+            // cm[j*M + b] = plane (over the 32 in-word patterns) of bit b of syndrome S_{j+1}
+            for (int si = lane; si < 2 * T * M; si += 32) {
+                const int j = si / M, b = si % M;
+                const int word = j / C::PER, sh = (j % C::PER) * M + b;
+                uint32_t plane = 0;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    if (q < N) {
+                        const uint32_t pat = (q == 0) ? 0xAAAAAAAAu : (q == 1) ? 0xCCCCCCCCu : (q == 2) ? 0xF0F0F0F0u : (q == 3) ? 0xFF00FF00u : 0xFFFF0000u;
+                        const uint32_t col = tb.col[(int)wm.sidx[q] * SW + word];
+                        plane ^= ((col >> sh) & 1u) ? pat : 0u;
+                    }
+                }
+                wm.cm[si] = plane;
+            }
+        }
+        // pattern bits 5..9 = lane index
+        uint32_t Ul[NA], Ub[NA];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) { Ul[a] = 0; Ub[a] = 0; }
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                const uint32_t c = __shfl_sync(PK_FULL, f.aug[a], 5 + b);
+                Ul[a] ^= ((lane >> b) & 1) ? c : 0u;
+            }
+        }
+        double lsum = 0.0;   // reliabilities flipped by pattern bits 5..9 (lane part)
+        if constexpr (LUT) {
+#pragma unroll
+            for (int b = 0; b < 5; ++b)
+                if (5 + b < N && ((lane >> b) & 1)) lsum += wm.skey[5 + b];
+        }
+        // pattern bits 10.. = base
+        {
+            uint32_t hb = base0 >> 10;
+            while (hb) {
+                const int b = __ffs(hb) - 1;
+                hb &= hb - 1;
+#pragma unroll
+                for (int a = 0; a < NA; ++a) Ub[a] ^= __shfl_sync(PK_FULL, f.aug[a], 10 + b);
+            }
+        }
         __syncwarp();
+
+        for (uint32_t base = base0;; base += 1024) {
+            if (base >= kp.max_trials) { s.trials = base; s.flags |= PK_FLAG_TRUNCATED; return; }
+            uint32_t u[SW];
+#pragma unroll
+            for (int q = 0; q < SW; ++q) u[q] = f.S0[q] ^ Ul[q] ^ Ub[q];
+            const uint32_t lane_first = base + 32u * lane;
+            const uint32_t vmask = (s.bound <= lane_first) ? 0u : ((s.bound - lane_first >= 32u) ? PK_FULL : ((1u << (s.bound - lane_first)) - 1u));
+            uint32_t cand;   // bit q: trial lane_first + q succeeded (and, LUT: its flip weight may still beat l0)
+            if constexpr (LUT) {
+                uint32_t ok = 0;
+#pragma unroll 8
+                for (int q = 0; q < 32; ++q) {
+                    const uint32_t e = tb.lut[u[0] ^ wm.cm[q]];
+                    ok |= (e & 0x8000u) ? 0u : (1u << q);
+                }
+                ok &= vmask;
+                cand = 0;
+                // Per-lane pre-filter with an APPROXIMATE l (pattern part + located positions, any summation
+                // order).  It only discards trials whose l exceeds l0 by far more than the rounding slack, so
+                // the exact in-order test below sees every possible improvement (a stale l0 is conservative:
+                // l0 only decreases).
+                double bsum = 0.0;
+                {
+                    uint32_t hb = base >> 10;
+                    while (hb) {
+                        const int b = __ffs(hb) - 1;
+                        hb &= hb - 1;
+                        bsum += wm.skey[10 + b];
+                    }
+                }
+                while (ok) {
+                    const int q = __ffs(ok) - 1;
+                    ok &= ok - 1;
+                    const uint32_t e = tb.lut[u[0] ^ wm.cm[q]];
+                    const double lp = wm.wl[q] + lsum + bsum;
+                    double la = lp;
+#pragma unroll
+                    for (int j = 0; j < T; ++j) {
+                        const uint32_t p = (e >> (j * M)) & (uint32_t)N;
+                        if (p != (uint32_t)N) {
+                            uint32_t pw = Ul[SW] ^ Ub[SW] ^ wm.pb[q * NW];
+#pragma unroll
+                            for (int w = 1; w < NW; ++w)
+                                pw = ((p >> 5) == (uint32_t)w) ? (Ul[SW + w] ^ Ub[SW + w] ^ wm.pb[q * NW + w]) : pw;
+                            const double a = wm.alpha[p];
+                            la += ((pw >> (p & 31)) & 1u) ? -a : a;
+                        }
+                    }
+                    if (!((la - s.l0) > 1e-9 * (lp + s.l0))) cand |= 1u << q;
+                }
+            } else {
+                auto getS = [&](int j, uint32_t *o) {
+#pragma unroll
+                    for (int b = 0; b < M; ++b) {
+                        const int bit = ((j - 1) % C::PER) * M + b;
+                        o[b] = wm.cm[(j - 1) * M + b] ^ (0u - ((u[(j - 1) / C::PER] >> bit) & 1u));
+                    }
+                };
+                cand = pk_bs_decode<M, T>(getS, wm.z + lane, 33) & vmask;
+            }
+            __syncwarp();
+
+            // ---- candidates in pattern order
+            bool impr_here = false, stop = false;
+            uint32_t last_is = 0;
+            uint32_t lanes_with = __ballot_sync(PK_FULL, cand != 0);
+            while (lanes_with && !stop) {
+                const int src = __ffs(lanes_with) - 1;
+                lanes_with &= lanes_with - 1;
+                uint32_t word = __shfl_sync(PK_FULL, cand, src);
+                const uint32_t usrc = __shfl_sync(PK_FULL, u[0], src);
+                while (word) {
+                    const int q = __ffs(word) - 1;
+                    word &= word - 1;
+                    const uint32_t is = base + 32u * src + q;
+                    if (is >= s.bound) { stop = true; break; }
+                    uint32_t A[NW], F[NW];
+                    if constexpr (LUT) {
+                        lut_positions(tb.lut[usrc ^ wm.cm[q]], A);
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) {
+                            const int p = lane + 32 * w;
+                            const uint32_t zb = (p < N) ? ((wm.z[p * 33 + src] >> q) & 1u) : 0u;
+                            A[w] = __ballot_sync(PK_FULL, zb);
+                        }
+                    }
+                    const bool sel = (lane < 31) && ((is >> lane) & 1u);
+                    int m = 0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        F[w] = __reduce_xor_sync(PK_FULL, sel ? f.aug[SW + w] : 0u) ^ A[w];
+                        m += __popc(F[w]);
+                    }
+                    if (!may_improve(wm, m, s.l0)) continue;
+                    bool same = s.have;   // same codeword as the current best: l == l0 exactly, no improvement
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) same = same && (F[w] == s.bestF[w]);
+                    if (same) continue;
+                    const double l = calc_l(wm, F);
+                    if (l < s.l0) {
+                        impr_here = true;
+                        last_is = is;
+                        if (commit(s, wm, kp, l, m, F, is)) return;
+                    }
+                }
+            }
+            if (s.bound <= base + 1024u) {
+                s.trials = s.bound;
+                if (impr_here && last_is + 1 > s.trials) s.trials = last_is + 1;
+                return;
+            }
+            {   // next base: bits 10.. change
+                uint32_t diff = ((base + 1024u) ^ base) >> 10;
+                while (diff) {
+                    const int b = __ffs(diff) - 1;
+                    diff &= diff - 1;
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) Ub[a] ^= __shfl_sync(PK_FULL, f.aug[a], 10 + b);
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    __device__ static void search_finish(Search &s) {
+        if (s.early) s.flags |= PK_FLAG_EARLY_RETURN;
+        if (!s.have) s.flags |= PK_FLAG_NO_DECISION;
+    }
+    __device__ static void park(const Search &s, uint32_t frame, uint32_t base, PkLongRec *r) {
+        r->l0 = s.l0;
+        r->frame = frame; r->base = base; r->bound = s.bound; r->m0 = (uint32_t)s.m0;
+        r->tsteps = s.tsteps; r->nimpr = s.nimpr;
+        r->sflags = (s.first_ok ? 1u : 0u) | (s.have ? 2u : 0u) | (s.flags << 8);
+        r->pad = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) r->bestF[w] = s.bestF[w];
+    }
+    __device__ static void unpark(Search &s, const PkLongRec *r) {
+        s.l0 = r->l0;
+        s.m0 = (int)r->m0;
+        s.bound = r->bound;
+        s.tsteps = r->tsteps; s.nimpr = r->nimpr;
+        s.first_ok = (r->sflags & 1u) != 0;
+        s.have = (r->sflags & 2u) != 0;
+        s.early = false;
+        s.flags = r->sflags >> 8;
+        s.trials = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s.bestF[w] = r->bestF[w];
     }
 };
 
 // ------------------------------------------------------------------ table staging
 template <int M, int T, bool LUT>
-__device__ __forceinline__ void pk_stage_tables(unsigned char *smem, const PkDevTables &tb) {
+__device__ __forceinline__ void pk_stage_tables(unsigned char *smem, const PkDevTables &tb, bool need_mul) {
     typedef PkSmem<M, T, LUT> SM;
     typedef PkCfg<M, T> C;
     const int tid = threadIdx.x, nth = blockDim.x;
     if constexpr (!LUT) {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(tb.mul);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(smem + SM::MUL_OFF);
-        for (int i = tid; i < (int)(SM::MUL_SZ / 4); i += nth) dst[i] = src[i];
-        uint16_t *xo = reinterpret_cast<uint16_t *>(smem + SM::XOFF_OFF);
-        for (int i = tid; i < C::N; i += nth) xo[i] = tb.xoff[i];
+        if (need_mul) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(tb.mul);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + SM::MUL_OFF);
+            for (int i = tid; i < (int)(SM::MUL_SZ / 4); i += nth) dst[i] = src[i];
+            uint16_t *xo = reinterpret_cast<uint16_t *>(smem + SM::XOFF_OFF);
+            for (int i = tid; i < C::N; i += nth) xo[i] = tb.xoff[i];
+        }
         uint32_t *col = reinterpret_cast<uint32_t *>(smem + SM::COL_OFF);
         for (int i = tid; i < C::N * SM::SW; i += nth) col[i] = tb.hcol[i];
     } else {
@@ -409,203 +721,233 @@ struct PkWarpTotals {
     }
 };
 
-// ------------------------------------------------------------------ replay kernel
-template <int M, int T, bool LUT>
-__global__ void __launch_bounds__(PK_WARPS * 32)
-k_replay(PkDevTables tb, PkKanekoParams kp, const double *__restrict__ y, long B, uint8_t *__restrict__ decided,
-         uint32_t *__restrict__ trials, pk_frame_rec *__restrict__ recs, unsigned long long *totals,
-         unsigned long long *queue) {
-    typedef PkSmem<M, T, LUT> SM;
-    typedef KanekoWarp<M, T, LUT> KW;
-    constexpr int N = KW::N, NW = KW::NW;
-    extern __shared__ __align__(16) unsigned char smem[];
-    pk_stage_tables<M, T, LUT>(smem, tb);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *wb = smem + SM::LUT_OFF + pk_align16(SM::lut_sz(tb.nk)) + (size_t)warp * SM::W_SZ;
-    double *w_alpha = reinterpret_cast<double *>(wb + SM::W_ALPHA);
-    double *w_skey = reinterpret_cast<double *>(wb + SM::W_SKEY);
-    uint8_t *w_sidx = wb + SM::W_SIDX;
-    const uint8_t *s_mul = smem + SM::MUL_OFF;
-    const uint16_t *s_xoff = reinterpret_cast<const uint16_t *>(smem + SM::XOFF_OFF);
-    const uint32_t *s_col = reinterpret_cast<const uint32_t *>(smem + SM::COL_OFF);
-    const uint16_t *s_lut = reinterpret_cast<const uint16_t *>(smem + SM::LUT_OFF);
-
-    PkWarpTotals tot;
-    tot.clear();
-    const int grab = kp.frames_per_grab;
-    for (;;) {
-        unsigned long long f0 = 0;
-        if (lane == 0) f0 = atomicAdd(queue, (unsigned long long)grab);
-        f0 = __shfl_sync(PK_FULL, f0, 0);
-        if ((long)f0 >= B) break;
-        const long f1 = ((long)f0 + grab < B) ? (long)f0 + grab : B;
-        for (long f = (long)f0; f < f1; ++f) {
-            double yv[NW];
+// Frame f of SNR point s draws from Philox4x32-10 with key = seed and counter (f_lo, f_hi, block, s):
+// blocks 0.. hold the info bits (128 per block), blocks 0x100+q the Box-Muller pair of positions 2q, 2q+1.
+template <int M, int NW, bool GEN>
+__device__ __forceinline__ void pk_load_frame(const PkIo &io, const PkDevTables &tb, long f, double *stage, uint32_t *w_u,
+                                              bool dump, double (&yv)[NW], uint32_t (&CW)[NW]) {
+    constexpr int N = (1 << M) - 1;
+    const int lane = threadIdx.x & 31;
+    if constexpr (!GEN) {
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const int p = lane + 32 * w;
-                yv[w] = (p < N) ? __ldg(y + f * N + p) : 0.0;
-            }
-            typename KW::Result R;
-            KW::decode(s_mul, s_xoff, s_col, s_lut, w_alpha, w_skey, w_sidx, yv, kp, R);
-            if (!(R.flags & PK_FLAG_NO_DECISION)) {
+        for (int w = 0; w < NW; ++w) {
+            const int p = lane + 32 * w;
+            yv[w] = (p < N) ? __ldg(io.y + f * N + p) : 0.0;
+            CW[w] = 0;
+        }
+    } else {
+        const int K = tb.k, NK = tb.nk;
+        const uint32_t k0 = (uint32_t)io.gp.seed, k1 = (uint32_t)(io.gp.seed >> 32);
+        const unsigned long long gf = io.gp.first_frame + (unsigned long long)f;
+        const uint32_t c0 = (uint32_t)gf, c1 = (uint32_t)(gf >> 32);
+        // k information bits (generateRandomPoly, bchCoder.cpp:236-240)
+        uint32_t uw = 0;
+        if (lane * 32 < K) {
+            PkPhilox r = pk_philox(c0, c1, (uint32_t)(lane >> 2), io.gp.snr_index, k0, k1);
+            uw = r.c[lane & 3];
+            const int rem = K - lane * 32;
+            if (rem < 32) uw &= (1u << rem) - 1u;
+        }
+        if (lane <= NW) w_u[lane] = uw;
+        __syncwarp();
+        // c(x) = u(x) g(x) over GF(2) (multiplyPolynomials, bchCoder.cpp:120-132): XOR of (u << d) over the
+        // set coefficients g_d, d split across lanes, then one warp XOR-reduce per word.
+        uint32_t cwp[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) cwp[w] = 0;
+        for (int d = lane; d <= NK; d += 32) {
+            if ((tb.gmask[d >> 5] >> (d & 31)) & 1u) {
+                const int ws = d >> 5, bs = d & 31;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) {
-                    const int p = lane + 32 * w;
-                    if (p < N) decided[f * N + p] = (uint8_t)(((R.YH[w] ^ R.F[w]) >> lane) & 1u);
+                    const int lo = w - ws;
+                    const uint32_t a = (lo >= 0) ? w_u[lo] : 0u;
+                    const uint32_t b = (lo >= 1) ? w_u[lo - 1] : 0u;
+                    cwp[w] ^= __funnelshift_l(b, a, bs);
                 }
-            }
-            if (lane == 0) {
-                if (trials) trials[f] = R.trials;
-                if (recs) {
-                    pk_frame_rec r;
-                    r.trials = R.trials; r.extra_cmp = R.extra_cmp; r.extra_sum = R.extra_sum;
-                    r.bit_errors = 0; r.flags = (uint8_t)R.flags; r.reserved = 0;
-                    recs[f] = r;
-                }
-                tot.add(N, R.trials, R.extra_cmp, R.extra_sum, R.flags, 0);
             }
         }
-    }
-    if (lane == 0) tot.flush(totals);
-}
-
-// ------------------------------------------------------------------ generation kernel
-// Frame f of SNR point s draws from Philox4x32-10 with key = seed and counter
-// (f_lo, f_hi, block, s): blocks 0.. hold the info bits (128 per block), blocks
-// 0x100+q the Box-Muller pair for positions 2q, 2q+1.
-template <int M, int T, bool LUT>
-__global__ void __launch_bounds__(PK_WARPS * 32)
-k_generate(PkDevTables tb, PkKanekoParams kp, PkGenParams gp, long B, pk_frame_rec *__restrict__ recs,
-           unsigned long long *totals, unsigned long long *queue, uint8_t *__restrict__ d_info,
-           uint8_t *__restrict__ d_cw, double *__restrict__ d_y, int dump_only) {
-    typedef PkSmem<M, T, LUT> SM;
-    typedef KanekoWarp<M, T, LUT> KW;
-    constexpr int N = KW::N, NW = KW::NW;
-    extern __shared__ __align__(16) unsigned char smem[];
-    pk_stage_tables<M, T, LUT>(smem, tb);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *wb = smem + SM::LUT_OFF + pk_align16(SM::lut_sz(tb.nk)) + (size_t)warp * SM::W_SZ;
-    double *w_alpha = reinterpret_cast<double *>(wb + SM::W_ALPHA);
-    double *w_skey = reinterpret_cast<double *>(wb + SM::W_SKEY);
-    uint8_t *w_sidx = wb + SM::W_SIDX;
-    uint32_t *w_u = reinterpret_cast<uint32_t *>(wb + SM::W_U);
-    const uint8_t *s_mul = smem + SM::MUL_OFF;
-    const uint16_t *s_xoff = reinterpret_cast<const uint16_t *>(smem + SM::XOFF_OFF);
-    const uint32_t *s_col = reinterpret_cast<const uint32_t *>(smem + SM::COL_OFF);
-    const uint16_t *s_lut = reinterpret_cast<const uint16_t *>(smem + SM::LUT_OFF);
-    const int K = tb.k, NK = tb.nk;
-    const uint32_t k0 = (uint32_t)gp.seed, k1 = (uint32_t)(gp.seed >> 32);
-    uint32_t gm[NW];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) gm[w] = tb.gmask[w];
-
-    PkWarpTotals tot;
-    tot.clear();
-    const int grab = kp.frames_per_grab;
-    for (;;) {
-        unsigned long long f0 = 0;
-        if (lane == 0) f0 = atomicAdd(queue, (unsigned long long)grab);
-        f0 = __shfl_sync(PK_FULL, f0, 0);
-        if ((long)f0 >= B) break;
-        const long f1 = ((long)f0 + grab < B) ? (long)f0 + grab : B;
-        for (long f = (long)f0; f < f1; ++f) {
-            const unsigned long long gf = gp.first_frame + (unsigned long long)f;
-            const uint32_t c0 = (uint32_t)gf, c1 = (uint32_t)(gf >> 32);
-            // ---- k information bits (generateRandomPoly, bchCoder.cpp:236-240)
-            uint32_t uw = 0;
-            if (lane * 32 < K) {
-                PkPhilox r = pk_philox(c0, c1, (uint32_t)(lane >> 2), gp.snr_index, k0, k1);
-                uw = r.c[lane & 3];
-                const int rem = K - lane * 32;
-                if (rem < 32) uw &= (1u << rem) - 1u;
-            }
-            if (lane <= NW) w_u[lane] = uw;   // lane < 32 always >= NW+1 entries
-            __syncwarp();
-            // ---- c(x) = u(x) g(x) over GF(2) (multiplyPolynomials, bchCoder.cpp:120-132):
-            // XOR of (u << d) over the set coefficients g_d, d split across lanes.
-            uint32_t cwp[NW];
+        for (int w = 0; w < NW; ++w) CW[w] = __reduce_xor_sync(PK_FULL, cwp[w]);
+        // BPSK + AWGN (addNoise, bchCoder.cpp:243-250): y = (c ? +1 : -1) + N(0, sigma^2), f64 Box-Muller
+        for (int q = lane; 2 * q < N; q += 32) {
+            PkPhilox r = pk_philox(c0, c1, 0x100u + (uint32_t)q, io.gp.snr_index, k0, k1);
+            const unsigned long long a = ((unsigned long long)r.c[0] << 32) | r.c[1];
+            const unsigned long long b = ((unsigned long long)r.c[2] << 32) | r.c[3];
+            const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);   // (0,1]
+            const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);           // [0,1)
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+            const int p0 = 2 * q, p1 = 2 * q + 1;
+            stage[p0] = (pk_getbit<NW>(CW, p0) ? 1.0 : -1.0) + io.gp.sigma * (rad * cs);
+            if (p1 < N) stage[p1] = (pk_getbit<NW>(CW, p1) ? 1.0 : -1.0) + io.gp.sigma * (rad * sn);
+        }
+        __syncwarp();
 #pragma unroll
-            for (int w = 0; w < NW; ++w) cwp[w] = 0;
-            for (int d = lane; d <= NK; d += 32) {
-                if ((gm[d >> 5] >> (d & 31)) & 1u) {
-                    const int ws = d >> 5, bs = d & 31;
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) {
-                        const int lo = w - ws;
-                        const uint32_t a = (lo >= 0) ? w_u[lo] : 0u;
-                        const uint32_t b = (lo >= 1) ? w_u[lo - 1] : 0u;
-                        cwp[w] ^= __funnelshift_l(b, a, bs);
-                    }
-                }
-            }
-            uint32_t CW[NW];
-#pragma unroll
-            for (int w = 0; w < NW; ++w) CW[w] = __reduce_xor_sync(PK_FULL, cwp[w]);
-            // ---- BPSK + AWGN (addNoise, bchCoder.cpp:243-250): y = (c ? +1 : -1) + N(0, sigma^2)
-            for (int q = lane; 2 * q < N; q += 32) {
-                PkPhilox r = pk_philox(c0, c1, 0x100u + (uint32_t)q, gp.snr_index, k0, k1);
-                const unsigned long long a = ((unsigned long long)r.c[0] << 32) | r.c[1];
-                const unsigned long long b = ((unsigned long long)r.c[2] << 32) | r.c[3];
-                const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);   // (0,1]
-                const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);           // [0,1)
-                const double rad = sqrt(-2.0 * log(u1));
-                double sn, cs;
-                sincospi(2.0 * u2, &sn, &cs);
-                const int p0 = 2 * q, p1 = 2 * q + 1;
-                const double b0 = ((CW[p0 >> 5] >> (p0 & 31)) & 1u) ? 1.0 : -1.0;
-                w_skey[p0] = b0 + gp.sigma * (rad * cs);
-                if (p1 < N) {
-                    const double b1 = pk_getbit<NW>(CW, p1) ? 1.0 : -1.0;
-                    w_skey[p1] = b1 + gp.sigma * (rad * sn);
-                }
-            }
-            __syncwarp();
-            double yv[NW];
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const int p = lane + 32 * w;
-                yv[w] = (p < N) ? w_skey[p] : 0.0;
-            }
-            __syncwarp();
-            if (d_info) {
-                for (int i = lane; i < K; i += 32) d_info[f * K + i] = (uint8_t)((w_u[i >> 5] >> (i & 31)) & 1u);
+        for (int w = 0; w < NW; ++w) {
+            const int p = lane + 32 * w;
+            yv[w] = (p < N) ? stage[p] : 0.0;
+        }
+        __syncwarp();
+        if (dump) {
+            if (io.d_info) {
+                for (int i = lane; i < K; i += 32) io.d_info[f * K + i] = (uint8_t)((w_u[i >> 5] >> (i & 31)) & 1u);
             }
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const int p = lane + 32 * w;
                 if (p < N) {
-                    if (d_cw) d_cw[f * N + p] = (uint8_t)((CW[w] >> lane) & 1u);
-                    if (d_y) d_y[f * N + p] = yv[w];
+                    if (io.d_cw) io.d_cw[f * N + p] = (uint8_t)((CW[w] >> lane) & 1u);
+                    if (io.d_y) io.d_y[f * N + p] = yv[w];
                 }
-            }
-            __syncwarp();
-            if (dump_only) continue;
-
-            typename KW::Result R;
-            KW::decode(s_mul, s_xoff, s_col, s_lut, w_alpha, w_skey, w_sidx, yv, kp, R);
-            // ---- compare with the transmitted word (dataForPlot.cpp:66-73)
-            uint32_t be = 0;
-            if (!(R.flags & PK_FLAG_NO_DECISION)) {
-#pragma unroll
-                for (int w = 0; w < NW; ++w) be += __popc(R.YH[w] ^ R.F[w] ^ CW[w]);
-            } else {
-#pragma unroll
-                for (int w = 0; w < NW; ++w) be += __popc(CW[w]);   // undecided buffer counted as all-zero
-            }
-            uint32_t fl = R.flags | (be ? PK_FLAG_FRAME_ERROR : 0);
-            if (lane == 0) {
-                if (recs) {
-                    pk_frame_rec r;
-                    r.trials = R.trials; r.extra_cmp = R.extra_cmp; r.extra_sum = R.extra_sum;
-                    r.bit_errors = (uint16_t)be; r.flags = (uint8_t)fl; r.reserved = 0;
-                    recs[f] = r;
-                }
-                tot.add(N, R.trials, R.extra_cmp, R.extra_sum, fl, be);
             }
         }
+        __syncwarp();
     }
-    if (lane == 0) tot.flush(totals);
+}
+
+// finished frame -> outputs (replay: decisions + trial count; generation: compare with the sent word,
+// dataForPlot.cpp:66-73) and the warp's running totals
+template <int M, int NW, bool GEN>
+__device__ __forceinline__ void pk_emit(const PkIo &io, long f, const uint32_t (&YH)[NW], const uint32_t (&bestF)[NW],
+                                        const uint32_t (&CW)[NW], uint32_t trials, uint32_t ecmp, uint32_t esum,
+                                        uint32_t flags, PkWarpTotals &tot) {
+    constexpr int N = (1 << M) - 1;
+    const int lane = threadIdx.x & 31;
+    uint32_t be = 0;
+    if constexpr (!GEN) {
+        if (!(flags & PK_FLAG_NO_DECISION)) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const int p = lane + 32 * w;
+                if (p < N) io.decided[f * N + p] = (uint8_t)(((YH[w] ^ bestF[w]) >> lane) & 1u);
+            }
+        }
+        if (lane == 0 && io.trials) io.trials[f] = trials;
+    } else {
+        if (!(flags & PK_FLAG_NO_DECISION)) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) be += __popc(YH[w] ^ bestF[w] ^ CW[w]);
+        } else {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) be += __popc(CW[w]);   // undecided buffer counted as all-zero
+        }
+        flags |= be ? PK_FLAG_FRAME_ERROR : 0;
+    }
+    if (lane == 0) {
+        if (io.recs) {
+            pk_frame_rec r;
+            r.trials = trials; r.extra_cmp = ecmp; r.extra_sum = esum;
+            r.bit_errors = (uint16_t)be; r.flags = (uint8_t)flags; r.reserved = 0;
+            io.recs[f] = r;
+        }
+        tot.add(N, trials, ecmp, esum, flags, be);
+    }
+}
+
+// ------------------------------------------------------------------ phase A
+template <int M, int T, bool LUT, bool GEN>
+__global__ void __launch_bounds__(PK_WARPS_A * 32)
+k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, PkLongRec *longs, long long_cap) {
+    typedef PkSmem<M, T, LUT> SM;
+    typedef KanekoWarp<M, T, LUT> KW;
+    constexpr int NW = KW::NW;
+    extern __shared__ __align__(16) unsigned char smem[];
+    pk_stage_tables<M, T, LUT>(smem, tb, true);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wb = smem + SM::tables(tb.nk) + (size_t)warp * SM::W_SZ_A;
+    typename KW::WarpMem wm = KW::warp_mem(wb);
+    uint32_t *w_u = reinterpret_cast<uint32_t *>(wb + SM::W_U);
+    typename KW::Tables tabs;
+    tabs.mul = smem + SM::MUL_OFF;
+    tabs.xoff = reinterpret_cast<const uint16_t *>(smem + SM::XOFF_OFF);
+    tabs.col = reinterpret_cast<const uint32_t *>(smem + SM::COL_OFF);
+    tabs.lut = reinterpret_cast<const uint16_t *>(smem + SM::LUT_OFF);
+    // frames are parked only when a wide kernel exists for this code (long_cap > 0 says so)
+    const uint32_t limit = (long_cap > 0) ? PK_LIMIT_A : 0xFFFFFFFFu;
+
+    PkWarpTotals tot;
+    tot.clear();
+    const int grab = kp.frames_per_grab;
+    for (;;) {
+        unsigned long long f0 = 0;
+        if (lane == 0) f0 = atomicAdd(&ctl->queue_a, (unsigned long long)grab);
+        f0 = __shfl_sync(PK_FULL, f0, 0);
+        if ((long)f0 >= B) break;
+        const long f1 = ((long)f0 + grab < B) ? (long)f0 + grab : B;
+        for (long f = (long)f0; f < f1; ++f) {
+            double yv[NW];
+            uint32_t CW[NW];
+            pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, true, yv, CW);
+            if (GEN && io.dump_only) continue;
+            typename KW::Frame fr;
+            typename KW::Search s;
+            KW::setup(tabs, wm, yv, kp, fr);
+            KW::search_init(s, fr);
+            uint32_t next = 0;
+            bool done = KW::narrow(tabs, wm, kp, fr, s, 0u, limit, &next);
+            if (!done) {
+                unsigned long long slot = 0;
+                if (lane == 0) slot = atomicAdd(&ctl->n_long, 1ull);
+                slot = __shfl_sync(PK_FULL, slot, 0);
+                if ((long)slot < long_cap) {
+                    if (lane == 0) KW::park(s, (uint32_t)f, next, longs + slot);
+                    continue;
+                }
+                // list full: finish here (phase B ignores slots >= long_cap)
+                KW::narrow(tabs, wm, kp, fr, s, next, 0xFFFFFFFFu, &next);
+            }
+            KW::search_finish(s);
+            pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr, s.tsteps, s.flags, tot);
+        }
+    }
+    if (lane == 0) tot.flush(io.totals);
+}
+
+// ------------------------------------------------------------------ phase B
+template <int M, int T, bool LUT, bool GEN>
+__global__ void __launch_bounds__(PK_WARPS_B * 32, 3)
+k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkLongRec *longs, long long_cap) {
+    typedef PkSmem<M, T, LUT> SM;
+    typedef KanekoWarp<M, T, LUT> KW;
+    constexpr int NW = KW::NW;
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long n_long = ctl->n_long;
+    if ((long)n_long > long_cap) n_long = (unsigned long long)long_cap;
+    if (n_long == 0) return;
+    pk_stage_tables<M, T, LUT>(smem, tb, false);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wb = smem + SM::tables(tb.nk) + (size_t)warp * SM::W_SZ_B;
+    typename KW::WarpMem wm = KW::warp_mem(wb);
+    uint32_t *w_u = reinterpret_cast<uint32_t *>(wb + SM::W_U);
+    typename KW::Tables tabs;
+    tabs.mul = smem + SM::MUL_OFF;
+    tabs.xoff = reinterpret_cast<const uint16_t *>(smem + SM::XOFF_OFF);
+    tabs.col = reinterpret_cast<const uint32_t *>(smem + SM::COL_OFF);
+    tabs.lut = reinterpret_cast<const uint16_t *>(smem + SM::LUT_OFF);
+
+    PkWarpTotals tot;
+    tot.clear();
+    for (;;) {
+        unsigned long long idx = 0;
+        if (lane == 0) idx = atomicAdd(&ctl->queue_b, 1ull);
+        idx = __shfl_sync(PK_FULL, idx, 0);
+        if (idx >= n_long) break;
+        const PkLongRec *rec = longs + idx;
+        const long f = (long)rec->frame;
+        double yv[NW];
+        uint32_t CW[NW];
+        pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, false, yv, CW);   // dumps were written in phase A
+        typename KW::Frame fr;
+        typename KW::Search s;
+        KW::setup(tabs, wm, yv, kp, fr);
+        KW::unpark(s, rec);
+        KW::wide(tabs, wm, kp, fr, s, rec->base);
+        KW::search_finish(s);
+        pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr, s.tsteps, s.flags, tot);
+    }
+    if (lane == 0) tot.flush(io.totals);
 }
 
 // ------------------------------------------------------------------ algebraic decoder alone
@@ -617,7 +959,7 @@ k_bdd(PkDevTables tb, const uint8_t *__restrict__ words, long B, uint8_t *__rest
     typedef PkSmem<M, T, false> SM;
     typedef PkCfg<M, T> C;
     extern __shared__ __align__(16) unsigned char smem[];
-    pk_stage_tables<M, T, false>(smem, tb);
+    pk_stage_tables<M, T, false>(smem, tb, true);
     const uint8_t *s_mul = smem + SM::MUL_OFF;
     const uint16_t *s_xoff = reinterpret_cast<const uint16_t *>(smem + SM::XOFF_OFF);
     const uint32_t *s_col = reinterpret_cast<const uint32_t *>(smem + SM::COL_OFF);
@@ -690,43 +1032,55 @@ k_encode(PkDevTables tb, const uint8_t *__restrict__ info, long B, uint8_t *__re
 template <int M, int T>
 struct PkLaunch {
     typedef PkCfg<M, T> C;
+    typedef PkTraits<M, T> TR;
 
     static bool host_alg(const uint32_t *Sw, const uint8_t *mul, const uint16_t *xoff, uint32_t *A) {
         return pk_alg_decode<M, T>(Sw, mul, xoff, A);
     }
 
-    template <bool LUT>
-    static cudaError_t geom_k(int nk, int sm_count, PkLaunchGeom *out) {
-        const size_t smem = PkSmem<M, T, LUT>::total(nk, PK_WARPS);
-        cudaError_t e = cudaFuncSetAttribute(k_replay<M, T, LUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    template <bool LUT, bool GEN>
+    static cudaError_t geom_one(int nk, int sm_count, PkLaunchGeom *ga, PkLaunchGeom *gb) {
+        const size_t sa = PkSmem<M, T, LUT>::total_a(nk);
+        cudaError_t e = cudaFuncSetAttribute(k_phase_a<M, T, LUT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_generate<M, T, LUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_phase_a<M, T, LUT, GEN>, PK_WARPS_A * 32, sa);
         if (e != cudaSuccess) return e;
-        int per_sm_a = 0, per_sm_b = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_replay<M, T, LUT>, PK_WARPS * 32, smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_generate<M, T, LUT>, PK_WARPS * 32, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm_a < 1 || per_sm_b < 1) return cudaErrorLaunchOutOfResources;
-        // persistent grids: every resident slot of every SM; out[0] = replay, out[1] = generate
-        out[0].grid = sm_count * per_sm_a;
-        out[1].grid = sm_count * per_sm_b;
-        out[0].block = out[1].block = PK_WARPS * 32;
-        out[0].smem = out[1].smem = smem;
+        if (per < 1) return cudaErrorLaunchOutOfResources;
+        ga->grid = sm_count * per;      // persistent: every resident slot of every SM
+        ga->block = PK_WARPS_A * 32;
+        ga->smem = sa;
+        gb->grid = 0; gb->block = PK_WARPS_B * 32; gb->smem = 0;
+        if constexpr (LUT || TR::BS_OK) {
+            const size_t sb = PkSmem<M, T, LUT>::total_b(nk);
+            e = cudaFuncSetAttribute(k_phase_b<M, T, LUT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_phase_b<M, T, LUT, GEN>, PK_WARPS_B * 32, sb);
+            if (e != cudaSuccess) return e;
+            if (per < 1) return cudaErrorLaunchOutOfResources;
+            gb->grid = sm_count * per;
+            gb->smem = sb;
+        }
         return cudaSuccess;
     }
-    // coset-table kernels exist only where the u16 entry (t positions of m bits + flag) fits
-    static constexpr bool LUT_OK = (T * M <= 15);
+    // out[0..1] = replay phase A / B, out[2..3] = generation phase A / B
     static cudaError_t geom_kaneko(bool lut, int nk, int sm_count, PkLaunchGeom *out) {
-        if constexpr (LUT_OK) {
-            if (lut) return geom_k<true>(nk, sm_count, out);
+        cudaError_t e;
+        if constexpr (TR::LUT_OK) {
+            if (lut) {
+                e = geom_one<true, false>(nk, sm_count, out + 0, out + 1);
+                if (e != cudaSuccess) return e;
+                return geom_one<true, true>(nk, sm_count, out + 2, out + 3);
+            }
         } else {
             if (lut) return cudaErrorInvalidValue;
         }
-        return geom_k<false>(nk, sm_count, out);
+        e = geom_one<false, false>(nk, sm_count, out + 0, out + 1);
+        if (e != cudaSuccess) return e;
+        return geom_one<false, true>(nk, sm_count, out + 2, out + 3);
     }
     static cudaError_t geom_bdd(int sm_count, PkLaunchGeom *out) {
-        const size_t smem = PkSmem<M, T, false>::total(0, 0);
+        const size_t smem = PkSmem<M, T, false>::tables(0);
         cudaError_t e = cudaFuncSetAttribute(k_bdd<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
@@ -739,41 +1093,36 @@ struct PkLaunch {
         return cudaSuccess;
     }
 
-    static cudaError_t replay(bool lut, const PkLaunchGeom &g, const PkDevTables &tb, const PkKanekoParams &kp,
-                              const double *d_y, long B, uint8_t *d_decided, uint32_t *d_trials, pk_frame_rec *d_recs,
-                              unsigned long long *d_totals, unsigned int *d_queue, cudaStream_t st) {
-        unsigned long long *q = reinterpret_cast<unsigned long long *>(d_queue);
-        cudaError_t e = cudaMemsetAsync(q, 0, sizeof(unsigned long long), st);
+    template <bool LUT, bool GEN>
+    static cudaError_t run(const PkLaunchGeom *g, const PkDevTables &tb, const PkKanekoParams &kp, const PkIo &io, long B,
+                           PkPhaseCtl *ctl, PkLongRec *longs, long long_cap, cudaStream_t st) {
+        cudaError_t e = cudaMemsetAsync(ctl, 0, sizeof(PkPhaseCtl), st);
         if (e != cudaSuccess) return e;
-        if constexpr (LUT_OK) {
-            if (lut) {
-                k_replay<M, T, true><<<g.grid, g.block, g.smem, st>>>(tb, kp, d_y, B, d_decided, d_trials, d_recs, d_totals, q);
+        const bool wide_ok = (LUT || TR::BS_OK) && g[1].grid > 0 && long_cap > 0 && !(GEN && io.dump_only);
+        k_phase_a<M, T, LUT, GEN><<<g[0].grid, g[0].block, g[0].smem, st>>>(tb, kp, io, B, ctl, longs, wide_ok ? long_cap : 0);
+        ++g_pk_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if constexpr (LUT || TR::BS_OK) {
+            if (wide_ok) {
+                k_phase_b<M, T, LUT, GEN><<<g[1].grid, g[1].block, g[1].smem, st>>>(tb, kp, io, ctl, longs, long_cap);
                 ++g_pk_launches;
-                return cudaGetLastError();
+                e = cudaGetLastError();
             }
         }
-        k_replay<M, T, false><<<g.grid, g.block, g.smem, st>>>(tb, kp, d_y, B, d_decided, d_trials, d_recs, d_totals, q);
-        ++g_pk_launches;
-        return cudaGetLastError();
+        return e;
     }
-    static cudaError_t generate(bool lut, const PkLaunchGeom &g, const PkDevTables &tb, const PkKanekoParams &kp,
-                                const PkGenParams &gp, long B, pk_frame_rec *d_recs, unsigned long long *d_totals,
-                                unsigned int *d_queue, uint8_t *d_info, uint8_t *d_cw, double *d_y, int dump_only,
-                                cudaStream_t st) {
-        unsigned long long *q = reinterpret_cast<unsigned long long *>(d_queue);
-        cudaError_t e = cudaMemsetAsync(q, 0, sizeof(unsigned long long), st);
-        if (e != cudaSuccess) return e;
-        if constexpr (LUT_OK) {
-            if (lut) {
-                k_generate<M, T, true><<<g.grid, g.block, g.smem, st>>>(tb, kp, gp, B, d_recs, d_totals, q, d_info, d_cw, d_y, dump_only);
-                ++g_pk_launches;
-                return cudaGetLastError();
-            }
+    static cudaError_t kaneko(bool lut, bool gen, const PkLaunchGeom *g4, const PkDevTables &tb, const PkKanekoParams &kp,
+                              const PkIo &io, long B, PkPhaseCtl *ctl, PkLongRec *longs, long long_cap, cudaStream_t st) {
+        const PkLaunchGeom *g = g4 + (gen ? 2 : 0);
+        if constexpr (TR::LUT_OK) {
+            if (lut) return gen ? run<true, true>(g, tb, kp, io, B, ctl, longs, long_cap, st)
+                                : run<true, false>(g, tb, kp, io, B, ctl, longs, long_cap, st);
         }
-        k_generate<M, T, false><<<g.grid, g.block, g.smem, st>>>(tb, kp, gp, B, d_recs, d_totals, q, d_info, d_cw, d_y, dump_only);
-        ++g_pk_launches;
-        return cudaGetLastError();
+        return gen ? run<false, true>(g, tb, kp, io, B, ctl, longs, long_cap, st)
+                   : run<false, false>(g, tb, kp, io, B, ctl, longs, long_cap, st);
     }
+
     static cudaError_t bdd(const PkLaunchGeom &g, const PkDevTables &tb, const uint8_t *d_words, long B,
                            uint8_t *d_answers, uint8_t *d_ok, cudaStream_t st) {
         long need = (B + g.block - 1) / g.block;
@@ -791,6 +1140,6 @@ struct PkLaunch {
     }
 
     static constexpr PkKernelSet make() {
-        return PkKernelSet{M, T, &host_alg, &geom_kaneko, &geom_bdd, &replay, &generate, &bdd, &encode};
+        return PkKernelSet{M, T, TR::BS_OK, &host_alg, &geom_kaneko, &geom_bdd, &kaneko, &bdd, &encode};
     }
 };

@@ -23,6 +23,37 @@ struct PkGenParams {
     uint32_t snr_index;
 };
 
+// Where frames come from / go to (one launch pair).
+struct PkIo {
+    // replay mode
+    const double *y;
+    uint8_t *decided;
+    uint32_t *trials;
+    // generation mode
+    PkGenParams gp;
+    uint8_t *d_info, *d_cw;
+    double *d_y;
+    int dump_only;
+    // both
+    pk_frame_rec *recs;
+    unsigned long long *totals;
+};
+
+// A frame parked by phase A for the wide search of phase B.
+struct PkLongRec {
+    double l0;
+    uint32_t frame, base, bound, m0;
+    uint32_t tsteps, nimpr, sflags, pad;   // sflags: bit0 first_ok, bit1 have, bits 8.. = frame flags
+    uint32_t bestF[8];
+};
+// Device-side control block of one phase A / phase B launch pair (zeroed by the launcher).
+struct PkPhaseCtl {
+    unsigned long long queue_a;     // next frame of phase A
+    unsigned long long queue_b;     // next parked frame of phase B
+    unsigned long long n_long;      // parked frames
+    unsigned long long pad;
+};
+
 struct PkLaunchGeom {
     int grid, block;
     size_t smem;
@@ -30,21 +61,17 @@ struct PkLaunchGeom {
 
 struct PkKernelSet {
     int m, t;
+    bool has_bitsliced;   // phase B runs the bit-sliced decoder (pk_bs.cuh) for this code
     // host instance of the algebraic decoder (coset-table construction)
     bool (*host_alg_decode)(const uint32_t *, const uint8_t *, const uint16_t *, uint32_t *);
-    // geometry (queries the device once; sets the dynamic shared-memory attribute)
-    cudaError_t (*geom_kaneko)(bool lut, int nk, int sm_count, PkLaunchGeom *out /*[2]: replay, generate*/);
+    // geometry (queries the device once; sets the dynamic shared-memory attributes):
+    // out[0..1] = replay phase A / B, out[2..3] = generation phase A / B (grid 0 = no such kernel)
+    cudaError_t (*geom_kaneko)(bool lut, int nk, int sm_count, PkLaunchGeom *out);
     cudaError_t (*geom_bdd)(int sm_count, PkLaunchGeom *out);
-    // Kaneko decode of B frames from y (replay mode).  queue: device u32 zeroed by the callee.
-    cudaError_t (*launch_replay)(bool lut, const PkLaunchGeom &g, const PkDevTables &tb, const PkKanekoParams &kp,
-                                 const double *d_y, long B, uint8_t *d_decided, uint32_t *d_trials,
-                                 pk_frame_rec *d_recs, unsigned long long *d_totals, unsigned int *d_queue,
-                                 cudaStream_t st);
-    // generate + encode + AWGN + decode + compare (generation mode)
-    cudaError_t (*launch_generate)(bool lut, const PkLaunchGeom &g, const PkDevTables &tb, const PkKanekoParams &kp,
-                                   const PkGenParams &gp, long B, pk_frame_rec *d_recs,
-                                   unsigned long long *d_totals, unsigned int *d_queue,
-                                   uint8_t *d_info, uint8_t *d_cw, double *d_y, int dump_only, cudaStream_t st);
+    // Kaneko decode of B frames: phase A (+ phase B when a wide kernel exists and long_cap > 0)
+    cudaError_t (*launch_kaneko)(bool lut, bool gen, const PkLaunchGeom *g4, const PkDevTables &tb,
+                                 const PkKanekoParams &kp, const PkIo &io, long B, PkPhaseCtl *ctl, PkLongRec *longs,
+                                 long long_cap, cudaStream_t st);
     // algebraic decoder alone, one thread per word
     cudaError_t (*launch_bdd)(const PkLaunchGeom &g, const PkDevTables &tb, const uint8_t *d_words, long B,
                               uint8_t *d_answers, uint8_t *d_ok, cudaStream_t st);
