@@ -106,6 +106,9 @@ int pk_kaneko_create(pk_code *code, double llr_snr_db, long J, long max_trials, 
 void pk_kaneko_destroy(pk_kaneko *dec);
 /* tuning / introspection */
 int pk_kaneko_set_frames_per_grab(pk_kaneko *dec, int frames);
+/* trials (multiple of 32) a frame may spend in the narrow phase-A search before it is handed to the
+ * wide phase-B search (1024 patterns per warp step); tuning only, results do not depend on it */
+int pk_kaneko_set_phase_a_limit(pk_kaneko *dec, long trials);
 int pk_kaneko_launch_geometry(const pk_kaneko *dec, int *grid, int *block, long *smem_bytes);
 
 /* Replay mode, host buffers: decode(answer, word, res) for B frames

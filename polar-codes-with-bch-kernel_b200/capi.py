@@ -29,7 +29,7 @@ POINT_FIELDS = ("frames", "frame_errors", "bit_errors", "trials", "cmp", "sum", 
 SYMBOLS = (
     "pk_last_error pk_device_count pk_code_create pk_code_create_host pk_code_destroy pk_code_info pk_code_tables "
     "pk_code_uses_lut pk_code_set_lut pk_code_coset_table pk_encode_batch pk_bch_decode_batch pk_kaneko_create "
-    "pk_kaneko_destroy pk_kaneko_set_frames_per_grab pk_kaneko_launch_geometry pk_kaneko_decode_batch "
+    "pk_kaneko_destroy pk_kaneko_set_frames_per_grab pk_kaneko_set_phase_a_limit pk_kaneko_launch_geometry pk_kaneko_decode_batch "
     "pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames pk_generate_frames_dev "
     "pk_kaneko_run_point pk_make_kernel_matrix pk_launch_count pk_launch_count_reset"
 ).split()
@@ -68,6 +68,7 @@ def _load():
     lib.pk_kaneko_destroy.argtypes = [vp]
     lib.pk_kaneko_destroy.restype = None
     lib.pk_kaneko_set_frames_per_grab.argtypes = [vp, i]
+    lib.pk_kaneko_set_phase_a_limit.argtypes = [vp, l]
     lib.pk_kaneko_launch_geometry.argtypes = [vp, ip, ip, C.POINTER(l)]
     lib.pk_kaneko_decode_batch.argtypes = [vp, vp, l, vp, vp, vp, vp]
     lib.pk_kaneko_decode_batch_dev.argtypes = [vp, vp, l, vp, vp, vp, vp, vp]
@@ -189,6 +190,9 @@ class Kaneko:
 
     def set_frames_per_grab(self, g):
         _check(lib.pk_kaneko_set_frames_per_grab(self.h, int(g)))
+
+    def set_phase_a_limit(self, trials):
+        _check(lib.pk_kaneko_set_phase_a_limit(self.h, int(trials)))
 
     def geometry(self):
         g, b, s = C.c_int(), C.c_int(), C.c_long()

@@ -87,7 +87,9 @@ struct PkBsChienStep<M, T, T + 1> {
 // Z  : out, Z[p * zstride] = word whose bit q is set iff Lambda_q(alpha^{-p}) == 0 (position p is
 //      located for trial q); written for every p in [0, N).
 // returns the word of verdicts (bit q = Decoder::decode() of trial q).
-template <int M, int T, class SFn>
+// LOOP = true: the t Berlekamp-Massey steps run as ONE loop body (fits the 32 KB instruction cache; products
+// known to be zero are skipped by warp-uniform branches); LOOP = false: fully unrolled (more constant folding).
+template <int M, int T, bool LOOP, class SFn>
 PK_HD uint32_t pk_bs_decode(SFn getS, uint32_t *Z, int zstride) {
     constexpr int N = PkGF<M>::N;
     constexpr int LB = (2 * T < 2) ? 1 : (2 * T < 4) ? 2 : (2 * T < 8) ? 3 : (2 * T < 16) ? 4 : 5;   // bits of L <= 2T
@@ -104,6 +106,78 @@ PK_HD uint32_t pk_bs_decode(SFn getS, uint32_t *Z, int zstride) {
 #pragma unroll
     for (int b = 0; b < LB; ++b) Lb[b] = 0;
 
+    if constexpr (LOOP) {
+#pragma unroll 1
+        for (int it = 0; it < T; ++it) {
+            const int r = 2 * it + 1;
+            // B <- x*B for step r
+#pragma unroll
+            for (int k = T; k >= 1; --k)
+#pragma unroll
+                for (int b = 0; b < M; ++b) Bp[k][b] = Bp[k - 1][b];
+#pragma unroll
+            for (int b = 0; b < M; ++b) Bp[0][b] = 0;
+            const int dl = (r - 1 < T) ? r - 1 : T;   // deg Lambda <= dl, deg x^s B and new Lambda <= du
+            const int du = (r < T) ? r : T;
+            uint32_t acc[2 * M - 1], delta[M];
+#pragma unroll
+            for (int b = 0; b < 2 * M - 1; ++b) acc[b] = 0;
+#pragma unroll
+            for (int k = 0; k <= T; ++k) {
+                if (k <= dl) {   // warp-uniform: skips the products known to be zero
+                    uint32_t sj[M];
+                    getS(r - k, sj);
+                    pk_bs_mac<M>(acc, Lam[k], sj);
+                }
+            }
+            pk_bs_reduce<M>(acc);
+            uint32_t nz = 0;
+#pragma unroll
+            for (int b = 0; b < M; ++b) { delta[b] = acc[b]; nz |= acc[b]; }
+            // 2L <= r-1  <=>  L <= it
+            uint32_t lt = 0, eq = ~0u;
+#pragma unroll
+            for (int b = LB - 1; b >= 0; --b) {
+                const uint32_t cb = 0u - (uint32_t)((it >> b) & 1);
+                lt |= eq & ~Lb[b] & cb;
+                eq &= ~(Lb[b] ^ cb);
+            }
+            const uint32_t upd = nz & (lt | eq);
+#pragma unroll
+            for (int k = 0; k <= T; ++k) {
+                if (k <= du) {
+#pragma unroll
+                    for (int b = 0; b < 2 * M - 1; ++b) acc[b] = 0;
+                    pk_bs_mac<M>(acc, gamma, Lam[k]);
+                    pk_bs_mac<M>(acc, delta, Bp[k]);
+                    pk_bs_reduce<M>(acc);
+#pragma unroll
+                    for (int b = 0; b < M; ++b) {
+                        Bp[k][b] = (Bp[k][b] & ~upd) | (Lam[k][b] & upd);
+                        Lam[k][b] = acc[b];
+                    }
+                }
+            }
+            uint32_t carry = ~0u;   // L <- upd ? r - L : L
+#pragma unroll
+            for (int b = 0; b < LB; ++b) {
+                const uint32_t rb = 0u - (uint32_t)((r >> b) & 1);
+                const uint32_t nl = ~Lb[b];
+                const uint32_t sum = rb ^ nl ^ carry;
+                carry = (rb & nl) | (carry & (rb ^ nl));
+                Lb[b] = (Lb[b] & ~upd) | (sum & upd);
+            }
+#pragma unroll
+            for (int b = 0; b < M; ++b) gamma[b] = (gamma[b] & ~upd) | (delta[b] & upd);
+            // B <- x*B for the even step r+1 (its discrepancy is zero for a binary code)
+#pragma unroll
+            for (int k = T; k >= 1; --k)
+#pragma unroll
+                for (int b = 0; b < M; ++b) Bp[k][b] = Bp[k - 1][b];
+#pragma unroll
+            for (int b = 0; b < M; ++b) Bp[0][b] = 0;
+        }
+    } else {
 #pragma unroll
     for (int r = 1; r <= 2 * T; ++r) {
 #pragma unroll
@@ -163,6 +237,7 @@ PK_HD uint32_t pk_bs_decode(SFn getS, uint32_t *Z, int zstride) {
 #pragma unroll
             for (int b = 0; b < M; ++b) gamma[b] = (gamma[b] & ~upd) | (delta[b] & upd);
         }
+    }
     }
     // L <= T
     uint32_t okL;

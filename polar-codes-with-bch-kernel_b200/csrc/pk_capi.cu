@@ -265,6 +265,10 @@ int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_
     d->kp.J = (J < 0 || J >= c->n) ? -1 : (int)J;
     d->kp.max_trials = (max_trials <= 0 || max_trials > 0x7FFFFFFFL) ? 0x7FFFFFFFu : (uint32_t)max_trials;
     d->kp.frames_per_grab = 2;
+    // a narrow BM+Chien step (32 trials) costs about as much latency as a bit-sliced wide step (1024 trials),
+    // so those frames move to phase B almost at once; coset-table steps are cheap and stay longer
+    d->kp.limit_a = c->use_lut ? 256u : 64u;
+    d->kp.big_span = 8192u;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, c->device);
     if (e == cudaSuccess) e = c->ks->geom_kaneko(c->use_lut, c->nk, prop.multiProcessorCount, d->geom4);
@@ -300,6 +304,12 @@ void pk_kaneko_destroy(pk_kaneko *d) {
 int pk_kaneko_set_frames_per_grab(pk_kaneko *d, int g) {
     if (!d || g < 1) return fail(PK_ERR_ARG, "bad argument");
     d->kp.frames_per_grab = g;
+    return PK_OK;
+}
+
+int pk_kaneko_set_phase_a_limit(pk_kaneko *d, long trials) {
+    if (!d || trials < 32) return fail(PK_ERR_ARG, "bad argument");
+    d->kp.limit_a = (uint32_t)std::min(trials, 1L << 30) & ~31u;
     return PK_OK;
 }
 

@@ -12,7 +12,7 @@
 // (per-frame work spans 1 .. 2^31 trials).
 //   Phase A (k_phase_a): "narrow" search -- the 32 lanes evaluate 32 consecutive test patterns
 //     per step (BM+Chien in registers or a coset-table lookup).  Almost every frame at medium
-//     and high SNR finishes here.  A frame still running after PK_LIMIT_A trials is parked in a
+//     and high SNR finishes here.  A frame still running after kp.limit_a trials is parked in a
 //     long list with its search state.
 //   Phase B (k_phase_b): "wide" search of the parked frames, 1024 test patterns per warp step:
 //     lane l, bit q  <->  pattern base + 32 l + q.  For t*m > 15 codes the algebraic decoder
@@ -35,7 +35,9 @@
 #define PK_FULL 0xFFFFFFFFu
 #define PK_WARPS_A 8        // warps per CTA, phase A
 #define PK_WARPS_B 4        // warps per CTA, phase B (the bit-sliced decoder needs ~170 registers)
-#define PK_LIMIT_A 1024u    // trials a frame may spend in phase A before it is parked (multiple of 1024)
+#ifndef PK_BS_LOOP
+#define PK_BS_LOOP true     // bit-sliced BM as one loop body (instruction-cache friendly)
+#endif
 
 // totals slots (pk_point_result layout)
 enum { PK_T_FRAMES = 0, PK_T_FERR, PK_T_BERR, PK_T_TRIALS, PK_T_CMP, PK_T_SUM, PK_T_MAXTR, PK_T_FLAGS };
@@ -147,6 +149,7 @@ struct KanekoWarp {
         int m0;
         bool first_ok, have, early;
         uint32_t bound, trials, tsteps, nimpr, flags;
+        uint32_t step_last;   // wide search: 1 + index of the last improvement of the current step, 0 = none
         uint32_t bestF[NW];
     };
 
@@ -256,7 +259,7 @@ struct KanekoWarp {
         s.m0 = 0;
         s.first_ok = true; s.have = false; s.early = false;
         s.bound = pk_pattern_bound(N);      // long T = n (:354)
-        s.trials = 0; s.tsteps = 0; s.nimpr = 0;
+        s.trials = 0; s.tsteps = 0; s.nimpr = 0; s.step_last = 0;
         s.flags = f.flags;
 #pragma unroll
         for (int w = 0; w < NW; ++w) s.bestF[w] = 0;
@@ -439,10 +442,16 @@ struct KanekoWarp {
     }
 
     // ---- wide search (phase B): 1024 patterns per step, pattern = base + 32*lane + bit.
-    // Resumes a parked search at trial `base0` (multiple of 1024, > 0).
+    // Resumes a parked search at trial `start` (> 0, any multiple of 32): the first step covers the block of
+    // 1024 patterns containing `start` with the already-run patterns masked out.
+    // G = warps of the CTA cooperating on this frame (warp wi takes block gbase + 1024 wi of every group step);
+    // for G > 1 the search state travels through `shared` in warp order (baton passing), so improvements are
+    // still committed in pattern order.  All G warps return with identical s.
+    template <int G>
     __device__ static void wide(const Tables &tb, const WarpMem &wm, const PkKanekoParams &kp, const Frame &f,
-                                Search &s, uint32_t base0) {
+                                Search &s, uint32_t start, Search *shared, int wi) {
         const int lane = threadIdx.x & 31;
+        const uint32_t base0 = (start & ~1023u) + 1024u * (uint32_t)wi;
         // pattern bits 0..4 = bit index in the word: their column contributions are per-frame constants
         if constexpr (LUT) {
             // cm[q] = coset-index delta of in-word pattern q; pb[q][w] = its one-hot XOR
@@ -515,15 +524,20 @@ struct KanekoWarp {
         }
         __syncwarp();
 
-        for (uint32_t base = base0;; base += 1024) {
-            if (base >= kp.max_trials) { s.trials = base; s.flags |= PK_FLAG_TRUNCATED; return; }
+        for (uint32_t base = base0;; base += 1024u * G) {
+            const uint32_t gbase = base - 1024u * (uint32_t)wi;   // first pattern of this group step
+            if (gbase >= kp.max_trials) { s.trials = gbase; s.flags |= PK_FLAG_TRUNCATED; return; }
+            s.step_last = 0;
             uint32_t u[SW];
 #pragma unroll
             for (int q = 0; q < SW; ++q) u[q] = f.S0[q] ^ Ul[q] ^ Ub[q];
             const uint32_t lane_first = base + 32u * lane;
-            const uint32_t vmask = (s.bound <= lane_first) ? 0u : ((s.bound - lane_first >= 32u) ? PK_FULL : ((1u << (s.bound - lane_first)) - 1u));
-            uint32_t cand;   // bit q: trial lane_first + q succeeded (and, LUT: its flip weight may still beat l0)
-            if constexpr (LUT) {
+            uint32_t vmask = (s.bound <= lane_first) ? 0u : ((s.bound - lane_first >= 32u) ? PK_FULL : ((1u << (s.bound - lane_first)) - 1u));
+            if (lane_first < start) vmask = 0u;   // patterns below `start` were run by phase A (start is a multiple of 32)
+            uint32_t cand = 0;   // bit q: trial lane_first + q succeeded (and, LUT: its metric may still beat l0)
+            if (base >= s.bound || base + 1024u <= start) {
+                // nothing to run in this block (G > 1: blocks past the bound; first step: blocks below `start`)
+            } else if constexpr (LUT) {
                 uint32_t ok = 0;
 #pragma unroll 8
                 for (int q = 0; q < 32; ++q) {
@@ -566,69 +580,111 @@ struct KanekoWarp {
                     if (!((la - s.l0) > 1e-9 * (lp + s.l0))) cand |= 1u << q;
                 }
             } else {
-                auto getS = [&](int j, uint32_t *o) {
+                auto getS = [&](int j, uint32_t *o) {   // j may be a run-time value (looped BM)
+                    const int wi = (j - 1) / C::PER, sh = ((j - 1) % C::PER) * M;
+                    uint32_t uw = u[0];
 #pragma unroll
-                    for (int b = 0; b < M; ++b) {
-                        const int bit = ((j - 1) % C::PER) * M + b;
-                        o[b] = wm.cm[(j - 1) * M + b] ^ (0u - ((u[(j - 1) / C::PER] >> bit) & 1u));
-                    }
+                    for (int q = 1; q < SW; ++q) uw = (wi == q) ? u[q] : uw;
+                    uw >>= sh;
+#pragma unroll
+                    for (int b = 0; b < M; ++b) o[b] = wm.cm[(j - 1) * M + b] ^ (0u - ((uw >> b) & 1u));
                 };
-                cand = pk_bs_decode<M, T>(getS, wm.z + lane, 33) & vmask;
+                cand = pk_bs_decode<M, T, PK_BS_LOOP>(getS, wm.z + lane, 33) & vmask;
             }
             __syncwarp();
 
-            // ---- candidates in pattern order
-            bool impr_here = false, stop = false;
-            uint32_t last_is = 0;
-            uint32_t lanes_with = __ballot_sync(PK_FULL, cand != 0);
-            while (lanes_with && !stop) {
-                const int src = __ffs(lanes_with) - 1;
-                lanes_with &= lanes_with - 1;
-                uint32_t word = __shfl_sync(PK_FULL, cand, src);
-                const uint32_t usrc = __shfl_sync(PK_FULL, u[0], src);
-                while (word) {
-                    const int q = __ffs(word) - 1;
-                    word &= word - 1;
-                    const uint32_t is = base + 32u * src + q;
-                    if (is >= s.bound) { stop = true; break; }
-                    uint32_t A[NW], F[NW];
-                    if constexpr (LUT) {
-                        lut_positions(tb.lut[usrc ^ wm.cm[q]], A);
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < NW; ++w) {
-                            const int p = lane + 32 * w;
-                            const uint32_t zb = (p < N) ? ((wm.z[p * 33 + src] >> q) & 1u) : 0u;
-                            A[w] = __ballot_sync(PK_FULL, zb);
-                        }
-                    }
-                    const bool sel = (lane < 31) && ((is >> lane) & 1u);
-                    int m = 0;
+            // exact evaluation of candidate (lane src, bit q) against state st: true iff its metric beats st.l0
+            auto eval = [&](int src, int q, uint32_t usrc, uint32_t is, const Search &st, uint32_t (&F)[NW], int &m,
+                            double &l) -> bool {
+                uint32_t A[NW];
+                if constexpr (LUT) {
+                    lut_positions(tb.lut[usrc ^ wm.cm[q]], A);
+                } else {
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {
-                        F[w] = __reduce_xor_sync(PK_FULL, sel ? f.aug[SW + w] : 0u) ^ A[w];
-                        m += __popc(F[w]);
-                    }
-                    if (!may_improve(wm, m, s.l0)) continue;
-                    bool same = s.have;   // same codeword as the current best: l == l0 exactly, no improvement
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) same = same && (F[w] == s.bestF[w]);
-                    if (same) continue;
-                    const double l = calc_l(wm, F);
-                    if (l < s.l0) {
-                        impr_here = true;
-                        last_is = is;
-                        if (commit(s, wm, kp, l, m, F, is)) return;
+                        const int p = lane + 32 * w;
+                        const uint32_t zb = (p < N) ? ((wm.z[p * 33 + src] >> q) & 1u) : 0u;
+                        A[w] = __ballot_sync(PK_FULL, zb);
                     }
                 }
+                const bool sel = (lane < 31) && ((is >> lane) & 1u);
+                m = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    F[w] = __reduce_xor_sync(PK_FULL, sel ? f.aug[SW + w] : 0u) ^ A[w];
+                    m += __popc(F[w]);
+                }
+                if (!may_improve(wm, m, st.l0)) return false;
+                bool same = st.have;   // same codeword as the current best: l == l0 exactly, no improvement
+#pragma unroll
+                for (int w = 0; w < NW; ++w) same = same && (F[w] == st.bestF[w]);
+                if (same) return false;
+                l = calc_l(wm, F);
+                return l < st.l0;
+            };
+            if (G > 1) {
+                // cooperative search: every warp first thins its own candidates IN PARALLEL against the state
+                // at the start of the step (conservative: l0 only decreases), so that the ordered hand-over
+                // below only sees the rare real improvements
+                uint32_t keep = 0;
+                uint32_t lanes_with = __ballot_sync(PK_FULL, cand != 0);
+                while (lanes_with) {
+                    const int src = __ffs(lanes_with) - 1;
+                    lanes_with &= lanes_with - 1;
+                    uint32_t word = __shfl_sync(PK_FULL, cand, src), word2 = 0;
+                    const uint32_t usrc = __shfl_sync(PK_FULL, u[0], src);
+                    while (word) {
+                        const int q = __ffs(word) - 1;
+                        word &= word - 1;
+                        uint32_t F[NW];
+                        int m;
+                        double l;
+                        if (eval(src, q, usrc, base + 32u * src + q, s, F, m, l)) word2 |= 1u << q;
+                    }
+                    if (lane == src) keep = word2;
+                }
+                cand = keep;
             }
-            if (s.bound <= base + 1024u) {
+            // ---- candidates in pattern order (for G > 1: warp 0's block first, then warp 1's, ...)
+#pragma unroll 1
+            for (int turn = 0; turn < G; ++turn) {
+                if (turn == wi) {
+                    if (G > 1 && turn > 0) s = *shared;
+                    bool stop = s.early;
+                    uint32_t lanes_with = __ballot_sync(PK_FULL, cand != 0);
+                    while (lanes_with && !stop) {
+                        const int src = __ffs(lanes_with) - 1;
+                        lanes_with &= lanes_with - 1;
+                        uint32_t word = __shfl_sync(PK_FULL, cand, src);
+                        const uint32_t usrc = __shfl_sync(PK_FULL, u[0], src);
+                        while (word) {
+                            const int q = __ffs(word) - 1;
+                            word &= word - 1;
+                            const uint32_t is = base + 32u * src + q;
+                            if (is >= s.bound) { stop = true; break; }
+                            uint32_t F[NW];
+                            int m;
+                            double l;
+                            if (eval(src, q, usrc, is, s, F, m, l)) {
+                                s.step_last = is + 1;
+                                if (commit(s, wm, kp, l, m, F, is)) { stop = true; break; }
+                            }
+                        }
+                    }
+                    if (G > 1 && lane == 0) *shared = s;
+                }
+                if (G > 1) __syncthreads();
+            }
+            if (G > 1) s = *shared;
+            if (s.early) return;
+            if (s.bound <= gbase + 1024u * G) {
                 s.trials = s.bound;
-                if (impr_here && last_is + 1 > s.trials) s.trials = last_is + 1;
+                if (s.step_last > s.trials) s.trials = s.step_last;
                 return;
             }
+            if (G > 1) __syncthreads();   // everyone has re-read the state before the next step overwrites it
             {   // next base: bits 10.. change
-                uint32_t diff = ((base + 1024u) ^ base) >> 10;
+                uint32_t diff = ((base + 1024u * G) ^ base) >> 10;
                 while (diff) {
                     const int b = __ffs(diff) - 1;
                     diff &= diff - 1;
@@ -662,7 +718,7 @@ struct KanekoWarp {
         s.have = (r->sflags & 2u) != 0;
         s.early = false;
         s.flags = r->sflags >> 8;
-        s.trials = 0;
+        s.trials = 0; s.step_last = 0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) s.bestF[w] = r->bestF[w];
     }
@@ -865,7 +921,7 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
     tabs.col = reinterpret_cast<const uint32_t *>(smem + SM::COL_OFF);
     tabs.lut = reinterpret_cast<const uint16_t *>(smem + SM::LUT_OFF);
     // frames are parked only when a wide kernel exists for this code (long_cap > 0 says so)
-    const uint32_t limit = (long_cap > 0) ? PK_LIMIT_A : 0xFFFFFFFFu;
+    const uint32_t limit = (long_cap > 0) ? kp.limit_a : 0xFFFFFFFFu;
 
     PkWarpTotals tot;
     tot.clear();
@@ -888,13 +944,18 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
             uint32_t next = 0;
             bool done = KW::narrow(tabs, wm, kp, fr, s, 0u, limit, &next);
             if (!done) {
-                unsigned long long slot = 0;
-                if (lane == 0) slot = atomicAdd(&ctl->n_long, 1ull);
-                slot = __shfl_sync(PK_FULL, slot, 0);
-                if ((long)slot < long_cap) {
-                    if (lane == 0) KW::park(s, (uint32_t)f, next, longs + slot);
-                    continue;
+                // park: frames with a long pattern range left go to the "big" end of the list (one CTA each in
+                // phase B), the others to the "small" end (one warp each)
+                long slot = -1;
+                if (lane == 0) {
+                    if ((long)atomicAdd(&ctl->n_total, 1ull) < long_cap) {
+                        const bool big = (s.bound > next) && (s.bound - next >= kp.big_span);
+                        slot = big ? long_cap - 1 - (long)atomicAdd(&ctl->n_big, 1ull) : (long)atomicAdd(&ctl->n_long, 1ull);
+                        KW::park(s, (uint32_t)f, next, longs + slot);
+                    }
                 }
+                slot = __shfl_sync(PK_FULL, slot, 0);
+                if (slot >= 0) continue;
                 // list full: finish here (phase B ignores slots >= long_cap)
                 KW::narrow(tabs, wm, kp, fr, s, next, 0xFFFFFFFFu, &next);
             }
@@ -913,9 +974,8 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
     typedef KanekoWarp<M, T, LUT> KW;
     constexpr int NW = KW::NW;
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long n_long = ctl->n_long;
-    if ((long)n_long > long_cap) n_long = (unsigned long long)long_cap;
-    if (n_long == 0) return;
+    const unsigned long long n_long = ctl->n_long, n_big = ctl->n_big;
+    if (n_long + n_big == 0) return;
     pk_stage_tables<M, T, LUT>(smem, tb, false);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wb = smem + SM::tables(tb.nk) + (size_t)warp * SM::W_SZ_B;
@@ -926,9 +986,34 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
     tabs.xoff = reinterpret_cast<const uint16_t *>(smem + SM::XOFF_OFF);
     tabs.col = reinterpret_cast<const uint32_t *>(smem + SM::COL_OFF);
     tabs.lut = reinterpret_cast<const uint16_t *>(smem + SM::LUT_OFF);
+    __shared__ typename KW::Search s_shared;
+    __shared__ unsigned long long s_idx;
 
     PkWarpTotals tot;
     tot.clear();
+    // ---- big frames: the whole CTA searches one frame, 1024 patterns per warp per step
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_idx = atomicAdd(&ctl->queue_big, 1ull);
+        __syncthreads();
+        const unsigned long long idx = s_idx;
+        if (idx >= n_big) break;
+        const PkLongRec *rec = longs + (long_cap - 1 - (long)idx);
+        const long f = (long)rec->frame;
+        double yv[NW];
+        uint32_t CW[NW];
+        pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, false, yv, CW);
+        typename KW::Frame fr;
+        typename KW::Search s;
+        KW::setup(tabs, wm, yv, kp, fr);     // every warp keeps its own copy of the frame tables
+        KW::unpark(s, rec);
+        KW::template wide<PK_WARPS_B>(tabs, wm, kp, fr, s, rec->base, &s_shared, warp);
+        if (warp == 0) {
+            KW::search_finish(s);
+            pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr, s.tsteps, s.flags, tot);
+        }
+    }
+    // ---- small frames: one warp each
     for (;;) {
         unsigned long long idx = 0;
         if (lane == 0) idx = atomicAdd(&ctl->queue_b, 1ull);
@@ -943,7 +1028,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
         typename KW::Search s;
         KW::setup(tabs, wm, yv, kp, fr);
         KW::unpark(s, rec);
-        KW::wide(tabs, wm, kp, fr, s, rec->base);
+        KW::template wide<1>(tabs, wm, kp, fr, s, rec->base, nullptr, 0);
         KW::search_finish(s);
         pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr, s.tsteps, s.flags, tot);
     }

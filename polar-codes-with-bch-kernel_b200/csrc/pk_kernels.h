@@ -13,6 +13,8 @@ struct PkKanekoParams {
     int J;                // cap on T, < 0 = none (KanekoKernelProcessor.cpp:392-393)
     uint32_t max_trials;  // safety cap, 0x7FFFFFFF = the reference bound
     int frames_per_grab;  // frames a warp takes from the queue per atomic
+    uint32_t limit_a;     // trials (multiple of 32) a frame may spend in the narrow phase A before it is parked
+    uint32_t big_span;    // parked frames with at least this many patterns left are searched by a whole CTA
 };
 
 // Generation-mode parameters of one launch.
@@ -49,9 +51,11 @@ struct PkLongRec {
 // Device-side control block of one phase A / phase B launch pair (zeroed by the launcher).
 struct PkPhaseCtl {
     unsigned long long queue_a;     // next frame of phase A
-    unsigned long long queue_b;     // next parked frame of phase B
-    unsigned long long n_long;      // parked frames
-    unsigned long long pad;
+    unsigned long long queue_b;     // next parked "small" frame of phase B (one warp each)
+    unsigned long long n_long;      // parked small frames: longs[0 .. n_long)
+    unsigned long long n_total;     // parked frames of both kinds (capacity check)
+    unsigned long long queue_big;   // next parked "big" frame (one CTA each)
+    unsigned long long n_big;       // parked big frames: longs[cap-1 .. cap-n_big] (filled from the top)
 };
 
 struct PkLaunchGeom {
