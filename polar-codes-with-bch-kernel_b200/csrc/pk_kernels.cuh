@@ -449,7 +449,7 @@ struct KanekoWarp {
     // still committed in pattern order.  All G warps return with identical s.
     template <int G>
     __device__ static void wide(const Tables &tb, const WarpMem &wm, const PkKanekoParams &kp, const Frame &f,
-                                Search &s, uint32_t start, Search *shared, int wi) {
+                                Search &s, uint32_t start, Search *shared, uint32_t *votes, int wi) {
         const int lane = threadIdx.x & 31;
         const uint32_t base0 = (start & ~1023u) + 1024u * (uint32_t)wi;
         // pattern bits 0..4 = bit index in the word: their column contributions are per-frame constants
@@ -646,43 +646,59 @@ struct KanekoWarp {
                 cand = keep;
             }
             // ---- candidates in pattern order (for G > 1: warp 0's block first, then warp 1's, ...)
+            bool handover = true;
+            if (G > 1) {
+                // most steps leave no candidate in any warp: one barrier settles that and the state is unchanged
+                volatile uint32_t *fl = votes + (((gbase >> 10) / G) & 1u) * G;   // double-buffered by step parity
+                const uint32_t mine = __ballot_sync(PK_FULL, cand != 0);
+                if (lane == 0) fl[wi] = mine ? 1u : 0u;
+                __syncthreads();
+                uint32_t anyc = 0;
+#pragma unroll
+                for (int g = 0; g < G; ++g) anyc |= fl[g];
+                handover = anyc != 0;
+            }
+            if (handover) {
 #pragma unroll 1
-            for (int turn = 0; turn < G; ++turn) {
-                if (turn == wi) {
-                    if (G > 1 && turn > 0) s = *shared;
-                    bool stop = s.early;
-                    uint32_t lanes_with = __ballot_sync(PK_FULL, cand != 0);
-                    while (lanes_with && !stop) {
-                        const int src = __ffs(lanes_with) - 1;
-                        lanes_with &= lanes_with - 1;
-                        uint32_t word = __shfl_sync(PK_FULL, cand, src);
-                        const uint32_t usrc = __shfl_sync(PK_FULL, u[0], src);
-                        while (word) {
-                            const int q = __ffs(word) - 1;
-                            word &= word - 1;
-                            const uint32_t is = base + 32u * src + q;
-                            if (is >= s.bound) { stop = true; break; }
-                            uint32_t F[NW];
-                            int m;
-                            double l;
-                            if (eval(src, q, usrc, is, s, F, m, l)) {
-                                s.step_last = is + 1;
-                                if (commit(s, wm, kp, l, m, F, is)) { stop = true; break; }
+                for (int turn = 0; turn < G; ++turn) {
+                    if (turn == wi) {
+                        if (G > 1 && turn > 0) s = *shared;
+                        bool stop = s.early;
+                        uint32_t lanes_with = __ballot_sync(PK_FULL, cand != 0);
+                        while (lanes_with && !stop) {
+                            const int src = __ffs(lanes_with) - 1;
+                            lanes_with &= lanes_with - 1;
+                            uint32_t word = __shfl_sync(PK_FULL, cand, src);
+                            const uint32_t usrc = __shfl_sync(PK_FULL, u[0], src);
+                            while (word) {
+                                const int q = __ffs(word) - 1;
+                                word &= word - 1;
+                                const uint32_t is = base + 32u * src + q;
+                                if (is >= s.bound) { stop = true; break; }
+                                uint32_t F[NW];
+                                int m;
+                                double l;
+                                if (eval(src, q, usrc, is, s, F, m, l)) {
+                                    s.step_last = is + 1;
+                                    if (commit(s, wm, kp, l, m, F, is)) { stop = true; break; }
+                                }
                             }
                         }
+                        if (G > 1 && lane == 0) *shared = s;
                     }
-                    if (G > 1 && lane == 0) *shared = s;
+                    if (G > 1) __syncthreads();
                 }
-                if (G > 1) __syncthreads();
+                if (G > 1) {
+                    s = *shared;
+                    __syncthreads();   // everyone has re-read the state before a later step overwrites it
+                }
             }
-            if (G > 1) s = *shared;
             if (s.early) return;
             if (s.bound <= gbase + 1024u * G) {
                 s.trials = s.bound;
                 if (s.step_last > s.trials) s.trials = s.step_last;
                 return;
             }
-            if (G > 1) __syncthreads();   // everyone has re-read the state before the next step overwrites it
             {   // next base: bits 10.. change
                 uint32_t diff = ((base + 1024u * G) ^ base) >> 10;
                 while (diff) {
@@ -988,16 +1004,21 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
     tabs.lut = reinterpret_cast<const uint16_t *>(smem + SM::LUT_OFF);
     __shared__ typename KW::Search s_shared;
     __shared__ unsigned long long s_idx;
+    __shared__ uint32_t s_votes[2 * PK_WARPS_B];
 
     PkWarpTotals tot;
     tot.clear();
-    // ---- big frames: the whole CTA searches one frame, 1024 patterns per warp per step
+    // ---- big frames: the whole CTA searches one frame, 1024 patterns per warp per step.  Cooperation costs
+    // ~10 % throughput (hand-over barriers), so when there are far more big frames than CTAs only one round of
+    // them is searched cooperatively and the rest go warp-per-frame below; with few big frames (the tail
+    // regime of medium / high SNR launches) all of them are.
+    const unsigned long long n_coop = (n_big > 8ull * gridDim.x) ? (unsigned long long)gridDim.x : n_big;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_idx = atomicAdd(&ctl->queue_big, 1ull);
         __syncthreads();
         const unsigned long long idx = s_idx;
-        if (idx >= n_big) break;
+        if (idx >= n_coop) break;
         const PkLongRec *rec = longs + (long_cap - 1 - (long)idx);
         const long f = (long)rec->frame;
         double yv[NW];
@@ -1007,19 +1028,21 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
         typename KW::Search s;
         KW::setup(tabs, wm, yv, kp, fr);     // every warp keeps its own copy of the frame tables
         KW::unpark(s, rec);
-        KW::template wide<PK_WARPS_B>(tabs, wm, kp, fr, s, rec->base, &s_shared, warp);
+        KW::template wide<PK_WARPS_B>(tabs, wm, kp, fr, s, rec->base, &s_shared, s_votes, warp);
         if (warp == 0) {
             KW::search_finish(s);
             pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr, s.tsteps, s.flags, tot);
         }
     }
-    // ---- small frames: one warp each
+    // ---- small frames (and the big ones left over): one warp each
+    const unsigned long long n_solo = n_long + (n_big - n_coop);
     for (;;) {
         unsigned long long idx = 0;
         if (lane == 0) idx = atomicAdd(&ctl->queue_b, 1ull);
         idx = __shfl_sync(PK_FULL, idx, 0);
-        if (idx >= n_long) break;
-        const PkLongRec *rec = longs + idx;
+        if (idx >= n_solo) break;
+        // big leftovers first (longest searches first), then the small list
+        const PkLongRec *rec = (idx < n_big - n_coop) ? longs + (long_cap - 1 - (long)(n_coop + idx)) : longs + (idx - (n_big - n_coop));
         const long f = (long)rec->frame;
         double yv[NW];
         uint32_t CW[NW];
@@ -1028,7 +1051,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
         typename KW::Search s;
         KW::setup(tabs, wm, yv, kp, fr);
         KW::unpark(s, rec);
-        KW::template wide<1>(tabs, wm, kp, fr, s, rec->base, nullptr, 0);
+        KW::template wide<1>(tabs, wm, kp, fr, s, rec->base, nullptr, nullptr, 0);
         KW::search_finish(s);
         pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr, s.tsteps, s.flags, tot);
     }
