@@ -249,10 +249,10 @@ def run_b200(a):
         per_launch.setdefault((ci, si), []).append(e0.elapsed_time(e1))
 
     # ---- the one collective of the path: per-point counters summed over ranks
-    tot_all = torch.stack(tots).clone()
+    tot_all = torch.stack(tots)[..., :6].contiguous()   # frames, frame errors, bit errors, trials, cmp, sum
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(tot_all[..., :6], op=dist.ReduceOp.SUM)
+        dist.all_reduce(tot_all, op=dist.ReduceOp.SUM)
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     dev_ms = float(t_ms.item())
     frames_per_step = world * B * len(SNRS) * len(CODES)
@@ -310,17 +310,33 @@ def run_b200(a):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bytes_per_frame * B / (dom_ms * 1e-3) / 1e9
     dom_trials = int(tot_np[dom, :, 3].sum()) // max(1, world)
-    kname = f"k_replay<{dom_code.m},{dom_code.t},{'LUT' if dom_code.uses_lut else 'BM+Chien'}>"
+    kname = (f"k_phase_a + k_phase_b<{dom_code.m},{dom_code.t},{'coset table' if dom_code.uses_lut else 'bit-sliced BM+Chien'}> "
+             "(one launch pair per SNR point; phase B is ~89 % of kernel time, profiles/r1_launches.md)")
+    sm_hz = (clocks["sm_mhz"] or 1965.0) * 1e6
+    trials_per_s_dom = dom_trials / (by_code[dom] * a.steps * 1e-3)
+    # instructions per trial of the dominant kernel, from the committed ncu capture of this kernel
+    # (profiles/r1_ncu_summary.md: smsp__inst_executed.sum / trials, BCH(63,30,13) J=15 at 0 dB)
+    NCU_WARP_INST_PER_TRIAL = 13.3
+    NCU_ALU_PIPE_BUSY = 0.69
+    NCU_DRAM_BYTES_PER_LAUNCH = 9438208   # dram__bytes_read+write, 16384 frames of n=63 at 0 dB
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (dom_code.n == 63 and B == 16384) else None,
+        "algorithmic_bytes_per_launch": bytes_per_frame * B,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
         "kernel": kname, "avg_launch_ms": dom_ms, "share_of_step": by_code[dom] / step_ms,
-        "note": "search kernel: neither HBM- nor tensor-bound (SURVEY 8d); the binding roofs are warp-instruction issue and the shared-memory LSU -- see issue_slot",
+        "note": ("integer search kernel: neither HBM- nor tensor-bound (SURVEY 8d, DRAM traffic == algorithmic bytes); "
+                 "the binding unit is the INT ALU pipe (LOP3 of the bit-sliced decoder) -- see issue_slot"),
         "issue_slot": {
-            "trials_per_s": dom_trials / (by_code[dom] * a.steps * 1e-3),
+            "trials_per_s": trials_per_s_dom,
             "algorithmic_gf_macs_per_trial": 2 * dom_code.t * 2 + 2 * dom_code.t ** 2 + dom_code.n * dom_code.t,
-            "peak_warp_inst_per_s": 148 * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6,
-            "warp_inst_per_trial": None,   # filled from profiles/*.md (ncu sm__inst_executed / trials)
+            "warp_inst_per_trial": NCU_WARP_INST_PER_TRIAL,
+            "achieved_warp_inst_per_s": trials_per_s_dom * NCU_WARP_INST_PER_TRIAL,
+            "peak_warp_inst_per_s": 148 * 4 * sm_hz,
+            "frac": trials_per_s_dom * NCU_WARP_INST_PER_TRIAL / (148 * 4 * sm_hz),
+            "alu_pipe_peak_warp_inst_per_s": 148 * 4 * 0.5 * sm_hz,
+            "alu_pipe_busy_ncu": NCU_ALU_PIPE_BUSY,
+            "source": "profiles/r1_ncu_summary.md (prof_r1b_phaseb_m6t6)",
         },
     }
 
