@@ -161,6 +161,38 @@ int pk_kaneko_run_point(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t 
 /* n x n nested-BCH polarisation kernel, makeMatrix (src/bchCoder.cpp:317-345); row-major bytes. */
 int pk_make_kernel_matrix(const pk_code *code, uint8_t *out /*[n][n]*/);
 
+/* ======================================================================================================
+ * Polar codes with binary matrix kernels (the reference's vendored library, headers/external + out/external):
+ * mixed-kernel encoder, trellis kernel processor and SC / SC-list decoder.  Bits are 0/1 bytes, LLRs are
+ * fp32 with LLR > 0 <=> bit 0 (Modem.h:64,78; MixedKernelListDecoder.cpp:80).
+ * ====================================================================================================== */
+typedef struct pk_polar pk_polar;
+
+/* CMixedKernelListDecoder(std::istream& Spec, unsigned ListSize) (MixedKernelListDecoder.cpp:10,
+ * CMixedKernelEncoder::CMixedKernelEncoder MixedKernelEncoder.cpp:7-97): spec_text is the reference's code
+ * specification ("N K dmin layers nShort nPunct", kernel names, shortened / punctured indices, N0-K freezing
+ * constraints "w i_1 .. i_w").  Kernels are matrix kernels loaded from a file ("-path" or "<path",
+ * Kernel.cpp:93-107,255-262).  list_size 1 = plain SC; <= 32.  device < 0: host tables only. */
+int pk_polar_create(const char *spec_text, int list_size, int device, pk_polar **out);
+void pk_polar_destroy(pk_polar *p);
+int pk_polar_info(const pk_polar *p, int *N, int *K, int *N0, int *layers, int *list_size);
+/* m_ppNumOfActiveBits of the kernel of `layer` (TrellisKernelProcessor.cpp:105,154): out[l][l+1] */
+int pk_polar_trellis_profile(const pk_polar *p, int layer, int *size, uint8_t *out);
+/* (2^m) x (2^m) extended-BCH polarisation kernel, makeMatrix of the root bchCoder.cpp:356-389; m in [3,5] */
+int pk_make_ebch_kernel(int m, uint8_t *out /*[2^m][2^m]*/);
+/* CBinaryEncoder::Encode (Codec.h:52; MixedKernelEncoder.cpp:142-176) */
+int pk_polar_encode_batch(pk_polar *p, const uint8_t *info /*[B][K]*/, long B, uint8_t *cw /*[B][N]*/);
+/* CKernProcLLR::GetLLRs (KernProc.h:40; TrellisKernelProcessor.cpp:234-295), stride 1, for B independent
+ * kernel blocks: out[b][ph] = LLR of kernel input ph given inputs u[b][0..ph) and output LLRs chan[b][:] */
+int pk_polar_kernel_llrs(pk_polar *p, int layer, const float *chan /*[B][l]*/, const uint8_t *u /*[B][l]*/, long B,
+                         float *out /*[B][l]*/);
+/* CBinarySoftDecoder::Decode (Codec.h:100-118; MixedKernelListDecoder.cpp:211-269): count[b] list entries,
+ * best first; inf [B][L][K]; cw [B][L][N] and metric [B][L] may be NULL */
+int pk_polar_decode_batch(pk_polar *p, const float *llr /*[B][N]*/, long B, int *count, uint8_t *inf, uint8_t *cw,
+                          float *metric);
+int pk_polar_decode_batch_dev(pk_polar *p, const float *d_llr, long B, int *d_count, uint8_t *d_inf, uint8_t *d_cw,
+                              float *d_metric, void *stream);
+
 /* Introspection for bench.py: kernels launched by this library since load / reset. */
 uint64_t pk_launch_count(void);
 void pk_launch_count_reset(void);

@@ -215,3 +215,61 @@ class Reference(_Base):
             self.lib.ref_set_J(self.J)
         self.lib.ref_fun(self.h, path_noext.encode(), p, e, C.c_double(max_snr))
         return np.loadtxt(path_noext + ".csv", delimiter=",", ndmin=2)
+
+
+class PolarReference:
+    """The reference's vendored SC-list polar library (oracle/_ref/libpolar_ref.so via polar_ref_harness.cpp,
+    built through oracle/polar_shim).  TEST INFRASTRUCTURE ONLY."""
+
+    def __init__(self, spec_text: str, L: int = 1):
+        path = os.path.join(REF_DIR, "libpolar_ref.so")
+        self.lib = lib = C.CDLL(path, mode=os.RTLD_NOW)
+        lib.pref_create.restype = C.c_void_p
+        lib.pref_create.argtypes = [C.c_char_p, C.c_uint]
+        lib.pref_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        lib.pref_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+        lib.pref_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pref_trellis_llrs.argtypes = [C.c_char_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pref_trellis_llrs.restype = C.c_int
+        self.h = lib.pref_create(spec_text.encode(), L)
+        if not self.h:
+            raise ValueError("reference rejected the specification")
+        v = [C.c_int() for _ in range(4)]
+        lib.pref_dims(self.h, *[C.byref(x) for x in v])
+        self.N, self.K, self.N0, self.layers = (x.value for x in v)
+        self.L = L
+
+    def encode(self, info):
+        info = np.ascontiguousarray(info, np.uint8)
+        cw = np.zeros((info.shape[0], self.N), np.uint8)
+        self.lib.pref_encode(self.h, info.ctypes.data, info.shape[0], cw.ctypes.data)
+        return cw
+
+    def decode(self, llr):
+        llr = np.ascontiguousarray(llr, np.float32)
+        B = llr.shape[0]
+        cnt = np.zeros(B, np.int32)
+        inf = np.zeros((B, self.L, self.K), np.uint8)
+        cw = np.zeros((B, self.L, self.N), np.uint8)
+        met = np.zeros((B, self.L), np.float32)
+        self.lib.pref_decode(self.h, llr.ctypes.data, B, cnt.ctypes.data, inf.ctypes.data, cw.ctypes.data, met.ctypes.data)
+        return cnt, inf, cw, met
+
+
+def polar_ref_available() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "libpolar_ref.so"))
+
+
+def polar_ref_trellis_llrs(kernel_file: str, chan, u, stride: int = 1):
+    """CTrellisKernelProcessor::GetLLRs over phases 0..l-1 for ONE kernel block group: chan/u [l*stride]."""
+    lib = C.CDLL(os.path.join(REF_DIR, "libpolar_ref.so"), mode=os.RTLD_NOW)
+    lib.pref_trellis_llrs.argtypes = [C.c_char_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pref_trellis_llrs.restype = C.c_int
+    chan = np.ascontiguousarray(chan, np.float32)
+    u = np.ascontiguousarray(u, np.uint8)
+    out = np.zeros(chan.shape, np.float32)
+    ab = np.zeros(64 * 65, np.uint32)
+    l = lib.pref_trellis_llrs(kernel_file.encode(), stride, chan.ctypes.data, u.ctypes.data, out.ctypes.data, ab.ctypes.data)
+    if l < 0:
+        raise ValueError("reference trellis processor failed")
+    return out, ab[: l * (l + 1)].reshape(l, l + 1)

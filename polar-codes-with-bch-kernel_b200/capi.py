@@ -31,7 +31,9 @@ SYMBOLS = (
     "pk_code_uses_lut pk_code_set_lut pk_code_coset_table pk_encode_batch pk_bch_decode_batch pk_kaneko_create "
     "pk_kaneko_destroy pk_kaneko_set_frames_per_grab pk_kaneko_set_phase_a_limit pk_kaneko_launch_geometry pk_kaneko_decode_batch "
     "pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames pk_generate_frames_dev "
-    "pk_kaneko_run_point pk_make_kernel_matrix pk_launch_count pk_launch_count_reset"
+    "pk_kaneko_run_point pk_make_kernel_matrix pk_launch_count pk_launch_count_reset "
+    "pk_polar_create pk_polar_destroy pk_polar_info pk_polar_trellis_profile pk_make_ebch_kernel pk_polar_encode_batch "
+    "pk_polar_kernel_llrs pk_polar_decode_batch pk_polar_decode_batch_dev"
 ).split()
 
 
@@ -78,6 +80,16 @@ def _load():
     lib.pk_generate_frames_dev.argtypes = [vp, d, i, u64, u64, l, vp, vp, vp, vp]
     lib.pk_kaneko_run_point.argtypes = [vp, d, i, u64, l, l, vp]
     lib.pk_make_kernel_matrix.argtypes = [vp, vp]
+    lib.pk_polar_create.argtypes = [C.c_char_p, i, i, pp]
+    lib.pk_polar_destroy.argtypes = [vp]
+    lib.pk_polar_destroy.restype = None
+    lib.pk_polar_info.argtypes = [vp, ip, ip, ip, ip, ip]
+    lib.pk_polar_trellis_profile.argtypes = [vp, i, ip, vp]
+    lib.pk_make_ebch_kernel.argtypes = [i, vp]
+    lib.pk_polar_encode_batch.argtypes = [vp, vp, l, vp]
+    lib.pk_polar_kernel_llrs.argtypes = [vp, i, vp, vp, l, vp]
+    lib.pk_polar_decode_batch.argtypes = [vp, vp, l, vp, vp, vp, vp]
+    lib.pk_polar_decode_batch_dev.argtypes = [vp, vp, l, vp, vp, vp, vp, vp]
     lib.pk_launch_count.restype = u64
     lib.pk_launch_count_reset.restype = None
     return lib
@@ -251,3 +263,72 @@ def counters_from_recs(recs, n):
     tr = recs["trials"].astype(np.uint64)
     run = tr - (recs["flags"] & PK_FLAG_EARLY_RETURN).astype(np.uint64)
     return tr, run * np.uint64(n + 6) + recs["extra_cmp"], run * np.uint64(n + 1) + recs["extra_sum"]
+
+
+SPEC_DIR = os.path.join(_HERE, "specs")
+
+
+def ebch_kernel(m):
+    """(2^m) x (2^m) extended-BCH kernel matrix (root bchCoder.cpp:356-389)."""
+    n = 1 << m
+    out = np.zeros((n, n), np.uint8)
+    _check(lib.pk_make_ebch_kernel(int(m), _np_ptr(out)))
+    return out
+
+
+def load_spec(name="polar_256_128_ebch16.spec.in"):
+    """A committed specification template with @KERNEL@ replaced by the absolute path of the kernel file."""
+    txt = open(os.path.join(SPEC_DIR, name)).read()
+    return txt.replace("@KERNEL@", os.path.join(SPEC_DIR, "ebch16.kernel"))
+
+
+class Polar:
+    """pk_polar handle: mixed-kernel polar code + SC (L = 1) / SC-list decoder; device=None: host tables only."""
+
+    def __init__(self, spec_text, L=1, device=0):
+        h = C.c_void_p()
+        _check(lib.pk_polar_create(spec_text.encode(), int(L), -1 if device is None else int(device), C.byref(h)))
+        self.h = h
+        v = [C.c_int() for _ in range(5)]
+        _check(lib.pk_polar_info(h, *[C.byref(x) for x in v]))
+        self.N, self.K, self.N0, self.layers, self.L = (x.value for x in v)
+
+    def close(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib.pk_polar_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def trellis_profile(self, layer=0):
+        sz = C.c_int()
+        _check(lib.pk_polar_trellis_profile(self.h, layer, C.byref(sz), None))
+        out = np.zeros((sz.value, sz.value + 1), np.uint8)
+        _check(lib.pk_polar_trellis_profile(self.h, layer, C.byref(sz), _np_ptr(out)))
+        return out
+
+    def encode(self, info):
+        info = np.ascontiguousarray(info, np.uint8)
+        cw = np.zeros((info.shape[0], self.N), np.uint8)
+        _check(lib.pk_polar_encode_batch(self.h, _np_ptr(info), info.shape[0], _np_ptr(cw)))
+        return cw
+
+    def kernel_llrs(self, chan, u, layer=0):
+        chan = np.ascontiguousarray(chan, np.float32)
+        u = np.ascontiguousarray(u, np.uint8)
+        out = np.zeros(chan.shape, np.float32)
+        _check(lib.pk_polar_kernel_llrs(self.h, layer, _np_ptr(chan), _np_ptr(u), chan.shape[0], _np_ptr(out)))
+        return out
+
+    def decode(self, llr):
+        llr = np.ascontiguousarray(llr, np.float32)
+        B = llr.shape[0]
+        cnt = np.zeros(B, np.int32)
+        inf = np.zeros((B, self.L, self.K), np.uint8)
+        cw = np.zeros((B, self.L, self.N), np.uint8)
+        met = np.zeros((B, self.L), np.float32)
+        _check(lib.pk_polar_decode_batch(self.h, _np_ptr(llr), B, _np_ptr(cnt), _np_ptr(inf), _np_ptr(cw), _np_ptr(met)))
+        return cnt, inf, cw, met
+
+    def decode_dev(self, d_llr, B, d_count, d_inf, d_cw=None, d_metric=None, stream=None):
+        _check(lib.pk_polar_decode_batch_dev(self.h, d_llr, B, d_count, d_inf, d_cw, d_metric, stream))

@@ -43,6 +43,9 @@ int upload(pk_code *c, const std::vector<Tp> &h, const Tp **dptr) {
 }
 }  // namespace
 
+// shared with pk_polar.cu
+int pk_set_error(int code, const std::string &msg) { return fail(code, msg); }
+
 struct pk_kaneko {
     pk_code *code = nullptr;
     PkKanekoParams kp{};

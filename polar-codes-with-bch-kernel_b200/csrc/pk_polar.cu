@@ -1,0 +1,681 @@
+// pk_polar.cu -- sm_100a kernels and C ABI for polar codes with binary matrix (e.g. extended-BCH) kernels.
+//
+// Mapping (reference file:line -> here):
+//   CMixedKernelEncoder::Encode               out/external/MixedKernelEncoder.cpp:142-176  -> k_polar_encode
+//   CMatrixBinaryKernel::Multiply / MatrixMultiply   Kernel.cpp:202-208, LinAlg.cpp:685-711 -> kernel_multiply()
+//   CTrellisKernelProcessor::GetLLRs          TrellisKernelProcessor.cpp:234-295          -> get_llrs() / viterbi()
+//   CListKernelEngine::IterativelyCalcS / IterativelyUpdateC   KernelListEngine.cpp:370-447,266-315 -> calc_s() / update_c()
+//   CMixedKernelListDecoder::Decode / ContinuePathsFrozen / ContinuePathsUnfrozen
+//                                             MixedKernelListDecoder.cpp:211-269,61-98,100-185 -> k_polar_decode
+//   CTVMemoryEngine path stack (Pop / Push, lazily initialised)   TVMemoryEngine.cpp:85-141, misc.h:212-226 -> PathStack
+//
+// One CTA per frame, ONE WARP PER LIST PATH (L warps).  The per-path arrays of the reference's Tal-Vardy memory
+// engine (LLR arrays S, partial-sum arrays C, kernel-processor offsets) live in shared memory and are copied
+// eagerly on a clone (a few hundred bytes), which is observably identical to the reference's copy-on-write.
+// Kernel LLRs are min-sum Viterbi over the per-phase minimal trellis in GATHER form (each next state takes the
+// minimum over its <= 2 incoming branches), lanes across trellis states; every value is a single fp32 add or
+// min of the reference's operands, so kernel LLRs and path metrics are bit-identical to the reference's floats.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pk_capi.h"
+#include "pk_polar.h"
+
+extern unsigned long long g_pk_launches;
+int pk_set_error(int code, const std::string &msg);   // pk_capi.cu
+
+#define PKP_FULL 0xFFFFFFFFu
+#define PKP_UPPER 100000.0f   // MTYPE_UPPER_BOUND (SeqConfigOrig.h:173): LLR of a shortened symbol
+
+struct PkPolarKernelDev {
+    const uint8_t *mat;    // [l][l]
+    const uint8_t *ab;     // [l][l+1]
+    const uint32_t *pred;
+    const uint32_t *off;   // [l*l]
+    int size, max_ab;
+};
+struct PkPolarDev {
+    int N, K, N0, layers, nw;
+    int ksize[PK_POLAR_MAX_LAYERS];
+    int outer[PK_POLAR_MAX_LAYERS + 1];
+    PkPolarKernelDev kern[PK_POLAR_MAX_LAYERS];
+    const uint8_t *frozen;     // [N0] 1 = frozen symbol
+    const uint32_t *cmask;     // [N0][nw]
+    const uint16_t *info_pos;  // [K]
+    const uint8_t *symtype;    // [N0] or null
+    int all_static;            // every freezing constraint is "symbol = 0"
+    int max_ab;                // over layers
+};
+
+// ------------------------------------------------------------------ shared building blocks
+// dest[c*stride + i] (^)= XOR_r K[r][c] * src[r*stride + i]   (MatrixMultiply, LinAlg.cpp:685-711), one warp
+__device__ __forceinline__ void kernel_multiply(const PkPolarKernelDev &k, int stride, const uint8_t *src, uint8_t *dest) {
+    const int lane = threadIdx.x & 31, l = k.size;
+    for (int e = lane; e < l * stride; e += 32) {
+        const int c = e / stride, i = e - c * stride;
+        uint8_t v = 0;
+        for (int r = 0; r < l; ++r) v ^= k.mat[r * l + c] & src[r * stride + i];
+        dest[e] = v;
+    }
+    __syncwarp();
+}
+
+// min-sum Viterbi of one kernel phase for stride element i (TrellisKernelProcessor.cpp:260-293), one warp.
+// met: 2 << max_ab floats of warp-private shared memory.
+__device__ __forceinline__ float viterbi(const PkPolarKernelDev &k, int phase, int stride, int i, const float *chan,
+                                         const uint8_t *offs, float *met) {
+    const int lane = threadIdx.x & 31, l = k.size;
+    float *m0 = met, *m1 = met + (1 << k.max_ab);
+    if (lane == 0) m0[0] = 0.0f;
+    __syncwarp();
+    const uint8_t *ab = k.ab + phase * (l + 1);
+    for (int j = 0; j < l; ++j) {
+        float y = chan[j * stride + i];
+        if (offs[j * stride + i]) y = -y;
+        const uint32_t hd = y < 0.0f;
+        const float ay = fabsf(y);
+        const uint32_t *tab = k.pred + k.off[phase * l + j];
+        const int ns = 1 << ab[j + 1];
+        for (int s1 = lane; s1 < ns; s1 += 32) {
+            const uint32_t e = __ldg(tab + s1);
+            float best = HUGE_VALF;
+            const uint32_t a = e & 0xFFFFu, b = e >> 16;
+            if (a != 0xFFFFu) {
+                const float v = ((a >> 15) ^ hd) ? m0[a & 0x7FFFu] + ay : m0[a & 0x7FFFu];
+                best = v < best ? v : best;
+            }
+            if (b != 0xFFFFu) {
+                const float v = ((b >> 15) ^ hd) ? m0[b & 0x7FFFu] + ay : m0[b & 0x7FFFu];
+                best = v < best ? v : best;
+            }
+            m1[s1] = best;
+        }
+        __syncwarp();
+        float *t = m0; m0 = m1; m1 = t;
+    }
+    const float r = m0[1] - m0[0];   // :292
+    __syncwarp();
+    return r;
+}
+
+// GetLLRs (TrellisKernelProcessor.cpp:234-295): offset update for the newly known input `phase-1`, then one
+// Viterbi per stride element.  known: [l][stride] decided kernel inputs; offs: [l][stride] state.
+__device__ __forceinline__ void get_llrs(const PkPolarKernelDev &k, int stride, int phase, const uint8_t *known,
+                                         const float *chan, float *out, uint8_t *offs, float *met) {
+    const int lane = threadIdx.x & 31, l = k.size;
+    if (phase == 0) {
+        for (int e = lane; e < l * stride; e += 32) offs[e] = 0;
+    } else {
+        const uint8_t *row = k.mat + (phase - 1) * l;
+        for (int e = lane; e < l * stride; e += 32) {
+            const int c = e / stride, i = e - c * stride;
+            if (row[c]) offs[e] ^= known[(phase - 1) * stride + i];
+        }
+    }
+    __syncwarp();
+    for (int i = 0; i < stride; ++i) {
+        const float v = viterbi(k, phase, stride, i, chan, offs, met);
+        if (lane == 0) out[i] = v;
+    }
+    __syncwarp();
+}
+
+// per-path shared-memory layout
+struct PathLayout {
+    int s_off[PK_POLAR_MAX_LAYERS + 1];   // S arrays of layers 1..m (floats, offset in floats)
+    int c_off[PK_POLAR_MAX_LAYERS + 1];   // C arrays of layers 0..m (bytes)
+    int o_off[PK_POLAR_MAX_LAYERS];       // kernel-processor offsets of layers 0..m-1 (bytes)
+    int u_off;                            // decided symbols, N0 bits as uint32 (bytes offset, 4-aligned)
+    int floats, bytes;                    // totals per path
+};
+__host__ __device__ inline PathLayout path_layout(const PkPolarDev &d) {
+    PathLayout p;
+    int f = 0, b = 0;
+    p.s_off[0] = 0;
+    for (int j = 1; j <= d.layers; ++j) { p.s_off[j] = f; f += d.outer[j]; }
+    for (int j = 0; j <= d.layers; ++j) { p.c_off[j] = b; b += d.outer[j] * (j > 0 ? d.ksize[j - 1] : 1); }
+    for (int j = 0; j < d.layers; ++j) { p.o_off[j] = b; b += d.outer[j]; }
+    b = (b + 3) & ~3;
+    p.u_off = b;
+    b += d.nw * 4;
+    p.floats = f;
+    p.bytes = (b + 15) & ~15;
+    return p;
+}
+
+// ------------------------------------------------------------------ encoder (a15)
+__global__ void __launch_bounds__(128)
+k_polar_encode(PkPolarDev d, const uint8_t *__restrict__ info, long B, uint8_t *__restrict__ cw) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint8_t *a = smem + (size_t)warp * 2 * d.N0, *b = a + d.N0;
+    for (long f = (long)blockIdx.x * nwarps + warp; f < B; f += (long)gridDim.x * nwarps) {
+        // information symbols in place, frozen symbols evaluated in order (MixedKernelEncoder.cpp:148-159)
+        for (int i = lane; i < d.N0; i += 32) a[i] = 0;
+        __syncwarp();
+        for (int q = lane; q < d.K; q += 32) a[d.info_pos[q]] = info[f * d.K + q] ? 1 : 0;
+        __syncwarp();
+        if (!d.all_static && lane == 0) {
+            for (int i = 0; i < d.N0; ++i) {
+                if (!d.frozen[i]) continue;
+                uint8_t v = 0;
+                for (int w = 0; w < d.nw; ++w) {
+                    uint32_t m = d.cmask[i * d.nw + w];
+                    while (m) { const int t = __ffs(m) - 1; m &= m - 1; v ^= a[32 * w + t]; }
+                }
+                a[i] = v;
+            }
+        }
+        __syncwarp();
+        // layers m-1 .. 0: blocks of size l*stride, y = x F_l on every stride element (:161-173)
+        int stride = 1;
+        for (int L = d.layers - 1; L >= 0; --L) {
+            const int l = d.ksize[L], bs = l * stride;
+            for (int e = lane; e < d.N0; e += 32) {
+                const int blk = e / bs, r0 = e - blk * bs, c = r0 / stride, i = r0 - c * stride;
+                uint8_t v = 0;
+                for (int r = 0; r < l; ++r) v ^= d.kern[L].mat[r * l + c] & a[blk * bs + r * stride + i];
+                b[e] = v;
+            }
+            __syncwarp();
+            uint8_t *t = a; a = b; b = t;
+            stride = bs;
+        }
+        // Shorten (:115-139): drop shortened / punctured symbols
+        if (!d.symtype) {
+            for (int i = lane; i < d.N0; i += 32) cw[f * d.N + i] = a[i];
+        } else if (lane == 0) {
+            int o = 0;
+            for (int i = 0; i < d.N0; ++i)
+                if (d.symtype[i] == 0) cw[f * d.N + o++] = a[i];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ kernel LLRs of independent kernel blocks (a16/a17)
+// One warp per block: phases 0..l-1 in order with the given (genie) kernel inputs, stride 1.
+__global__ void __launch_bounds__(128)
+k_polar_kernel_llr(PkPolarKernelDev k, const float *__restrict__ chan, const uint8_t *__restrict__ u, long B,
+                   float *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, l = k.size;
+    const size_t per = (size_t)(2 << k.max_ab) * 4 + 4 * l + 2 * l + 16;
+    unsigned char *wb = smem + (size_t)warp * ((per + 15) & ~(size_t)15);
+    float *met = reinterpret_cast<float *>(wb);
+    float *ch = met + (2 << k.max_ab);
+    uint8_t *known = reinterpret_cast<uint8_t *>(ch + l), *offs = known + l;
+    for (long f = (long)blockIdx.x * nwarps + warp; f < B; f += (long)gridDim.x * nwarps) {
+        for (int i = lane; i < l; i += 32) { ch[i] = chan[f * l + i]; known[i] = u[f * l + i] ? 1 : 0; }
+        __syncwarp();
+        for (int ph = 0; ph < l; ++ph) {
+            float v;
+            get_llrs(k, 1, ph, known, ch, &v, offs, met);   // out[0] written by lane 0 into v (register of lane 0)
+            v = __shfl_sync(PKP_FULL, v, 0);
+            if (lane == 0) out[f * l + ph] = v;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ SC / SC-list decoder (a18, a19)
+struct ListCtl {            // CTA-shared list state
+    float R[32];            // path metrics m_pR
+    float llr[32];          // LLR of the current phase per path
+    uint8_t active[32];
+    uint8_t cont[32];       // continuation mask: 1 = extend with 0, 2 = extend with 1, 3 = both (clone)
+    uint8_t bit[32];        // decided symbol of this phase per path
+    int8_t clone_src[32];   // for a path created in this phase: the path it was cloned from, else -1
+    uint32_t stack[34];     // inactive path indices (lazily initialised stack, misc.h:212-226)
+    float cand_m[64];
+    uint32_t cand_s[64];
+    int n_cand;
+};
+__device__ __forceinline__ uint32_t stack_pop(uint32_t *st) {
+    if (st[st[0]] == 0xFFFFFFFFu) {
+        const uint32_t s = --st[0];
+        if (s > 0) st[st[0]] = 0xFFFFFFFFu;
+        return s;
+    }
+    return st[st[0]--];
+}
+__device__ __forceinline__ void stack_push(uint32_t x, uint32_t *st) { st[++st[0]] = x; }
+
+__global__ void __launch_bounds__(1024)
+k_polar_decode(PkPolarDev d, int L, const float *__restrict__ llr_in, long B, int *__restrict__ count,
+               uint8_t *__restrict__ inf_out, uint8_t *__restrict__ cw_out, float *__restrict__ metric_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PathLayout pl = path_layout(d);
+    // shared layout: [ListCtl][chan N0 floats][per path: floats | bytes][per warp: Viterbi metrics]
+    ListCtl *lc = reinterpret_cast<ListCtl *>(smem);
+    float *chan = reinterpret_cast<float *>(smem + ((sizeof(ListCtl) + 15) & ~(size_t)15));
+    unsigned char *paths = reinterpret_cast<unsigned char *>(chan + d.N0);
+    const size_t path_sz = (((size_t)pl.floats * 4 + 15) & ~(size_t)15) + pl.bytes;
+    unsigned char *metbase = paths + (size_t)L * path_sz;
+    float *met = reinterpret_cast<float *>(metbase + (size_t)warp * (2 << d.max_ab) * 4);
+    auto pS = [&](int p) { return reinterpret_cast<float *>(paths + (size_t)p * path_sz); };
+    auto pB = [&](int p) { return paths + (size_t)p * path_sz + (((size_t)pl.floats * 4 + 15) & ~(size_t)15); };
+    const int last = d.layers - 1, lsz = d.ksize[last];
+
+    for (long f = blockIdx.x; f < B; f += gridDim.x) {
+        __syncthreads();
+        // LoadLLRs (MixedKernelEncoder.cpp:179-203)
+        if (!d.symtype) {
+            for (int i = threadIdx.x; i < d.N0; i += blockDim.x) chan[i] = llr_in[f * d.N + i];
+        } else if (threadIdx.x == 0) {
+            int o = 0;
+            for (int i = 0; i < d.N0; ++i)
+                chan[i] = d.symtype[i] == 0 ? llr_in[f * d.N + o++] : (d.symtype[i] == 1 ? PKP_UPPER : 0.0f);
+        }
+        if (threadIdx.x == 0) {
+            // Cleanup + AssignInitialPath (TVMemoryEngine.cpp:58-94)
+            lc->stack[0] = (uint32_t)L;
+            lc->stack[L] = 0xFFFFFFFFu;
+            for (int p = 0; p < 32; ++p) { lc->active[p] = 0; lc->clone_src[p] = -1; }
+            const uint32_t pid = stack_pop(lc->stack);
+            lc->active[pid] = 1;
+            lc->R[pid] = 0.0f;
+        }
+        __syncthreads();
+        if (lc->active[warp]) {
+            uint32_t *uh = reinterpret_cast<uint32_t *>(pB(warp) + pl.u_off);
+            for (int w = lane; w < d.nw; w += 32) uh[w] = 0;
+        }
+        __syncthreads();
+
+        for (int phi = 0; phi < d.N0; ++phi) {
+            // ---- every active path: LLR of symbol phi (IterativelyCalcS, KernelListEngine.cpp:370-447)
+            if (lc->active[warp]) {
+                float *S = pS(warp);
+                uint8_t *Bp = pB(warp);
+                int pv = phi, mm = last;
+                while (mm > 0 && (pv % d.ksize[mm]) == 0) { pv /= d.ksize[mm]; --mm; }
+                const float *src = (mm == 0) ? chan : S + pl.s_off[mm];
+                for (int j = mm; j <= last; ++j) {
+                    float *dest = S + pl.s_off[j + 1];
+                    get_llrs(d.kern[j], d.outer[j + 1], pv % d.ksize[j], Bp + pl.c_off[j + 1], src, dest, Bp + pl.o_off[j], met);
+                    pv = 0;
+                    src = dest;
+                }
+                if (lane == 0) lc->llr[warp] = S[pl.s_off[d.layers]];
+            }
+            __syncthreads();
+            const bool frozen = d.frozen[phi] != 0;
+            if (frozen) {
+                // ---- ContinuePathsFrozen (MixedKernelListDecoder.cpp:61-98)
+                if (lc->active[warp]) {
+                    const uint32_t *uh = reinterpret_cast<const uint32_t *>(pB(warp) + pl.u_off);
+                    uint32_t par = 0;
+                    if (!d.all_static)
+                        for (int w = lane; w < d.nw; w += 32) par ^= __popc(uh[w] & d.cmask[phi * d.nw + w]) & 1u;
+                    par = __reduce_xor_sync(PKP_FULL, par);
+                    if (lane == 0) {
+                        const float v = lc->llr[warp];
+                        if ((par != 0) ^ (v < 0.0f)) lc->R[warp] -= fabsf(v);
+                        lc->bit[warp] = (uint8_t)par;
+                    }
+                }
+            } else if (threadIdx.x < 32) {
+                // ---- ContinuePathsUnfrozen (:100-185), list bookkeeping by warp 0
+                int J = 0;
+                if (lane == 0) {
+                    for (int p = 0; p < L; ++p) {
+                        lc->cont[p] = 0;
+                        lc->clone_src[p] = -1;
+                        if (!lc->active[p]) continue;
+                        const float v = lc->llr[p];
+                        const uint32_t D = v < 0.0f;
+                        lc->cand_m[J] = lc->R[p];
+                        lc->cand_s[J] = 2u * p + D;
+                        lc->cand_m[J + 1] = lc->R[p] - fabsf(v);
+                        lc->cand_s[J + 1] = 2u * p + (D ^ 1u);
+                        J += 2;
+                    }
+                    lc->n_cand = J;
+                }
+                __syncwarp();
+                J = lc->n_cand;
+                // descending order of (metric, second) pairs (CPairComparator = std::greater<pair>): rank by counting
+                const int keep = J < L ? J : L;
+                for (int c = lane; c < J; c += 32) {
+                    const float mc = lc->cand_m[c];
+                    const uint32_t sc = lc->cand_s[c];
+                    int rank = 0;
+                    for (int k = 0; k < J; ++k) {
+                        const float mk = lc->cand_m[k];
+                        rank += (mk > mc || (mk == mc && lc->cand_s[k] > sc)) ? 1 : 0;
+                    }
+                    if (rank < keep) atomicOr(reinterpret_cast<unsigned int *>(lc->cont) + (sc >> 3), (1u << (sc & 1u)) << (8 * ((sc >> 1) & 3)));
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    for (int p = 0; p < L; ++p)
+                        if (lc->active[p] && !lc->cont[p]) { stack_push((uint32_t)p, lc->stack); lc->active[p] = 0; }   // KillPath
+                    for (int p = 0; p < L; ++p) {
+                        switch (lc->cont[p]) {
+                        case 1: lc->bit[p] = 0; break;
+                        case 2: lc->bit[p] = 1; break;
+                        case 3: {
+                            const float v = lc->llr[p];
+                            const uint8_t C = v < 0.0f ? 1 : 0;
+                            lc->bit[p] = C;
+                            const uint32_t p1 = stack_pop(lc->stack);   // ClonePath
+                            lc->bit[p1] = C ^ 1;
+                            lc->active[p1] = 1;
+                            lc->R[p1] = lc->R[p] - fabsf(v);
+                            lc->clone_src[p1] = (int8_t)p;
+                            break;
+                        }
+                        default: break;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- clones copy their parent's arrays (eager version of the reference's copy-on-write)
+            if (!frozen && lc->active[warp] && lc->clone_src[warp] >= 0) {
+                const uint32_t *s = reinterpret_cast<const uint32_t *>(paths + (size_t)lc->clone_src[warp] * path_sz);
+                uint32_t *t = reinterpret_cast<uint32_t *>(paths + (size_t)warp * path_sz);
+                for (int i = lane; i < (int)(path_sz / 4); i += 32) t[i] = s[i];
+            }
+            __syncthreads();
+            // ---- write the decided symbol and propagate completed kernel blocks (IterativelyUpdateC, :266-315)
+            if (lc->active[warp]) {
+                uint8_t *Bp = pB(warp);
+                const uint8_t C = lc->bit[warp];
+                if (lane == 0) {
+                    Bp[pl.c_off[d.layers] + (phi % lsz)] = C;
+                    uint32_t *uh = reinterpret_cast<uint32_t *>(Bp + pl.u_off);
+                    if (C) uh[phi >> 5] |= 1u << (phi & 31);
+                }
+                __syncwarp();
+                int lambda = d.layers, stride = 1, pv = phi;
+                while (lambda > 0 && ((pv + 1) % d.ksize[lambda - 1]) == 0) {
+                    const int psi = pv / d.ksize[lambda - 1];
+                    const int next = stride * d.ksize[lambda - 1];
+                    const int phi0 = (lambda > 1) ? (psi % d.ksize[lambda - 2]) * next : 0;
+                    kernel_multiply(d.kern[lambda - 1], stride, Bp + pl.c_off[lambda], Bp + pl.c_off[lambda - 1] + phi0);
+                    stride = next;
+                    pv = psi;
+                    --lambda;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- final ordering (MixedKernelListDecoder.cpp:253-266): active paths by (R, index) descending
+        if (lc->active[warp]) {
+            const float r = lc->R[warp];
+            int rank = 0;
+            for (int p = 0; p < L; ++p)
+                if (lc->active[p] && (lc->R[p] > r || (lc->R[p] == r && p > warp))) ++rank;
+            const uint8_t *Bp = pB(warp);
+            const uint32_t *uh = reinterpret_cast<const uint32_t *>(Bp + pl.u_off);
+            if (inf_out)
+                for (int q = lane; q < d.K; q += 32) {
+                    const int pos = d.info_pos[q];
+                    inf_out[(f * L + rank) * d.K + q] = (uint8_t)((uh[pos >> 5] >> (pos & 31)) & 1u);
+                }
+            if (cw_out) {
+                const uint8_t *c0 = Bp + pl.c_off[0];
+                if (!d.symtype) {
+                    for (int i = lane; i < d.N0; i += 32) cw_out[(f * L + rank) * d.N + i] = c0[i];
+                } else if (lane == 0) {
+                    int o = 0;
+                    for (int i = 0; i < d.N0; ++i)
+                        if (d.symtype[i] == 0) cw_out[(f * L + rank) * d.N + o++] = c0[i];
+                }
+            }
+            if (metric_out && lane == 0) metric_out[f * L + rank] = r;
+        }
+        if (threadIdx.x == 0 && count) {
+            int J = 0;
+            for (int p = 0; p < L; ++p) J += lc->active[p] ? 1 : 0;
+            count[f] = J;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host handle + C ABI
+struct pk_polar {
+    pk_polar_code code;
+    PkPolarDev dev{};
+    int L = 1, device = 0;
+    std::vector<void *> allocs;
+    cudaStream_t stream = nullptr;
+    size_t smem_decode = 0;
+};
+
+namespace {
+template <class Tp>
+cudaError_t up(pk_polar *h, const std::vector<Tp> &v, const Tp **d) {
+    *d = nullptr;
+    if (v.empty()) return cudaSuccess;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, v.size() * sizeof(Tp));
+    if (e != cudaSuccess) return e;
+    h->allocs.push_back(p);
+    *d = static_cast<const Tp *>(p);
+    return cudaMemcpy(p, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice);
+}
+}  // namespace
+
+extern "C" {
+
+// CMixedKernelListDecoder(std::istream& Spec, unsigned ListSize) (MixedKernelListDecoder.cpp:10): spec_text in the
+// reference's specification format, L = list size (1 = plain successive cancellation), 1 <= L <= 32.
+int pk_polar_create(const char *spec_text, int L, int device, pk_polar **out) {
+    if (!out || !spec_text) return pk_set_error(PK_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (L < 1 || L > 32) return pk_set_error(PK_ERR_ARG, "list size must be in [1,32]");
+    pk_polar *h = new (std::nothrow) pk_polar;
+    if (!h) return pk_set_error(PK_ERR_ALLOC, "out of memory");
+    std::string err = pk_polar_parse(h->code, spec_text);
+    if (!err.empty()) { delete h; return pk_set_error(PK_ERR_ARG, err); }
+    h->L = L;
+    h->device = device;
+    if (device < 0) { *out = h; return PK_OK; }   // host-only handle (introspection / CPU tests)
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { delete h; return pk_set_error(PK_ERR_CUDA, "no CUDA device: libpkb200 has no CPU path"); }
+    if (device >= ndev) { delete h; return pk_set_error(PK_ERR_ARG, "bad device ordinal"); }
+    cudaError_t e = cudaSetDevice(device);
+    const pk_polar_code &c = h->code;
+    PkPolarDev &d = h->dev;
+    d.N = c.N; d.K = c.K; d.N0 = c.N0; d.layers = c.layers; d.nw = (c.N0 + 31) / 32;
+    d.max_ab = 0;
+    std::vector<PkPolarKernelDev> kd(c.kernels.size());
+    for (size_t i = 0; i < c.kernels.size() && e == cudaSuccess; ++i) {
+        const PkKernelTrellis &k = c.kernels[i];
+        kd[i].size = k.size; kd[i].max_ab = k.max_ab;
+        e = up(h, k.matrix, &kd[i].mat);
+        if (e == cudaSuccess) e = up(h, k.ab, &kd[i].ab);
+        if (e == cudaSuccess) e = up(h, k.pred, &kd[i].pred);
+        if (e == cudaSuccess) e = up(h, k.off, &kd[i].off);
+    }
+    for (int j = 0; j < c.layers; ++j) {
+        d.ksize[j] = c.ksize[j];
+        d.kern[j] = kd[c.kid[j]];
+        d.max_ab = std::max(d.max_ab, c.kernels[c.kid[j]].max_ab);
+    }
+    for (int j = 0; j <= c.layers; ++j) d.outer[j] = c.outer[j];
+    std::vector<uint8_t> fz(c.N0);
+    bool all_static = true;
+    for (int i = 0; i < c.N0; ++i) fz[i] = c.decision[i] >= 0;
+    for (uint32_t m : c.cmask) all_static = all_static && (m == 0);
+    d.all_static = all_static ? 1 : 0;
+    std::vector<uint16_t> ip(c.info_pos.begin(), c.info_pos.end());
+    if (e == cudaSuccess) e = up(h, fz, &d.frozen);
+    if (e == cudaSuccess) e = up(h, c.cmask, &d.cmask);
+    if (e == cudaSuccess) e = up(h, ip, &d.info_pos);
+    if (e == cudaSuccess) e = up(h, c.symtype, &d.symtype);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        const PathLayout pl = path_layout(d);
+        const size_t path_sz = (((size_t)pl.floats * 4 + 15) & ~(size_t)15) + pl.bytes;
+        h->smem_decode = ((sizeof(ListCtl) + 15) & ~(size_t)15) + (size_t)d.N0 * 4 + (size_t)L * path_sz + (size_t)L * (2 << d.max_ab) * 4;
+        e = cudaFuncSetAttribute(k_polar_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_decode);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_polar_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2 * d.N0);
+    }
+    if (e != cudaSuccess) {
+        std::string msg = std::string("pk_polar_create: ") + cudaGetErrorString(e);
+        for (void *p : h->allocs) cudaFree(p);
+        delete h;
+        return pk_set_error(PK_ERR_CUDA, msg);
+    }
+    *out = h;
+    return PK_OK;
+}
+
+void pk_polar_destroy(pk_polar *h) {
+    if (!h) return;
+    if (h->device >= 0) {
+        cudaSetDevice(h->device);
+        if (h->stream) cudaStreamDestroy(h->stream);
+        for (void *p : h->allocs) cudaFree(p);
+    }
+    delete h;
+}
+
+int pk_polar_info(const pk_polar *h, int *N, int *K, int *N0, int *layers, int *L) {
+    if (!h) return pk_set_error(PK_ERR_ARG, "NULL handle");
+    if (N) *N = h->code.N;
+    if (K) *K = h->code.K;
+    if (N0) *N0 = h->code.N0;
+    if (layers) *layers = h->code.layers;
+    if (L) *L = h->L;
+    return PK_OK;
+}
+
+// number of trellis state bits after every section, per phase, of the kernel of `layer`: out[l][l+1]
+// (m_ppNumOfActiveBits, TrellisKernelProcessor.cpp:105,154)
+int pk_polar_trellis_profile(const pk_polar *h, int layer, int *size, uint8_t *out) {
+    if (!h || layer < 0 || layer >= h->code.layers) return pk_set_error(PK_ERR_ARG, "bad layer");
+    const PkKernelTrellis &k = h->code.kernels[h->code.kid[layer]];
+    if (size) *size = k.size;
+    if (out) std::memcpy(out, k.ab.data(), k.ab.size());
+    return PK_OK;
+}
+
+// (2^m) x (2^m) extended-BCH polarisation kernel (root bchCoder.cpp:356-389), row-major bytes
+int pk_make_ebch_kernel(int m, uint8_t *out) {
+    if (m < 3 || m > 5 || !out) return pk_set_error(PK_ERR_ARG, "m must be in [3,5]");
+    std::vector<uint8_t> k;
+    pk_polar_ebch_kernel(m, k);
+    std::memcpy(out, k.data(), k.size());
+    return PK_OK;
+}
+
+#define PKP_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) { cudaFree(d0); cudaFree(d1); cudaFree(d2); cudaFree(d3); cudaFree(d4); \
+            return pk_set_error(PK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); }     \
+    } while (0)
+
+// CBinaryEncoder::Encode (Codec.h:52-70; MixedKernelEncoder.cpp:142) for B frames, bits as 0/1 bytes
+int pk_polar_encode_batch(pk_polar *h, const uint8_t *info, long B, uint8_t *cw) {
+    if (!h || B < 0 || (B && (!info || !cw))) return pk_set_error(PK_ERR_ARG, "bad arguments");
+    if (h->device < 0) return pk_set_error(PK_ERR_CUDA, "host-only handle: libpkb200 has no CPU compute path");
+    if (!B) return PK_OK;
+    void *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *d3 = nullptr, *d4 = nullptr;
+    PKP_CUDA(cudaSetDevice(h->device));
+    PKP_CUDA(cudaMalloc(&d0, (size_t)B * h->code.K));
+    PKP_CUDA(cudaMalloc(&d1, (size_t)B * h->code.N));
+    PKP_CUDA(cudaMemcpyAsync(d0, info, (size_t)B * h->code.K, cudaMemcpyHostToDevice, h->stream));
+    const int grid = (int)std::min<long>((B + 3) / 4, 148L * 8);
+    k_polar_encode<<<grid, 128, 4 * 2 * h->dev.N0, h->stream>>>(h->dev, (const uint8_t *)d0, B, (uint8_t *)d1);
+    ++g_pk_launches;
+    PKP_CUDA(cudaGetLastError());
+    PKP_CUDA(cudaMemcpyAsync(cw, d1, (size_t)B * h->code.N, cudaMemcpyDeviceToHost, h->stream));
+    PKP_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d0); cudaFree(d1);
+    return PK_OK;
+}
+
+// CKernProcLLR::GetLLRs (KernProc.h:40-60; TrellisKernelProcessor.cpp:234) for B independent kernel blocks of the
+// kernel of `layer`: chan [B][l] LLRs of the kernel outputs, u [B][l] the (known) kernel inputs; out [B][l]:
+// out[b][p] = LLR of input p given inputs 0..p-1.  Stride 1.
+int pk_polar_kernel_llrs(pk_polar *h, int layer, const float *chan, const uint8_t *u, long B, float *out) {
+    if (!h || layer < 0 || layer >= h->code.layers || B < 0 || (B && (!chan || !u || !out))) return pk_set_error(PK_ERR_ARG, "bad arguments");
+    if (h->device < 0) return pk_set_error(PK_ERR_CUDA, "host-only handle: libpkb200 has no CPU compute path");
+    if (!B) return PK_OK;
+    const PkPolarKernelDev &k = h->dev.kern[layer];
+    const int l = k.size;
+    void *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *d3 = nullptr, *d4 = nullptr;
+    PKP_CUDA(cudaSetDevice(h->device));
+    PKP_CUDA(cudaMalloc(&d0, (size_t)B * l * 4));
+    PKP_CUDA(cudaMalloc(&d1, (size_t)B * l));
+    PKP_CUDA(cudaMalloc(&d2, (size_t)B * l * 4));
+    PKP_CUDA(cudaMemcpyAsync(d0, chan, (size_t)B * l * 4, cudaMemcpyHostToDevice, h->stream));
+    PKP_CUDA(cudaMemcpyAsync(d1, u, (size_t)B * l, cudaMemcpyHostToDevice, h->stream));
+    const size_t per = (((size_t)(2 << k.max_ab) * 4 + 4 * l + 2 * l + 16) + 15) & ~(size_t)15;
+    PKP_CUDA(cudaFuncSetAttribute(k_polar_kernel_llr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per)));
+    const int grid = (int)std::min<long>((B + 3) / 4, 148L * 8);
+    k_polar_kernel_llr<<<grid, 128, 4 * per, h->stream>>>(k, (const float *)d0, (const uint8_t *)d1, B, (float *)d2);
+    ++g_pk_launches;
+    PKP_CUDA(cudaGetLastError());
+    PKP_CUDA(cudaMemcpyAsync(out, d2, (size_t)B * l * 4, cudaMemcpyDeviceToHost, h->stream));
+    PKP_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d0); cudaFree(d1); cudaFree(d2);
+    return PK_OK;
+}
+
+// CBinarySoftDecoder::Decode (Codec.h:100-118; MixedKernelListDecoder.cpp:211) for B frames, device buffers,
+// asynchronous on `stream` (NULL = the handle's stream).  llr [B][N] (positive = bit 0); count [B] list entries
+// per frame; inf [B][L][K], cw [B][L][N] (may be NULL), metric [B][L] (may be NULL), best path first.
+int pk_polar_decode_batch_dev(pk_polar *h, const float *d_llr, long B, int *d_count, uint8_t *d_inf, uint8_t *d_cw,
+                              float *d_metric, void *stream) {
+    if (!h || B < 0 || (B && !d_llr)) return pk_set_error(PK_ERR_ARG, "bad arguments");
+    if (h->device < 0) return pk_set_error(PK_ERR_CUDA, "host-only handle: libpkb200 has no CPU compute path");
+    if (!B) return PK_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return pk_set_error(PK_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_polar_decode, 32 * h->L, h->smem_decode);
+    if (per_sm < 1) return pk_set_error(PK_ERR_CUDA, "polar decode kernel does not fit (list size x code length too large for shared memory)");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, h->device);
+    const int grid = (int)std::min<long>(B, (long)prop.multiProcessorCount * per_sm);
+    k_polar_decode<<<grid, 32 * h->L, h->smem_decode, st>>>(h->dev, h->L, d_llr, B, d_count, d_inf, d_cw, d_metric);
+    ++g_pk_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pk_set_error(PK_ERR_CUDA, cudaGetErrorString(e));
+    return PK_OK;
+}
+
+// same with host buffers (H2D / D2H inside the call)
+int pk_polar_decode_batch(pk_polar *h, const float *llr, long B, int *count, uint8_t *inf, uint8_t *cw, float *metric) {
+    if (!h || B < 0 || (B && (!llr || !inf))) return pk_set_error(PK_ERR_ARG, "bad arguments");
+    if (h->device < 0) return pk_set_error(PK_ERR_CUDA, "host-only handle: libpkb200 has no CPU compute path");
+    if (!B) return PK_OK;
+    const int N = h->code.N, K = h->code.K, L = h->L;
+    void *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *d3 = nullptr, *d4 = nullptr;
+    PKP_CUDA(cudaSetDevice(h->device));
+    PKP_CUDA(cudaMalloc(&d0, (size_t)B * N * 4));
+    PKP_CUDA(cudaMalloc(&d1, (size_t)B * 4));
+    PKP_CUDA(cudaMalloc(&d2, (size_t)B * L * K));
+    PKP_CUDA(cudaMalloc(&d3, (size_t)B * L * N));
+    PKP_CUDA(cudaMalloc(&d4, (size_t)B * L * 4));
+    PKP_CUDA(cudaMemcpyAsync(d0, llr, (size_t)B * N * 4, cudaMemcpyHostToDevice, h->stream));
+    PKP_CUDA(cudaMemsetAsync(d2, 0, (size_t)B * L * K, h->stream));
+    PKP_CUDA(cudaMemsetAsync(d3, 0, (size_t)B * L * N, h->stream));
+    PKP_CUDA(cudaMemsetAsync(d4, 0, (size_t)B * L * 4, h->stream));
+    int rc = pk_polar_decode_batch_dev(h, (const float *)d0, B, (int *)d1, (uint8_t *)d2, (uint8_t *)d3, (float *)d4, h->stream);
+    if (rc) { cudaFree(d0); cudaFree(d1); cudaFree(d2); cudaFree(d3); cudaFree(d4); return rc; }
+    if (count) PKP_CUDA(cudaMemcpyAsync(count, d1, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    PKP_CUDA(cudaMemcpyAsync(inf, d2, (size_t)B * L * K, cudaMemcpyDeviceToHost, h->stream));
+    if (cw) PKP_CUDA(cudaMemcpyAsync(cw, d3, (size_t)B * L * N, cudaMemcpyDeviceToHost, h->stream));
+    if (metric) PKP_CUDA(cudaMemcpyAsync(metric, d4, (size_t)B * L * 4, cudaMemcpyDeviceToHost, h->stream));
+    PKP_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d0); cudaFree(d1); cudaFree(d2); cudaFree(d3); cudaFree(d4);
+    return PK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+"""CPU: polar host logic -- extended-BCH kernel construction, specification parser and the per-phase kernel
+trellises (state-complexity profile) against the survey's table and, where oracle/_ref/libpolar_ref.so exists,
+against the reference's own CTrellisKernelProcessor."""
+import os
+
+import numpy as np
+import pytest
+
+# active-bit profile of the 16 x 16 eBCH kernel per phase (sections 0..16)
+PROFILE = {
+    0: "0 1 1 1 1 1 1 1 1 1 1 1 1 1 1 1 1", 15: "0 1 1 1 1 1 1 1 1 1 1 1 1 1 1 1 1",
+    1: "0 1 2 2 2 2 2 2 2 2 2 2 2 2 2 2 1", 14: "0 1 2 2 2 2 2 2 2 2 2 2 2 2 2 2 1",
+    2: "0 1 2 3 3 3 3 3 3 3 3 3 3 2 2 2 1", 3: "0 1 2 3 4 4 4 4 4 4 4 4 4 3 2 2 1",
+    4: "0 1 2 3 4 5 5 5 5 5 5 5 5 4 3 2 1", 11: "0 1 2 3 4 5 5 5 5 5 5 5 5 4 3 2 1",
+    5: "0 1 2 3 4 5 6 6 6 6 6 6 5 4 3 2 1", 6: "0 1 2 3 4 5 6 7 7 7 6 6 5 4 3 2 1",
+    7: "0 1 2 3 4 5 6 7 8 8 7 6 5 4 3 2 1", 8: "0 1 2 3 4 5 6 7 8 8 7 6 5 4 3 2 1",
+    9: "0 1 2 3 4 5 6 7 7 7 7 6 5 4 3 2 1", 10: "0 1 2 3 4 5 5 6 6 6 6 6 5 4 3 2 1",
+    12: "0 1 2 3 4 4 4 4 4 4 4 4 4 4 3 2 1", 13: "0 1 2 2 3 3 3 3 3 3 3 3 3 3 3 2 1",
+}
+
+
+def test_ebch_kernel_matches_committed_file_and_survey(pk):
+    E = pk.ebch_kernel(4)
+    rows = ["".join(str(v) for v in r) for r in E]
+    assert rows[0] == "1000000000000000" and rows[5] == "1110010000000000" and rows[15] == "1" * 16
+    assert list(E.sum(1)) == [1, 2, 2, 2, 2, 4, 4, 4, 4, 6, 6, 8, 8, 8, 8, 16]
+    txt = open(os.path.join(pk.SPEC_DIR, "ebch16.kernel")).read().split()
+    assert int(txt[0]) == 16 and np.array_equal(np.array(txt[1:], np.uint8).reshape(16, 16), E)
+    assert pk.ebch_kernel(3).shape == (8, 8)
+
+
+def test_spec_parser_and_trellis_profile(pk):
+    p = pk.Polar(pk.load_spec(), L=8, device=None)
+    assert (p.N, p.K, p.N0, p.layers, p.L) == (256, 128, 256, 2, 8)
+    prof = p.trellis_profile(0)
+    assert prof.shape == (16, 17) and prof.max() == 8
+    for ph, s in PROFILE.items():
+        assert list(prof[ph]) == [int(x) for x in s.split()], ph
+    # branch evaluations per kernel block: sum over phases of sum_j 2 * 2^ab[j]
+    assert int((2 * 2 ** prof[:, :16].astype(np.int64)).sum()) == 11712
+
+
+def test_spec_errors(pk):
+    good = pk.load_spec()
+    for bad in ("", "256 300 1 2 0 0", good.replace("256 128", "255 128"), good.replace("-/", "A /", 1)):
+        with pytest.raises(pk.PkError):
+            pk.Polar(bad, device=None)
+    with pytest.raises(pk.PkError):
+        pk.Polar(good, L=64, device=None)
+    with pytest.raises(pk.PkError):   # no CPU compute path
+        pk.Polar(good, device=None).encode(np.zeros((1, 128), np.uint8))
+
+
+def test_trellis_profile_equals_reference_processor(pk, oracle_mod):
+    if not oracle_mod.polar_ref_available():
+        pytest.skip("oracle/_ref/libpolar_ref.so not built")
+    _, ab = oracle_mod.polar_ref_trellis_llrs(os.path.join(pk.SPEC_DIR, "ebch16.kernel"), np.ones(16, np.float32), np.zeros(16, np.uint8))
+    assert np.array_equal(ab, pk.Polar(pk.load_spec(), device=None).trellis_profile(0))
