@@ -295,3 +295,153 @@ PK_HD uint32_t pk_bs_decode(SFn getS, uint32_t *Z, int zstride) {
     for (int b = 0; b < LB; ++b) same &= ~(cnt[b] ^ dB[b]);
     return okL & dge1 & lam0 & same;
 }
+
+// ------------------------------------------------------------------ large codes: BM state in (shared) memory
+// Same algorithm as pk_bs_decode<.., LOOP = true>, for codes whose Lambda/B planes do not fit the register file
+// ((t+1) m > 56, e.g. (127,64,21): 77 planes each, (255,139,31): 128 planes each).  Lambda and B live in a
+// lane-private column of `st` (element (k, b) of Lambda at st[(k*M + b) * sstride], of B behind it), the loops over
+// coefficients are real loops (small code), only the Chien terms are pulled into registers.
+// Z as in pk_bs_decode (may point to global scratch).
+template <int M, int T, class SFn>
+PK_HD uint32_t pk_bs_decode_mem(SFn getS, uint32_t *st, int sstride, uint32_t *Z, int zstride) {
+    constexpr int N = PkGF<M>::N;
+    constexpr int LB = (2 * T < 2) ? 1 : (2 * T < 4) ? 2 : (2 * T < 8) ? 3 : (2 * T < 16) ? 4 : 5;
+    uint32_t *Lam = st, *Bp = st + (size_t)(T + 1) * M * sstride;
+    uint32_t gamma[M], Lb[LB];
+    for (int e = 0; e < 2 * (T + 1) * M; ++e) st[(size_t)e * sstride] = 0;
+    Lam[0] = ~0u;
+    Bp[0] = ~0u;
+#pragma unroll
+    for (int b = 0; b < M; ++b) gamma[b] = 0;
+    gamma[0] = ~0u;
+#pragma unroll
+    for (int b = 0; b < LB; ++b) Lb[b] = 0;
+
+#pragma unroll 1
+    for (int it = 0; it < T; ++it) {
+        const int r = 2 * it + 1;
+        const int dl = (r - 1 < T) ? r - 1 : T, du = (r < T) ? r : T;
+        // B <- x*B (only coefficients 0..du can be non-zero afterwards)
+#pragma unroll 1
+        for (int k = du; k >= 1; --k)
+#pragma unroll
+            for (int b = 0; b < M; ++b) Bp[(size_t)(k * M + b) * sstride] = Bp[(size_t)((k - 1) * M + b) * sstride];
+#pragma unroll
+        for (int b = 0; b < M; ++b) Bp[(size_t)b * sstride] = 0;
+        uint32_t acc[2 * M - 1], delta[M];
+#pragma unroll
+        for (int b = 0; b < 2 * M - 1; ++b) acc[b] = 0;
+#pragma unroll 1
+        for (int k = 0; k <= dl; ++k) {
+            uint32_t sj[M], lk[M];
+            getS(r - k, sj);
+#pragma unroll
+            for (int b = 0; b < M; ++b) lk[b] = Lam[(size_t)(k * M + b) * sstride];
+            pk_bs_mac<M>(acc, lk, sj);
+        }
+        pk_bs_reduce<M>(acc);
+        uint32_t nz = 0;
+#pragma unroll
+        for (int b = 0; b < M; ++b) { delta[b] = acc[b]; nz |= acc[b]; }
+        uint32_t lt = 0, eq = ~0u;
+#pragma unroll
+        for (int b = LB - 1; b >= 0; --b) {
+            const uint32_t cb = 0u - (uint32_t)((it >> b) & 1);
+            lt |= eq & ~Lb[b] & cb;
+            eq &= ~(Lb[b] ^ cb);
+        }
+        const uint32_t upd = nz & (lt | eq);
+#pragma unroll 1
+        for (int k = 0; k <= du; ++k) {
+            uint32_t lk[M], bk[M];
+#pragma unroll
+            for (int b = 0; b < M; ++b) {
+                lk[b] = Lam[(size_t)(k * M + b) * sstride];
+                bk[b] = Bp[(size_t)(k * M + b) * sstride];
+            }
+#pragma unroll
+            for (int b = 0; b < 2 * M - 1; ++b) acc[b] = 0;
+            pk_bs_mac<M>(acc, gamma, lk);
+            pk_bs_mac<M>(acc, delta, bk);
+            pk_bs_reduce<M>(acc);
+#pragma unroll
+            for (int b = 0; b < M; ++b) {
+                Bp[(size_t)(k * M + b) * sstride] = (bk[b] & ~upd) | (lk[b] & upd);
+                Lam[(size_t)(k * M + b) * sstride] = acc[b];
+            }
+        }
+        uint32_t carry = ~0u;
+#pragma unroll
+        for (int b = 0; b < LB; ++b) {
+            const uint32_t rb = 0u - (uint32_t)((r >> b) & 1);
+            const uint32_t nl = ~Lb[b];
+            const uint32_t sum = rb ^ nl ^ carry;
+            carry = (rb & nl) | (carry & (rb ^ nl));
+            Lb[b] = (Lb[b] & ~upd) | (sum & upd);
+        }
+#pragma unroll
+        for (int b = 0; b < M; ++b) gamma[b] = (gamma[b] & ~upd) | (delta[b] & upd);
+        // B <- x*B for the even step r+1
+        const int du2 = (r + 1 < T) ? r + 1 : T;
+#pragma unroll 1
+        for (int k = du2; k >= 1; --k)
+#pragma unroll
+            for (int b = 0; b < M; ++b) Bp[(size_t)(k * M + b) * sstride] = Bp[(size_t)((k - 1) * M + b) * sstride];
+#pragma unroll
+        for (int b = 0; b < M; ++b) Bp[(size_t)b * sstride] = 0;
+    }
+    uint32_t okL;
+    {
+        uint32_t lt = 0, eq = ~0u;
+#pragma unroll
+        for (int b = LB - 1; b >= 0; --b) {
+            if ((T >> b) & 1) { lt |= eq & ~Lb[b]; eq &= Lb[b]; }
+            else eq &= ~Lb[b];
+        }
+        okL = lt | eq;
+    }
+    // Chien terms into registers; degree and Lambda(0) on the way
+    uint32_t term[T + 1][M], dB[LB], dge1 = 0, lam0 = 0;
+#pragma unroll
+    for (int b = 0; b < LB; ++b) dB[b] = 0;
+#pragma unroll
+    for (int k = 0; k <= T; ++k) {
+        uint32_t nzk = 0;
+#pragma unroll
+        for (int b = 0; b < M; ++b) { term[k][b] = Lam[(size_t)(k * M + b) * sstride]; nzk |= term[k][b]; }
+        if (k == 0) lam0 = nzk;
+        else {
+            dge1 |= nzk;
+#pragma unroll
+            for (int b = 0; b < LB; ++b) dB[b] = (dB[b] & ~nzk) | (((k >> b) & 1) ? nzk : 0u);
+        }
+    }
+    uint32_t cnt[LB];
+#pragma unroll
+    for (int b = 0; b < LB; ++b) cnt[b] = 0;
+#pragma unroll 1
+    for (int p = 0; p < N; ++p) {
+        uint32_t nzv = 0;
+#pragma unroll
+        for (int b = 0; b < M; ++b) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k <= T; ++k) v ^= term[k][b];
+            nzv |= v;
+        }
+        const uint32_t z = ~nzv;
+        Z[(size_t)p * zstride] = z;
+        uint32_t carry = z;
+#pragma unroll
+        for (int b = 0; b < LB; ++b) {
+            const uint32_t t2 = cnt[b] & carry;
+            cnt[b] ^= carry;
+            carry = t2;
+        }
+        PkBsChienStep<M, T, 1>::run(term);
+    }
+    uint32_t same = ~0u;
+#pragma unroll
+    for (int b = 0; b < LB; ++b) same &= ~(cnt[b] ^ dB[b]);
+    return okL & dge1 & lam0 & same;
+}

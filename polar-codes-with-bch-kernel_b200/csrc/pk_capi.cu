@@ -55,6 +55,7 @@ struct pk_kaneko {
     // slots 0/1 = the handle's two pipeline streams, slot 2 = caller-supplied streams
     PkPhaseCtl *d_ctl = nullptr;              // [3]
     PkLongRec *d_longs[3] = {nullptr, nullptr, nullptr};
+    uint32_t *d_zscr[3] = {nullptr, nullptr, nullptr};   // root-word scratch of the large-code phase B
     long long_cap = 1L << 18;                 // frames per launch pair (and capacity of a list)
     unsigned long long *d_totals = nullptr;   // [8]
     unsigned long long *h_totals = nullptr;   // pinned [8]
@@ -296,7 +297,7 @@ void pk_kaneko_destroy(pk_kaneko *d) {
         cudaFree(d->d_y[s]); cudaFree(d->d_dec[s]); cudaFree(d->d_tr[s]); cudaFree(d->d_rec[s]);
     }
     cudaFree(d->d_ctl);
-    for (int i = 0; i < 3; ++i) cudaFree(d->d_longs[i]);
+    for (int i = 0; i < 3; ++i) { cudaFree(d->d_longs[i]); cudaFree(d->d_zscr[i]); }
     cudaFree(d->d_totals);
     cudaFree(d->d_grec);
     if (d->h_totals) cudaFreeHost(d->h_totals);
@@ -331,6 +332,11 @@ static int launch_pairs(pk_kaneko *d, int slot, bool gen, PkIo io, long B, cudaS
     const pk_code *c = d->code;
     const bool wide = d->geom4[gen ? 3 : 1].grid > 0;
     if (wide && !d->d_longs[slot]) PK_CUDA(cudaMalloc(&d->d_longs[slot], (size_t)d->long_cap * sizeof(PkLongRec)));
+    if (wide && !c->use_lut && (c->t + 1) * c->m > 56 && !d->d_zscr[slot]) {
+        const int gmax = std::max(d->geom4[1].grid, d->geom4[3].grid);
+        PK_CUDA(cudaMalloc(&d->d_zscr[slot], (size_t)gmax * 4 * c->n * 32 * sizeof(uint32_t)));
+    }
+    io.zscratch = d->d_zscr[slot];
     for (long off = 0; off < B; off += d->long_cap) {
         const long nb = std::min(d->long_cap, B - off);
         PkIo part = io;

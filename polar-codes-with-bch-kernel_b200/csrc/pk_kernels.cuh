@@ -73,6 +73,8 @@ template <int M, int T>
 struct PkTraits {
     static constexpr bool LUT_OK = (T * M <= 15);                 // u16 coset-table entry fits
     static constexpr bool BS_OK = ((T + 1) * M <= 56) && !LUT_OK; // bit-sliced decoder fits the register file
+    static constexpr bool BSM_OK = !LUT_OK && !BS_OK;             // bit-sliced decoder with its BM state in shared memory
+    static constexpr int MINB = BSM_OK ? 2 : 3;                   // phase-B CTAs per SM the register budget is set for
 };
 
 // ------------------------------------------------------------------ shared memory plan
@@ -104,11 +106,18 @@ struct PkSmem {
     static constexpr size_t W_WL = W_PB + W_PB_SZ;                                  // double[32] in-word pattern reliabilities (LUT)
     static constexpr size_t W_WL_SZ = LUT ? 256 : 0;
     static constexpr size_t W_Z = W_WL + W_WL_SZ;                                   // uint32[N][33] root words (bit-sliced)
-    static constexpr size_t W_Z_SZ = LUT ? 0 : pk_align16((size_t)C::N * 33 * 4);
-    static constexpr size_t W_SZ_B = W_Z + W_Z_SZ;
+    static constexpr bool BSM = !LUT && ((T + 1) * M > 56);                         // BM state in shared memory, Z in global scratch
+    static constexpr size_t W_Z_SZ = (LUT || BSM) ? 0 : pk_align16((size_t)C::N * 33 * 4);
+    static constexpr size_t W_ST = W_Z + W_Z_SZ;                                    // uint32[2][(T+1)*M][32] Lambda / B planes (BSM)
+    static constexpr size_t W_ST_SZ = BSM ? (size_t)2 * (T + 1) * M * 32 * 4 : 0;
+    static constexpr size_t W_SZ_B = W_ST + W_ST_SZ;
+    static constexpr int ZS = BSM ? 32 : 33;                                        // stride of the root-word buffer
     __host__ __device__ static constexpr size_t tables(int nk) { return LUT_OFF + pk_align16(lut_sz(nk)); }
     __host__ __device__ static constexpr size_t total_a(int nk) { return tables(nk) + (size_t)PK_WARPS_A * W_SZ_A; }
-    __host__ __device__ static constexpr size_t total_b(int nk) { return tables(nk) + (size_t)PK_WARPS_B * W_SZ_B; }
+    // phase B of the bit-sliced codes needs neither the GF product table nor the Chien offsets: columns only
+    static constexpr size_t B_COL_OFF = LUT ? COL_OFF : 0;
+    __host__ __device__ static constexpr size_t tables_b(int nk) { return LUT ? tables(nk) : COL_SZ; }
+    __host__ __device__ static constexpr size_t total_b(int nk) { return tables_b(nk) + (size_t)PK_WARPS_B * W_SZ_B; }
 };
 
 template <int NW>
@@ -135,7 +144,7 @@ struct KanekoWarp {
     struct WarpMem {     // per-warp shared scratch
         double *alpha, *skey, *pref;
         uint8_t *sidx;
-        uint32_t *cm, *pb, *z;
+        uint32_t *cm, *pb, *z, *st;
         double *wl;
     };
     struct Frame {       // per-frame registers
@@ -163,6 +172,7 @@ struct KanekoWarp {
         w.pb = reinterpret_cast<uint32_t *>(wb + SM::W_PB);
         w.z = reinterpret_cast<uint32_t *>(wb + SM::W_Z);
         w.wl = reinterpret_cast<double *>(wb + SM::W_WL);
+        w.st = reinterpret_cast<uint32_t *>(wb + SM::W_ST);
         return w;
     }
 
@@ -589,7 +599,10 @@ struct KanekoWarp {
 #pragma unroll
                     for (int b = 0; b < M; ++b) o[b] = wm.cm[(j - 1) * M + b] ^ (0u - ((uw >> b) & 1u));
                 };
-                cand = pk_bs_decode<M, T, PK_BS_LOOP>(getS, wm.z + lane, 33) & vmask;
+                if constexpr (SM::BSM)
+                    cand = pk_bs_decode_mem<M, T>(getS, wm.st + lane, 32, wm.z + lane, SM::ZS) & vmask;
+                else
+                    cand = pk_bs_decode<M, T, PK_BS_LOOP>(getS, wm.z + lane, SM::ZS) & vmask;
             }
             __syncwarp();
 
@@ -603,7 +616,7 @@ struct KanekoWarp {
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {
                         const int p = lane + 32 * w;
-                        const uint32_t zb = (p < N) ? ((wm.z[p * 33 + src] >> q) & 1u) : 0u;
+                        const uint32_t zb = (p < N) ? ((wm.z[p * SM::ZS + src] >> q) & 1u) : 0u;
                         A[w] = __ballot_sync(PK_FULL, zb);
                     }
                 }
@@ -754,7 +767,7 @@ __device__ __forceinline__ void pk_stage_tables(unsigned char *smem, const PkDev
             uint16_t *xo = reinterpret_cast<uint16_t *>(smem + SM::XOFF_OFF);
             for (int i = tid; i < C::N; i += nth) xo[i] = tb.xoff[i];
         }
-        uint32_t *col = reinterpret_cast<uint32_t *>(smem + SM::COL_OFF);
+        uint32_t *col = reinterpret_cast<uint32_t *>(smem + (need_mul ? SM::COL_OFF : SM::B_COL_OFF));
         for (int i = tid; i < C::N * SM::SW; i += nth) col[i] = tb.hcol[i];
     } else {
         uint32_t *col = reinterpret_cast<uint32_t *>(smem + SM::COL_OFF);
@@ -984,7 +997,7 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
 
 // ------------------------------------------------------------------ phase B
 template <int M, int T, bool LUT, bool GEN>
-__global__ void __launch_bounds__(PK_WARPS_B * 32, 3)
+__global__ void __launch_bounds__(PK_WARPS_B * 32, PkTraits<M, T>::MINB)
 k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkLongRec *longs, long long_cap) {
     typedef PkSmem<M, T, LUT> SM;
     typedef KanekoWarp<M, T, LUT> KW;
@@ -994,14 +1007,16 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
     if (n_long + n_big == 0) return;
     pk_stage_tables<M, T, LUT>(smem, tb, false);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *wb = smem + SM::tables(tb.nk) + (size_t)warp * SM::W_SZ_B;
+    unsigned char *wb = smem + SM::tables_b(tb.nk) + (size_t)warp * SM::W_SZ_B;
     typename KW::WarpMem wm = KW::warp_mem(wb);
     uint32_t *w_u = reinterpret_cast<uint32_t *>(wb + SM::W_U);
     typename KW::Tables tabs;
-    tabs.mul = smem + SM::MUL_OFF;
-    tabs.xoff = reinterpret_cast<const uint16_t *>(smem + SM::XOFF_OFF);
-    tabs.col = reinterpret_cast<const uint32_t *>(smem + SM::COL_OFF);
+    tabs.mul = nullptr;    // the wide search is bit-sliced or table-driven by the coset table only
+    tabs.xoff = nullptr;
+    tabs.col = reinterpret_cast<const uint32_t *>(smem + SM::B_COL_OFF);
     tabs.lut = reinterpret_cast<const uint16_t *>(smem + SM::LUT_OFF);
+    if constexpr (SM::BSM)   // root words of the bit-sliced Chien search go to a per-warp slice of global scratch
+        wm.z = io.zscratch + ((size_t)blockIdx.x * PK_WARPS_B + warp) * (size_t)KW::N * 32;
     __shared__ typename KW::Search s_shared;
     __shared__ unsigned long long s_idx;
     __shared__ uint32_t s_votes[2 * PK_WARPS_B];
@@ -1159,7 +1174,7 @@ struct PkLaunch {
         ga->block = PK_WARPS_A * 32;
         ga->smem = sa;
         gb->grid = 0; gb->block = PK_WARPS_B * 32; gb->smem = 0;
-        if constexpr (LUT || TR::BS_OK) {
+        if constexpr (true) {
             const size_t sb = PkSmem<M, T, LUT>::total_b(nk);
             e = cudaFuncSetAttribute(k_phase_b<M, T, LUT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
             if (e != cudaSuccess) return e;
@@ -1206,12 +1221,12 @@ struct PkLaunch {
                            PkPhaseCtl *ctl, PkLongRec *longs, long long_cap, cudaStream_t st) {
         cudaError_t e = cudaMemsetAsync(ctl, 0, sizeof(PkPhaseCtl), st);
         if (e != cudaSuccess) return e;
-        const bool wide_ok = (LUT || TR::BS_OK) && g[1].grid > 0 && long_cap > 0 && !(GEN && io.dump_only);
+        const bool wide_ok = g[1].grid > 0 && long_cap > 0 && !(GEN && io.dump_only);
         k_phase_a<M, T, LUT, GEN><<<g[0].grid, g[0].block, g[0].smem, st>>>(tb, kp, io, B, ctl, longs, wide_ok ? long_cap : 0);
         ++g_pk_launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        if constexpr (LUT || TR::BS_OK) {
+        if constexpr (true) {
             if (wide_ok) {
                 k_phase_b<M, T, LUT, GEN><<<g[1].grid, g[1].block, g[1].smem, st>>>(tb, kp, io, ctl, longs, long_cap);
                 ++g_pk_launches;
@@ -1248,6 +1263,6 @@ struct PkLaunch {
     }
 
     static constexpr PkKernelSet make() {
-        return PkKernelSet{M, T, TR::BS_OK, &host_alg, &geom_kaneko, &geom_bdd, &kaneko, &bdd, &encode};
+        return PkKernelSet{M, T, !TR::LUT_OK, &host_alg, &geom_kaneko, &geom_bdd, &kaneko, &bdd, &encode};
     }
 };

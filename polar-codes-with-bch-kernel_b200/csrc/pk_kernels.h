@@ -37,6 +37,7 @@ struct PkIo {
     double *d_y;
     int dump_only;
     // both
+    uint32_t *zscratch;   // phase B of large codes: root-word scratch, grid_b * 4 warps * n * 32 words
     pk_frame_rec *recs;
     unsigned long long *totals;
 };

@@ -60,3 +60,22 @@ def test_sc_list_decoder_matches_reference(pk, need_ref, L, B, snr):
     assert np.array_equal(g_inf, r_inf) and np.array_equal(g_cw, r_cw)
     # the decoder finds the sent word more often as L grows; at least sanity-check it decodes something
     assert (g_inf[:, 0, :] == info).all(1).mean() > 0.2
+
+
+def test_against_committed_golden_vectors(pk):
+    """Same checks against tests/golden/polar_vectors.npz (made from the reference library by
+    tests/golden/make_golden_polar.py) -- does not need oracle/_ref at run time."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "polar_vectors.npz"))
+    spec = pk.load_spec()
+    p1 = pk.Polar(spec, L=1, device=0)
+    got = p1.kernel_llrs(z["kernel_chan"], z["kernel_u"], layer=1)
+    assert np.array_equal(got.view(np.uint32), z["kernel_llr"].view(np.uint32))
+    for L in (1, 8, 32):
+        p = pk.Polar(spec, L=L, device=0)
+        k = f"L{L}"
+        info = np.unpackbits(z[k + "_info"], axis=1)[:, : p.K]
+        assert np.array_equal(np.packbits(p.encode(info), axis=1), z[k + "_cw"])
+        cnt, inf, cw, met = p.decode(z[k + "_llr"])
+        assert np.array_equal(cnt, z[k + "_count"])
+        assert np.array_equal(met.view(np.uint32), z[k + "_metric"].view(np.uint32))
+        assert np.array_equal(np.packbits(inf, axis=2), z[k + "_inf"])
