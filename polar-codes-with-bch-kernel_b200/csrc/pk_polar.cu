@@ -38,7 +38,7 @@ struct PkPolarKernelDev {
     const uint8_t *ab;     // [l][l+1]
     const uint32_t *pred;
     const uint32_t *off;   // [l*l]
-    int size, max_ab;
+    int size, max_ab, npred;
 };
 struct PkPolarDev {
     int N, K, N0, layers, nw;
@@ -53,6 +53,9 @@ struct PkPolarDev {
     int max_ab;                // over layers
 };
 
+// floats of Viterbi scratch per warp: 2 * 2^max_ab for lanes-across-states, 32 slices of 33 for lane-per-element
+__host__ __device__ inline int polar_met_floats(int max_ab) { return (2 << max_ab) + 2 > 1120 ? (2 << max_ab) + 2 : 1120; }
+
 // ------------------------------------------------------------------ shared building blocks
 // dest[c*stride + i] (^)= XOR_r K[r][c] * src[r*stride + i]   (MatrixMultiply, LinAlg.cpp:685-711), one warp
 __device__ __forceinline__ void kernel_multiply(const PkPolarKernelDev &k, int stride, const uint8_t *src, uint8_t *dest) {
@@ -66,35 +69,29 @@ __device__ __forceinline__ void kernel_multiply(const PkPolarKernelDev &k, int s
     __syncwarp();
 }
 
-// min-sum Viterbi of one kernel phase for stride element i (TrellisKernelProcessor.cpp:260-293), one warp.
-// met: 2 << max_ab floats of warp-private shared memory.
-__device__ __forceinline__ float viterbi(const PkPolarKernelDev &k, int phase, int stride, int i, const float *chan,
-                                         const uint8_t *offs, float *met) {
-    const int lane = threadIdx.x & 31, l = k.size;
-    float *m0 = met, *m1 = met + (1 << k.max_ab);
-    if (lane == 0) m0[0] = 0.0f;
+// min-sum Viterbi of one kernel phase for stride element i (TrellisKernelProcessor.cpp:260-293), one warp,
+// lanes across the next states.  sec[j] = offset of section j's predecessor table | (state bits after j) << 24.
+// A predecessor entry holds two (state | branch bit << 15) halves; a missing branch points to the DUMMY state
+// (index 2^max_ab) whose metric is +inf, which keeps the loop branch-free: x + 0.0f and min(x, inf) are exact.
+// m0/m1: 2^max_ab + 1 floats each of warp-private shared memory.
+__device__ __forceinline__ float viterbi(const uint32_t *__restrict__ pred, const uint32_t *__restrict__ sec, int l, int stride,
+                                         int dummy, const float *chan, const uint8_t *offs, float *m0, float *m1) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) { m0[0] = 0.0f; m0[dummy] = HUGE_VALF; m1[dummy] = HUGE_VALF; }
     __syncwarp();
-    const uint8_t *ab = k.ab + phase * (l + 1);
     for (int j = 0; j < l; ++j) {
-        float y = chan[j * stride + i];
-        if (offs[j * stride + i]) y = -y;
+        float y = chan[j * stride];
+        if (offs[j * stride]) y = -y;
         const uint32_t hd = y < 0.0f;
         const float ay = fabsf(y);
-        const uint32_t *tab = k.pred + k.off[phase * l + j];
-        const int ns = 1 << ab[j + 1];
+        const uint32_t sj = sec[j];
+        const uint32_t *tab = pred + (sj & 0xFFFFFFu);
+        const int ns = 1 << (sj >> 24);
         for (int s1 = lane; s1 < ns; s1 += 32) {
-            const uint32_t e = __ldg(tab + s1);
-            float best = HUGE_VALF;
-            const uint32_t a = e & 0xFFFFu, b = e >> 16;
-            if (a != 0xFFFFu) {
-                const float v = ((a >> 15) ^ hd) ? m0[a & 0x7FFFu] + ay : m0[a & 0x7FFFu];
-                best = v < best ? v : best;
-            }
-            if (b != 0xFFFFu) {
-                const float v = ((b >> 15) ^ hd) ? m0[b & 0x7FFFu] + ay : m0[b & 0x7FFFu];
-                best = v < best ? v : best;
-            }
-            m1[s1] = best;
+            const uint32_t e = tab[s1];
+            const float va = m0[e & 0x7FFFu] + ((((e >> 15) & 1u) ^ hd) ? ay : 0.0f);
+            const float vb = m0[(e >> 16) & 0x7FFFu] + (((e >> 31) ^ hd) ? ay : 0.0f);
+            m1[s1] = vb < va ? vb : va;
         }
         __syncwarp();
         float *t = m0; m0 = m1; m1 = t;
@@ -102,6 +99,35 @@ __device__ __forceinline__ float viterbi(const PkPolarKernelDev &k, int phase, i
     const float r = m0[1] - m0[0];   // :292
     __syncwarp();
     return r;
+}
+
+// Same recursion with ONE LANE PER STRIDE ELEMENT (lanes 0..stride-1 each walk their own trellis sequentially):
+// used at the outer layers when the phase's trellis is small (<= 16 states), where lanes-across-states would
+// leave the warp idle.  met: lane-private slice of 2 * 17 floats (index 16 = DUMMY).  Same float operations.
+__device__ __forceinline__ float viterbi_lane(const uint32_t *__restrict__ pred, const uint32_t *__restrict__ sec, int l, int stride,
+                                              const float *chan, const uint8_t *offs, float *met) {
+    float *m0 = met, *m1 = met + 17;
+    m0[0] = 0.0f;
+    m0[16] = HUGE_VALF;
+    m1[16] = HUGE_VALF;
+    for (int j = 0; j < l; ++j) {
+        float y = chan[j * stride];
+        if (offs[j * stride]) y = -y;
+        const uint32_t hd = y < 0.0f;
+        const float ay = fabsf(y);
+        const uint32_t sj = sec[j];
+        const uint32_t *tab = pred + (sj & 0xFFFFFFu);
+        const int ns = 1 << (sj >> 24);
+        for (int s1 = 0; s1 < ns; ++s1) {
+            const uint32_t e = tab[s1];
+            const uint32_t ia = min(e & 0x7FFFu, 16u), ib = min((e >> 16) & 0x7FFFu, 16u);
+            const float va = m0[ia] + ((((e >> 15) & 1u) ^ hd) ? ay : 0.0f);
+            const float vb = m0[ib] + (((e >> 31) ^ hd) ? ay : 0.0f);
+            m1[s1] = vb < va ? vb : va;
+        }
+        float *t = m0; m0 = m1; m1 = t;
+    }
+    return m0[1] - m0[0];
 }
 
 // GetLLRs (TrellisKernelProcessor.cpp:234-295): offset update for the newly known input `phase-1`, then one
@@ -119,9 +145,20 @@ __device__ __forceinline__ void get_llrs(const PkPolarKernelDev &k, int stride, 
         }
     }
     __syncwarp();
-    for (int i = 0; i < stride; ++i) {
-        const float v = viterbi(k, phase, stride, i, chan, offs, met);
-        if (lane == 0) out[i] = v;
+    const uint32_t *pred = k.pred, *sec = k.off + phase * l;   // off[] holds the packed section words
+    const int mab = k.ab[phase * (l + 1)];                     // ab[p][0] carries the phase's state complexity
+    if (stride > 1 && mab <= 4) {
+        for (int i0 = 0; i0 < stride; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < stride) out[i] = viterbi_lane(pred, sec, l, stride, chan + i, offs + i, met + lane * 35);   // 35: conflict-free slices
+        }
+    } else {
+        const int dummy = 1 << k.max_ab;
+        float *m0 = met, *m1 = met + dummy + 1;
+        for (int i = 0; i < stride; ++i) {
+            const float v = viterbi(pred, sec, l, stride, dummy, chan + i, offs + i, m0, m1);
+            if (lane == 0) out[i] = v;
+        }
     }
     __syncwarp();
 }
@@ -206,10 +243,10 @@ k_polar_kernel_llr(PkPolarKernelDev k, const float *__restrict__ chan, const uin
                    float *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, l = k.size;
-    const size_t per = (size_t)(2 << k.max_ab) * 4 + 4 * l + 2 * l + 16;
+    const size_t per = (size_t)polar_met_floats(k.max_ab) * 4 + 4 * l + 2 * l + 16;
     unsigned char *wb = smem + (size_t)warp * ((per + 15) & ~(size_t)15);
     float *met = reinterpret_cast<float *>(wb);
-    float *ch = met + (2 << k.max_ab);
+    float *ch = met + polar_met_floats(k.max_ab);
     uint8_t *known = reinterpret_cast<uint8_t *>(ch + l), *offs = known + l;
     for (long f = (long)blockIdx.x * nwarps + warp; f < B; f += (long)gridDim.x * nwarps) {
         for (int i = lane; i < l; i += 32) { ch[i] = chan[f * l + i]; known[i] = u[f * l + i] ? 1 : 0; }
@@ -247,83 +284,129 @@ __device__ __forceinline__ uint32_t stack_pop(uint32_t *st) {
 }
 __device__ __forceinline__ void stack_push(uint32_t x, uint32_t *st) { st[++st[0]] = x; }
 
+
+// copies the tables of every distinct kernel into shared memory and returns descriptors pointing there
+__device__ __forceinline__ void stage_polar_tables(const PkPolarDev &d, PkPolarKernelDev *sk, unsigned char *&sm) {
+    for (int j = 0; j < d.layers; ++j) {
+        int same = -1;
+        for (int i = 0; i < j; ++i)
+            if (d.kern[i].pred == d.kern[j].pred) same = i;
+        if (same >= 0) { sk[j] = sk[same]; continue; }
+        const PkPolarKernelDev &g = d.kern[j];
+        const int l = g.size;
+        uint32_t *pred = reinterpret_cast<uint32_t *>(sm);
+        uint32_t *off = pred + g.npred;
+        uint8_t *ab = reinterpret_cast<uint8_t *>(off + l * l);
+        uint8_t *mat = ab + l * (l + 1);
+        for (int i = threadIdx.x; i < g.npred; i += blockDim.x) pred[i] = g.pred[i];
+        for (int i = threadIdx.x; i < l * l; i += blockDim.x) { off[i] = g.off[i]; mat[i] = g.mat[i]; }
+        for (int i = threadIdx.x; i < l * (l + 1); i += blockDim.x) ab[i] = g.ab[i];
+        sk[j] = g;
+        sk[j].pred = pred; sk[j].off = off; sk[j].ab = ab; sk[j].mat = mat;
+        sm += ((size_t)g.npred * 4 + (size_t)l * l * 4 + (size_t)l * (l + 1) + (size_t)l * l + 15) & ~(size_t)15;
+    }
+    __syncthreads();
+}
+__host__ inline size_t polar_table_bytes(const PkPolarDev &d) {
+    size_t t = 0;
+    for (int j = 0; j < d.layers; ++j) {
+        bool dup = false;
+        for (int i = 0; i < j; ++i) dup = dup || d.kern[i].pred == d.kern[j].pred;
+        if (dup) continue;
+        const int l = d.kern[j].size;
+        t += ((size_t)d.kern[j].npred * 4 + (size_t)l * l * 4 + (size_t)l * (l + 1) + (size_t)l * l + 15) & ~(size_t)15;
+    }
+    return t;
+}
+
+// CTA = FPC frames x L list paths, one warp per (frame, path).  All frames of a CTA walk the N0 phases in lock
+// step (the frozen pattern is a property of the code), so CTA-wide barriers are uniform.
 __global__ void __launch_bounds__(1024)
-k_polar_decode(PkPolarDev d, int L, const float *__restrict__ llr_in, long B, int *__restrict__ count,
+k_polar_decode(PkPolarDev d, int L, int FPC, const float *__restrict__ llr_in, long B, int *__restrict__ count,
                uint8_t *__restrict__ inf_out, uint8_t *__restrict__ cw_out, float *__restrict__ metric_out) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ PkPolarKernelDev sk[PK_POLAR_MAX_LAYERS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fi = warp / L, path = warp - fi * L;           // frame slot in the CTA, list path
     const PathLayout pl = path_layout(d);
-    // shared layout: [ListCtl][chan N0 floats][per path: floats | bytes][per warp: Viterbi metrics]
-    ListCtl *lc = reinterpret_cast<ListCtl *>(smem);
-    float *chan = reinterpret_cast<float *>(smem + ((sizeof(ListCtl) + 15) & ~(size_t)15));
-    unsigned char *paths = reinterpret_cast<unsigned char *>(chan + d.N0);
+    unsigned char *sm = smem;
+    stage_polar_tables(d, sk, sm);
+    // shared layout after the tables: per frame [ListCtl][chan N0 floats][L paths], then per warp Viterbi scratch
     const size_t path_sz = (((size_t)pl.floats * 4 + 15) & ~(size_t)15) + pl.bytes;
-    unsigned char *metbase = paths + (size_t)L * path_sz;
-    float *met = reinterpret_cast<float *>(metbase + (size_t)warp * (2 << d.max_ab) * 4);
+    const size_t frame_sz = ((sizeof(ListCtl) + 15) & ~(size_t)15) + (size_t)d.N0 * 4 + (size_t)L * path_sz;
+    unsigned char *fb = sm + (size_t)fi * frame_sz;
+    ListCtl *lc = reinterpret_cast<ListCtl *>(fb);
+    float *chan = reinterpret_cast<float *>(fb + ((sizeof(ListCtl) + 15) & ~(size_t)15));
+    unsigned char *paths = reinterpret_cast<unsigned char *>(chan + d.N0);
+    float *met = reinterpret_cast<float *>(sm + (size_t)FPC * frame_sz) + (size_t)warp * polar_met_floats(d.max_ab);
     auto pS = [&](int p) { return reinterpret_cast<float *>(paths + (size_t)p * path_sz); };
     auto pB = [&](int p) { return paths + (size_t)p * path_sz + (((size_t)pl.floats * 4 + 15) & ~(size_t)15); };
     const int last = d.layers - 1, lsz = d.ksize[last];
 
-    for (long f = blockIdx.x; f < B; f += gridDim.x) {
+    for (long f0 = (long)blockIdx.x * FPC; f0 < B; f0 += (long)gridDim.x * FPC) {
+        const long f = f0 + fi;
+        const bool live = f < B;       // a frame slot past the end idles but keeps the barriers
         __syncthreads();
-        // LoadLLRs (MixedKernelEncoder.cpp:179-203)
-        if (!d.symtype) {
-            for (int i = threadIdx.x; i < d.N0; i += blockDim.x) chan[i] = llr_in[f * d.N + i];
-        } else if (threadIdx.x == 0) {
-            int o = 0;
-            for (int i = 0; i < d.N0; ++i)
-                chan[i] = d.symtype[i] == 0 ? llr_in[f * d.N + o++] : (d.symtype[i] == 1 ? PKP_UPPER : 0.0f);
-        }
-        if (threadIdx.x == 0) {
-            // Cleanup + AssignInitialPath (TVMemoryEngine.cpp:58-94)
-            lc->stack[0] = (uint32_t)L;
-            lc->stack[L] = 0xFFFFFFFFu;
-            for (int p = 0; p < 32; ++p) { lc->active[p] = 0; lc->clone_src[p] = -1; }
-            const uint32_t pid = stack_pop(lc->stack);
-            lc->active[pid] = 1;
-            lc->R[pid] = 0.0f;
+        if (live) {
+            // LoadLLRs (MixedKernelEncoder.cpp:179-203)
+            if (!d.symtype) {
+                for (int i = path * 32 + lane; i < d.N0; i += 32 * L) chan[i] = llr_in[f * d.N + i];
+            } else if (path == 0 && lane == 0) {
+                int o = 0;
+                for (int i = 0; i < d.N0; ++i)
+                    chan[i] = d.symtype[i] == 0 ? llr_in[f * d.N + o++] : (d.symtype[i] == 1 ? PKP_UPPER : 0.0f);
+            }
+            if (path == 0 && lane == 0) {
+                // Cleanup + AssignInitialPath (TVMemoryEngine.cpp:58-94)
+                lc->stack[0] = (uint32_t)L;
+                lc->stack[L] = 0xFFFFFFFFu;
+                for (int p = 0; p < 32; ++p) { lc->active[p] = 0; lc->clone_src[p] = -1; }
+                const uint32_t pid = stack_pop(lc->stack);
+                lc->active[pid] = 1;
+                lc->R[pid] = 0.0f;
+            }
         }
         __syncthreads();
-        if (lc->active[warp]) {
-            uint32_t *uh = reinterpret_cast<uint32_t *>(pB(warp) + pl.u_off);
+        if (live && lc->active[path]) {
+            uint32_t *uh = reinterpret_cast<uint32_t *>(pB(path) + pl.u_off);
             for (int w = lane; w < d.nw; w += 32) uh[w] = 0;
         }
         __syncthreads();
 
         for (int phi = 0; phi < d.N0; ++phi) {
             // ---- every active path: LLR of symbol phi (IterativelyCalcS, KernelListEngine.cpp:370-447)
-            if (lc->active[warp]) {
-                float *S = pS(warp);
-                uint8_t *Bp = pB(warp);
+            if (live && lc->active[path]) {
+                float *S = pS(path);
+                uint8_t *Bp = pB(path);
                 int pv = phi, mm = last;
                 while (mm > 0 && (pv % d.ksize[mm]) == 0) { pv /= d.ksize[mm]; --mm; }
                 const float *src = (mm == 0) ? chan : S + pl.s_off[mm];
                 for (int j = mm; j <= last; ++j) {
                     float *dest = S + pl.s_off[j + 1];
-                    get_llrs(d.kern[j], d.outer[j + 1], pv % d.ksize[j], Bp + pl.c_off[j + 1], src, dest, Bp + pl.o_off[j], met);
+                    get_llrs(sk[j], d.outer[j + 1], pv % d.ksize[j], Bp + pl.c_off[j + 1], src, dest, Bp + pl.o_off[j], met);
                     pv = 0;
                     src = dest;
                 }
-                if (lane == 0) lc->llr[warp] = S[pl.s_off[d.layers]];
+                if (lane == 0) lc->llr[path] = S[pl.s_off[d.layers]];
             }
             __syncthreads();
             const bool frozen = d.frozen[phi] != 0;
             if (frozen) {
                 // ---- ContinuePathsFrozen (MixedKernelListDecoder.cpp:61-98)
-                if (lc->active[warp]) {
-                    const uint32_t *uh = reinterpret_cast<const uint32_t *>(pB(warp) + pl.u_off);
+                if (live && lc->active[path]) {
+                    const uint32_t *uh = reinterpret_cast<const uint32_t *>(pB(path) + pl.u_off);
                     uint32_t par = 0;
                     if (!d.all_static)
                         for (int w = lane; w < d.nw; w += 32) par ^= __popc(uh[w] & d.cmask[phi * d.nw + w]) & 1u;
                     par = __reduce_xor_sync(PKP_FULL, par);
                     if (lane == 0) {
-                        const float v = lc->llr[warp];
-                        if ((par != 0) ^ (v < 0.0f)) lc->R[warp] -= fabsf(v);
-                        lc->bit[warp] = (uint8_t)par;
+                        const float v = lc->llr[path];
+                        if ((par != 0) ^ (v < 0.0f)) lc->R[path] -= fabsf(v);
+                        lc->bit[path] = (uint8_t)par;
                     }
                 }
-            } else if (threadIdx.x < 32) {
-                // ---- ContinuePathsUnfrozen (:100-185), list bookkeeping by warp 0
+            } else if (live && path == 0) {
+                // ---- ContinuePathsUnfrozen (:100-185), list bookkeeping by the first warp of the frame
                 int J = 0;
                 if (lane == 0) {
                     for (int p = 0; p < L; ++p) {
@@ -380,16 +463,16 @@ k_polar_decode(PkPolarDev d, int L, const float *__restrict__ llr_in, long B, in
             }
             __syncthreads();
             // ---- clones copy their parent's arrays (eager version of the reference's copy-on-write)
-            if (!frozen && lc->active[warp] && lc->clone_src[warp] >= 0) {
-                const uint32_t *s = reinterpret_cast<const uint32_t *>(paths + (size_t)lc->clone_src[warp] * path_sz);
-                uint32_t *t = reinterpret_cast<uint32_t *>(paths + (size_t)warp * path_sz);
+            if (live && !frozen && lc->active[path] && lc->clone_src[path] >= 0) {
+                const uint32_t *s = reinterpret_cast<const uint32_t *>(paths + (size_t)lc->clone_src[path] * path_sz);
+                uint32_t *t = reinterpret_cast<uint32_t *>(paths + (size_t)path * path_sz);
                 for (int i = lane; i < (int)(path_sz / 4); i += 32) t[i] = s[i];
             }
             __syncthreads();
             // ---- write the decided symbol and propagate completed kernel blocks (IterativelyUpdateC, :266-315)
-            if (lc->active[warp]) {
-                uint8_t *Bp = pB(warp);
-                const uint8_t C = lc->bit[warp];
+            if (live && lc->active[path]) {
+                uint8_t *Bp = pB(path);
+                const uint8_t C = lc->bit[path];
                 if (lane == 0) {
                     Bp[pl.c_off[d.layers] + (phi % lsz)] = C;
                     uint32_t *uh = reinterpret_cast<uint32_t *>(Bp + pl.u_off);
@@ -401,7 +484,7 @@ k_polar_decode(PkPolarDev d, int L, const float *__restrict__ llr_in, long B, in
                     const int psi = pv / d.ksize[lambda - 1];
                     const int next = stride * d.ksize[lambda - 1];
                     const int phi0 = (lambda > 1) ? (psi % d.ksize[lambda - 2]) * next : 0;
-                    kernel_multiply(d.kern[lambda - 1], stride, Bp + pl.c_off[lambda], Bp + pl.c_off[lambda - 1] + phi0);
+                    kernel_multiply(sk[lambda - 1], stride, Bp + pl.c_off[lambda], Bp + pl.c_off[lambda - 1] + phi0);
                     stride = next;
                     pv = psi;
                     --lambda;
@@ -411,12 +494,12 @@ k_polar_decode(PkPolarDev d, int L, const float *__restrict__ llr_in, long B, in
         }
 
         // ---- final ordering (MixedKernelListDecoder.cpp:253-266): active paths by (R, index) descending
-        if (lc->active[warp]) {
-            const float r = lc->R[warp];
+        if (live && lc->active[path]) {
+            const float r = lc->R[path];
             int rank = 0;
             for (int p = 0; p < L; ++p)
-                if (lc->active[p] && (lc->R[p] > r || (lc->R[p] == r && p > warp))) ++rank;
-            const uint8_t *Bp = pB(warp);
+                if (lc->active[p] && (lc->R[p] > r || (lc->R[p] == r && p > path))) ++rank;
+            const uint8_t *Bp = pB(path);
             const uint32_t *uh = reinterpret_cast<const uint32_t *>(Bp + pl.u_off);
             if (inf_out)
                 for (int q = lane; q < d.K; q += 32) {
@@ -435,7 +518,7 @@ k_polar_decode(PkPolarDev d, int L, const float *__restrict__ llr_in, long B, in
             }
             if (metric_out && lane == 0) metric_out[f * L + rank] = r;
         }
-        if (threadIdx.x == 0 && count) {
+        if (live && path == 0 && lane == 0 && count) {
             int J = 0;
             for (int p = 0; p < L; ++p) J += lc->active[p] ? 1 : 0;
             count[f] = J;
@@ -451,6 +534,7 @@ struct pk_polar {
     std::vector<void *> allocs;
     cudaStream_t stream = nullptr;
     size_t smem_decode = 0;
+    int fpc = 1;   // frames per CTA
 };
 
 namespace {
@@ -493,11 +577,30 @@ int pk_polar_create(const char *spec_text, int L, int device, pk_polar **out) {
     std::vector<PkPolarKernelDev> kd(c.kernels.size());
     for (size_t i = 0; i < c.kernels.size() && e == cudaSuccess; ++i) {
         const PkKernelTrellis &k = c.kernels[i];
-        kd[i].size = k.size; kd[i].max_ab = k.max_ab;
+        kd[i].size = k.size; kd[i].max_ab = k.max_ab; kd[i].npred = (int)k.pred.size();
+        // device copies: section word = table offset | (state bits after the section) << 24; the (always zero)
+        // entry ab[p][0] carries the phase's maximal state complexity instead
+        std::vector<uint32_t> sec(k.off);
+        std::vector<uint8_t> abd(k.ab);
+        for (int p = 0; p < k.size; ++p) {
+            uint8_t mx = 0;
+            for (int j = 0; j < k.size; ++j) {
+                const uint8_t a = k.ab[(size_t)p * (k.size + 1) + j + 1];
+                sec[(size_t)p * k.size + j] |= (uint32_t)a << 24;
+                mx = std::max(mx, a);
+            }
+            abd[(size_t)p * (k.size + 1)] = mx;
+        }
+        std::vector<uint32_t> predd(k.pred);   // missing branch (0xFFFF) -> DUMMY state 2^max_ab, branch bit 0
+        const uint32_t dummy = 1u << k.max_ab;
+        for (auto &w : predd) {
+            if ((w & 0xFFFFu) == 0xFFFFu) w = (w & 0xFFFF0000u) | dummy;
+            if ((w >> 16) == 0xFFFFu) w = (w & 0x0000FFFFu) | (dummy << 16);
+        }
         e = up(h, k.matrix, &kd[i].mat);
-        if (e == cudaSuccess) e = up(h, k.ab, &kd[i].ab);
-        if (e == cudaSuccess) e = up(h, k.pred, &kd[i].pred);
-        if (e == cudaSuccess) e = up(h, k.off, &kd[i].off);
+        if (e == cudaSuccess) e = up(h, abd, &kd[i].ab);
+        if (e == cudaSuccess) e = up(h, predd, &kd[i].pred);
+        if (e == cudaSuccess) e = up(h, sec, &kd[i].off);
     }
     for (int j = 0; j < c.layers; ++j) {
         d.ksize[j] = c.ksize[j];
@@ -519,7 +622,9 @@ int pk_polar_create(const char *spec_text, int L, int device, pk_polar **out) {
     if (e == cudaSuccess) {
         const PathLayout pl = path_layout(d);
         const size_t path_sz = (((size_t)pl.floats * 4 + 15) & ~(size_t)15) + pl.bytes;
-        h->smem_decode = ((sizeof(ListCtl) + 15) & ~(size_t)15) + (size_t)d.N0 * 4 + (size_t)L * path_sz + (size_t)L * (2 << d.max_ab) * 4;
+        const size_t frame_sz = ((sizeof(ListCtl) + 15) & ~(size_t)15) + (size_t)d.N0 * 4 + (size_t)L * path_sz;
+        h->fpc = std::max(1, 8 / L);   // at least 8 warps per CTA share the staged trellis tables
+        h->smem_decode = polar_table_bytes(d) + (size_t)h->fpc * frame_sz + (size_t)h->fpc * L * polar_met_floats(d.max_ab) * 4;
         e = cudaFuncSetAttribute(k_polar_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_decode);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_polar_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2 * d.N0);
     }
@@ -615,7 +720,7 @@ int pk_polar_kernel_llrs(pk_polar *h, int layer, const float *chan, const uint8_
     PKP_CUDA(cudaMalloc(&d2, (size_t)B * l * 4));
     PKP_CUDA(cudaMemcpyAsync(d0, chan, (size_t)B * l * 4, cudaMemcpyHostToDevice, h->stream));
     PKP_CUDA(cudaMemcpyAsync(d1, u, (size_t)B * l, cudaMemcpyHostToDevice, h->stream));
-    const size_t per = (((size_t)(2 << k.max_ab) * 4 + 4 * l + 2 * l + 16) + 15) & ~(size_t)15;
+    const size_t per = (((size_t)polar_met_floats(k.max_ab) * 4 + 4 * l + 2 * l + 16) + 15) & ~(size_t)15;
     PKP_CUDA(cudaFuncSetAttribute(k_polar_kernel_llr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per)));
     const int grid = (int)std::min<long>((B + 3) / 4, 148L * 8);
     k_polar_kernel_llr<<<grid, 128, 4 * per, h->stream>>>(k, (const float *)d0, (const uint8_t *)d1, B, (float *)d2);
@@ -638,12 +743,12 @@ int pk_polar_decode_batch_dev(pk_polar *h, const float *d_llr, long B, int *d_co
     if (cudaSetDevice(h->device) != cudaSuccess) return pk_set_error(PK_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_polar_decode, 32 * h->L, h->smem_decode);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_polar_decode, 32 * h->L * h->fpc, h->smem_decode);
     if (per_sm < 1) return pk_set_error(PK_ERR_CUDA, "polar decode kernel does not fit (list size x code length too large for shared memory)");
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, h->device);
-    const int grid = (int)std::min<long>(B, (long)prop.multiProcessorCount * per_sm);
-    k_polar_decode<<<grid, 32 * h->L, h->smem_decode, st>>>(h->dev, h->L, d_llr, B, d_count, d_inf, d_cw, d_metric);
+    const int grid = (int)std::min<long>((B + h->fpc - 1) / h->fpc, (long)prop.multiProcessorCount * per_sm);
+    k_polar_decode<<<grid, 32 * h->L * h->fpc, h->smem_decode, st>>>(h->dev, h->L, h->fpc, d_llr, B, d_count, d_inf, d_cw, d_metric);
     ++g_pk_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return pk_set_error(PK_ERR_CUDA, cudaGetErrorString(e));
