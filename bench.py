@@ -364,6 +364,34 @@ def run_b200(a):
                "sample": f"first {nb} frames of every (code, SNR point) of this run's inputs ({n_cpu} frames, {t_cpu:.1f} s); decisions and trial counts checked equal to the GPU's",
                "trials_per_s": tr_cpu / t_cpu}
 
+    # ---- side measurement (not part of `value`): polar SC / SC-list decode of BASELINE configs 3-4
+    polar = None
+    try:
+        spec = pk.load_spec()
+        polar = {"code": "(256,128), two layers of the 16x16 extended-BCH kernel, frozen set of this repository", "ebn0_db": 2.0}
+        rng = np.random.default_rng(5)
+        for Lp, Bp in ((1, 16384), (8, 4096), (32, 2048)):
+            pp = pk.Polar(spec, L=Lp, device=local)
+            info = rng.integers(0, 2, (Bp, pp.K), dtype=np.uint8)
+            sg = np.sqrt(1 / (2 * (pp.K / pp.N) * 10 ** 0.2))
+            cwp = pp.encode(info)
+            llr = torch.from_numpy((2 * ((1 - 2.0 * cwp) + sg * rng.standard_normal(cwp.shape)) / sg ** 2).astype(np.float32)).to(dev)
+            d_cnt = torch.zeros(Bp, dtype=torch.int32, device=dev)
+            d_inf = torch.zeros((Bp, Lp, pp.K), dtype=torch.uint8, device=dev)
+            best = None
+            for _ in range(3):
+                q0 = torch.cuda.Event(enable_timing=True); q1 = torch.cuda.Event(enable_timing=True)
+                q0.record(stream)
+                pp.decode_dev(llr.data_ptr(), Bp, d_cnt.data_ptr(), d_inf.data_ptr(), None, None, sp)
+                q1.record(stream)
+                torch.cuda.synchronize()
+                t_ms = q0.elapsed_time(q1)
+                best = t_ms if best is None else min(best, t_ms)
+            polar[f"L{Lp}_frames_per_s"] = Bp / best * 1e3
+            polar[f"L{Lp}_fer"] = float((d_inf[:, 0, :].cpu().numpy() != info).any(1).mean())
+    except Exception as ex:   # the polar side measurement must never break the headline line
+        polar = {"error": str(ex)}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -378,6 +406,7 @@ def run_b200(a):
         "gpu_launches": int(launches),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "per_code_ms_per_step": {CODES[c][3]: by_code[c] for c in range(len(CODES))},
+        "polar_side_measurement": polar,
     }
     if a.detail:
         for ci in range(len(CODES)):
