@@ -34,7 +34,7 @@ typedef enum {
 /* per-frame flags in pk_frame_rec.flags */
 #define PK_FLAG_EARLY_RETURN 0x01 /* left through `if (l < calcRightSide()) return;` (KanekoKernelProcessor.cpp:380) */
 #define PK_FLAG_NO_DECISION 0x02  /* no trial ever succeeded: the reference leaves `res` untouched */
-#define PK_FLAG_SORT_TIE 0x04     /* equal |alpha| keys met: std::sort's tie order is unspecified for n > 16 */
+#define PK_FLAG_SORT_TIE 0x04     /* informational: equal |alpha| keys met; their order was resolved by replaying libstdc++'s std::sort */
 #define PK_FLAG_FRAME_ERROR 0x08  /* generation mode: decided != transmitted (dataForPlot.cpp:66) */
 #define PK_FLAG_TRUNCATED 0x10    /* stopped by the max_trials safety cap (never set with the default cap) */
 

@@ -31,6 +31,7 @@
 #include "pk_alg.cuh"
 #include "pk_bs.cuh"
 #include "pk_kernels.h"
+#include "pk_stdsort.cuh"
 
 #define PK_FULL 0xFFFFFFFFu
 #define PK_WARPS_A 8        // warps per CTA, phase A
@@ -196,8 +197,9 @@ struct KanekoWarp {
             f.YH[w] = __ballot_sync(PK_FULL, hard[w]);
         }
         __syncwarp();
-        // std::sort by |alpha| ascending (:343) as a rank sort on the f64 bit patterns; ties broken by
-        // position (== std::sort for n <= 16, where libstdc++ runs a plain insertion sort; flagged otherwise).
+        // std::sort by |alpha| ascending (:343) as a rank sort on the f64 bit patterns; ties broken by position
+        // (== std::sort for n <= 16, where libstdc++ runs a plain, stable insertion sort).  For n > 16 a frame
+        // with equal keys is re-sorted by a literal replay of libstdc++'s introsort (pk_stdsort.cuh).
         {
             int rank[NW];
             bool tie = false;
@@ -223,8 +225,18 @@ struct KanekoWarp {
                     wm.sidx[rank[w]] = (uint8_t)p;
                 }
             }
+            if (__any_sync(PK_FULL, tie)) {
+                f.flags |= PK_FLAG_SORT_TIE;
+                if (N > 16) {
+                    // equal keys: std::sort's order is an artefact of libstdc++'s introsort -- replay it on one lane
+                    __syncwarp();
+                    if (lane == 0) {
+                        for (int i = 0; i < N; ++i) { wm.skey[i] = wm.alpha[i]; wm.sidx[i] = (uint8_t)i; }
+                        pk_stdsort::sort(wm.skey, wm.sidx, N);
+                    }
+                }
+            }
             if (lane == 0) wm.skey[N] = 0.0;  // the reference reads one past the end in calcT(n-t); value unused
-            if (__any_sync(PK_FULL, tie)) f.flags |= PK_FLAG_SORT_TIE;
         }
         __syncwarp();
         // prefix sums of the sorted reliabilities: pref[m] <= l of ANY flip set of weight m (used only to

@@ -44,6 +44,10 @@ def test_kaneko_replay_matches_oracle(pk, oracle_mod, m, t, J, snr, B, lut):
     kan = pk.Kaneko(code, J=J)
     g_dec, g_tr, recs, tot = kan.decode(y)
     assert not (recs["flags"] & (pk.PK_FLAG_NO_DECISION | pk.PK_FLAG_TRUNCATED | pk.PK_FLAG_SORT_TIE)).any()
+    _compare(pk, code, recs, g_dec, g_tr, tot, dec, tr, cmp_, sum_, B)
+
+
+def _compare(pk, code, recs, g_dec, g_tr, tot, dec, tr, cmp_, sum_, B):
     assert np.array_equal(g_tr, tr), f"trial counts differ at frames {np.nonzero(g_tr != tr)[0][:5]}"
     assert np.array_equal(g_dec, dec), f"decisions differ at frames {np.nonzero((g_dec != dec).any(1))[0][:5]}"
     d, c, s = pk.counters_from_recs(recs, code.n)
@@ -132,3 +136,37 @@ def test_run_point_stop_rule(pk, oracle_mod):
     assert res["trials"] == int(recs["trials"].sum())
     res2 = kan.run_point(5.0, 10, 7, 3000, 100)
     assert res2["frames"] == 3000 and res2["frame_errors"] < 100
+
+
+@pytest.mark.parametrize("m,t,J,B", [(4, 3, -1, 3000), (5, 3, -1, 1500), (5, 2, -1, 2000), (6, 6, 9, 600), (6, 4, 9, 600), (7, 10, 9, 60)])
+@pytest.mark.parametrize("lut", [True, False])
+def test_tied_reliabilities_follow_std_sort(pk, oracle_mod, m, t, J, B, lut):
+    """Quantised inputs: many equal |alpha|.  std::sort is unstable, the reference's order is whatever libstdc++'s
+    introsort produces -- the kernels replay it (pk_stdsort.cuh); decisions, trial counts, counters stay identical."""
+    code = pk.Code(m, t, device=0)
+    if lut and not code.uses_lut:
+        pytest.skip("no coset table for this code")
+    code.set_lut(lut)
+    o = oracle_mod.Oracle(m, t, J)
+    o.seed(21)
+    _, _, y = o.gen_frames(3.0, B)
+    yq = np.round(y, 1)
+    yq[yq == 0] = 0.1
+    dec, tr, cmp_, sum_ = o.kaneko_decode(yq)
+    kan = pk.Kaneko(code, J=J)
+    g_dec, g_tr, recs, tot = kan.decode(yq)
+    assert (recs["flags"] & pk.PK_FLAG_SORT_TIE).any()
+    _compare(pk, code, recs, g_dec, g_tr, tot, dec, tr, cmp_, sum_, B)
+
+
+def test_reference_infile_fixture(pk):
+    """in/infile.txt of the reference (a (63,39,9) word and 63 six-digit samples), 3-argument decode: the result the
+    compiled reference gives (tests/golden/infile_and_fun.npz) -- 15 trials and NOT the transmitted word."""
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "infile_and_fun.npz"))
+    code = pk.Code(6, 4, device=0)
+    dec, tr, recs, tot = pk.Kaneko(code).decode(z["infile_y"])
+    assert np.array_equal(dec, z["infile_dec3"]) and tr[0] == z["infile_trials3"][0] == 15
+    d, c, s = pk.counters_from_recs(recs, code.n)
+    assert c[0] == z["infile_cmp3"][0] and s[0] == z["infile_sum3"][0]
