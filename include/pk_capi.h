@@ -37,6 +37,8 @@ typedef enum {
 #define PK_FLAG_SORT_TIE 0x04     /* informational: equal |alpha| keys met; their order was resolved by replaying libstdc++'s std::sort */
 #define PK_FLAG_FRAME_ERROR 0x08  /* generation mode: decided != transmitted (dataForPlot.cpp:66) */
 #define PK_FLAG_TRUNCATED 0x10    /* stopped by the max_trials safety cap (never set with the default cap) */
+#define PK_FLAG_REF_UNDEFINED 0x20 /* 2-argument flavour only: the reference's unbounded `while (l >= calcT(j))` (:257) ran
+                                      past the reliability array here, i.e. its own result is undefined */
 
 /* One record per decoded frame (16 bytes). The reference's three operation counters
  * (KanekoKernelProcessor.cpp:367-369,386-404) are reconstructed as
@@ -104,6 +106,10 @@ int pk_bch_decode_batch(pk_code *code, const uint8_t *words /*[B][n]*/, long B,
  * T = min(j,J) (line 392, the *_e*.csv runs).  max_trials <= 0: the reference bound. */
 int pk_kaneko_create(pk_code *code, double llr_snr_db, long J, long max_trials, pk_kaneko **out);
 void pk_kaneko_destroy(pk_kaneko *dec);
+/* Which of the reference's decode flavours the handle runs: 0 (default) decode(answer, word, res), the one fun()
+ * uses (KanekoKernelProcessor.cpp:335-407); 1 decode(word, res), the file-mode flavour of main.cpp:158 (:212-276:
+ * bound 1 << T without "- 1", T starts unbounded, no cap J, 2n+1 added to both synthetic counters). */
+int pk_kaneko_set_variant(pk_kaneko *dec, int two_argument);
 /* tuning / introspection */
 int pk_kaneko_set_frames_per_grab(pk_kaneko *dec, int frames);
 /* trials (multiple of 32) a frame may spend in the narrow phase-A search before it is handed to the

@@ -17,6 +17,7 @@ PK_FLAG_NO_DECISION = 0x02
 PK_FLAG_SORT_TIE = 0x04
 PK_FLAG_FRAME_ERROR = 0x08
 PK_FLAG_TRUNCATED = 0x10
+PK_FLAG_REF_UNDEFINED = 0x20
 
 #: numpy view of pk_frame_rec (16 bytes)
 FRAME_REC = np.dtype(
@@ -29,7 +30,7 @@ POINT_FIELDS = ("frames", "frame_errors", "bit_errors", "trials", "cmp", "sum", 
 SYMBOLS = (
     "pk_last_error pk_device_count pk_code_create pk_code_create_host pk_code_destroy pk_code_info pk_code_tables "
     "pk_code_uses_lut pk_code_set_lut pk_code_coset_table pk_encode_batch pk_bch_decode_batch pk_kaneko_create "
-    "pk_kaneko_destroy pk_kaneko_set_frames_per_grab pk_kaneko_set_phase_a_limit pk_kaneko_launch_geometry pk_kaneko_decode_batch "
+    "pk_kaneko_destroy pk_kaneko_set_variant pk_kaneko_set_frames_per_grab pk_kaneko_set_phase_a_limit pk_kaneko_launch_geometry pk_kaneko_decode_batch "
     "pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames pk_generate_frames_dev "
     "pk_kaneko_run_point pk_make_kernel_matrix pk_launch_count pk_launch_count_reset "
     "pk_polar_create pk_polar_destroy pk_polar_info pk_polar_trellis_profile pk_make_ebch_kernel pk_polar_encode_batch "
@@ -71,6 +72,7 @@ def _load():
     lib.pk_kaneko_destroy.restype = None
     lib.pk_kaneko_set_frames_per_grab.argtypes = [vp, i]
     lib.pk_kaneko_set_phase_a_limit.argtypes = [vp, l]
+    lib.pk_kaneko_set_variant.argtypes = [vp, i]
     lib.pk_kaneko_launch_geometry.argtypes = [vp, ip, ip, C.POINTER(l)]
     lib.pk_kaneko_decode_batch.argtypes = [vp, vp, l, vp, vp, vp, vp]
     lib.pk_kaneko_decode_batch_dev.argtypes = [vp, vp, l, vp, vp, vp, vp, vp]
@@ -202,6 +204,10 @@ class Kaneko:
 
     def set_frames_per_grab(self, g):
         _check(lib.pk_kaneko_set_frames_per_grab(self.h, int(g)))
+
+    def set_variant(self, two_argument):
+        """False: decode(answer, word, res) (default); True: the file-mode flavour decode(word, res)."""
+        _check(lib.pk_kaneko_set_variant(self.h, int(bool(two_argument))))
 
     def set_phase_a_limit(self, trials):
         _check(lib.pk_kaneko_set_phase_a_limit(self.h, int(trials)))

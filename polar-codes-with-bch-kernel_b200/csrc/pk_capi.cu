@@ -273,6 +273,8 @@ int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_
     // so those frames move to phase B almost at once; coset-table steps are cheap and stay longer
     d->kp.limit_a = c->use_lut ? 256u : 64u;
     d->kp.big_span = 8192u;
+    d->kp.variant = 0;
+    d->kp.extra_ops = 0;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, c->device);
     if (e == cudaSuccess) e = c->ks->geom_kaneko(c->use_lut, c->nk, prop.multiProcessorCount, d->geom4);
@@ -308,6 +310,15 @@ void pk_kaneko_destroy(pk_kaneko *d) {
 int pk_kaneko_set_frames_per_grab(pk_kaneko *d, int g) {
     if (!d || g < 1) return fail(PK_ERR_ARG, "bad argument");
     d->kp.frames_per_grab = g;
+    return PK_OK;
+}
+
+// 0: KanekoKernelProcessor::decode(answer, word, res) -- what fun() uses (default);
+// 1: KanekoKernelProcessor::decode(word, res), the file-mode flavour of main.cpp:158
+int pk_kaneko_set_variant(pk_kaneko *d, int two_argument) {
+    if (!d) return fail(PK_ERR_ARG, "NULL handle");
+    d->kp.variant = two_argument ? 1 : 0;
+    d->kp.extra_ops = two_argument ? (uint32_t)(2 * d->code->n + 1) : 0u;
     return PK_OK;
 }
 

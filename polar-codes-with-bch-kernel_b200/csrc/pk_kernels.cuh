@@ -48,6 +48,10 @@ __host__ __device__ constexpr size_t pk_align16(size_t x) { return (x + 15) & ~(
 // (1 << T) - 1 as the reference's x86 build evaluates it: 32-bit SHL masks the count to
 // 5 bits, -fwrapv wraps the subtraction (KanekoKernelProcessor.cpp:354,361).
 __device__ __forceinline__ uint32_t pk_pattern_bound(int T) { return (1u << (T & 31)) - 1u; }
+// The 2-argument flavour (file mode, KanekoKernelProcessor.cpp:229,236) loops while i < (uint64_t(1) << T): a 64-bit
+// SHL (count masked to 6 bits), no "- 1", and T starts at LONG_MAX (= no bound).  Pattern indices here are 31-bit,
+// anything larger is "unbounded" (a search that long ends with PK_FLAG_TRUNCATED at max_trials).
+__device__ __forceinline__ uint32_t pk_pattern_bound2(int T) { return ((T & 63) >= 31) ? 0x7FFFFFFFu : (1u << (T & 63)); }
 
 // ------------------------------------------------------------------ Philox4x32-10
 struct PkPhilox {
@@ -276,11 +280,11 @@ struct KanekoWarp {
         __syncwarp();
     }
 
-    __device__ static void search_init(Search &s, const Frame &f) {
+    __device__ static void search_init(Search &s, const Frame &f, int variant) {
         s.l0 = DBL_MAX;
         s.m0 = 0;
         s.first_ok = true; s.have = false; s.early = false;
-        s.bound = pk_pattern_bound(N);      // long T = n (:354)
+        s.bound = variant ? 0x7FFFFFFFu : pk_pattern_bound(N);      // long T = n (:354) / uint64_t T = LONG_MAX (:229)
         s.trials = 0; s.tsteps = 0; s.nimpr = 0; s.step_last = 0;
         s.flags = f.flags;
 #pragma unroll
@@ -339,6 +343,8 @@ struct KanekoWarp {
                 if (!pk_getbit<NW>(Fs, p)) { bs += wm.skey[k]; ++cnt; }
                 ++k;
             }
+            // 3-argument flavour: j <= n-1-t is part of the loop condition (:384).  The 2-argument flavour (:257) has no
+            // such test and would read past the reliability array (undefined behaviour) -- flagged, same stop.
             const int jmax = N - 1 - T;
             jn = jmax + 1;
             for (int c0 = 0; c0 <= jmax; c0 += 32) {
@@ -355,8 +361,13 @@ struct KanekoWarp {
         }
         s.tsteps += (uint32_t)jn;
         ++s.nimpr;
-        const int Tn = (kp.J >= 0 && jn > kp.J) ? kp.J : jn;   // :392-393
-        s.bound = pk_pattern_bound(Tn);
+        if (kp.variant) {
+            if (jn == N - T) s.flags |= PK_FLAG_REF_UNDEFINED;
+            s.bound = pk_pattern_bound2(jn);                   // T = j (:264)
+        } else {
+            const int Tn = (kp.J >= 0 && jn > kp.J) ? kp.J : jn;   // :392-393
+            s.bound = pk_pattern_bound(Tn);
+        }
         return false;
     }
 
@@ -981,7 +992,7 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
             typename KW::Frame fr;
             typename KW::Search s;
             KW::setup(tabs, wm, yv, kp, fr);
-            KW::search_init(s, fr);
+            KW::search_init(s, fr, kp.variant);
             uint32_t next = 0;
             bool done = KW::narrow(tabs, wm, kp, fr, s, 0u, limit, &next);
             if (!done) {
@@ -1001,7 +1012,7 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
                 KW::narrow(tabs, wm, kp, fr, s, next, 0xFFFFFFFFu, &next);
             }
             KW::search_finish(s);
-            pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr, s.tsteps, s.flags, tot);
+            pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot);
         }
     }
     if (lane == 0) tot.flush(io.totals);
@@ -1058,7 +1069,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
         KW::template wide<PK_WARPS_B>(tabs, wm, kp, fr, s, rec->base, &s_shared, s_votes, warp);
         if (warp == 0) {
             KW::search_finish(s);
-            pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr, s.tsteps, s.flags, tot);
+            pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot);
         }
     }
     // ---- small frames (and the big ones left over): one warp each
@@ -1080,7 +1091,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
         KW::unpark(s, rec);
         KW::template wide<1>(tabs, wm, kp, fr, s, rec->base, nullptr, nullptr, 0);
         KW::search_finish(s);
-        pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr, s.tsteps, s.flags, tot);
+        pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot);
     }
     if (lane == 0) tot.flush(io.totals);
 }

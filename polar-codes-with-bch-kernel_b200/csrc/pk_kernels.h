@@ -15,6 +15,8 @@ struct PkKanekoParams {
     int frames_per_grab;  // frames a warp takes from the queue per atomic
     uint32_t limit_a;     // trials (multiple of 32) a frame may spend in the narrow phase A before it is parked
     uint32_t big_span;    // parked frames with at least this many patterns left are searched by a whole CTA
+    int variant;          // 0: decode(answer, word, res) (:335-407); 1: decode(word, res), the file-mode flavour (:212-276)
+    uint32_t extra_ops;   // per-frame constant added to both synthetic counters (2n+1 sort cost of the file-mode flavour, :221-224)
 };
 
 // Generation-mode parameters of one launch.

@@ -71,9 +71,8 @@ int main(int argc, char *argv[]) {
             for (int i = 0; i < n; ++i) in >> err[i];
             printVec(err.data(), n);
         }
-        // both single-word modes use the 3-argument rule here (the reference's file mode uses
-        // its 2-argument variant, which has no device implementation yet)
-        decoder.decode(res.data(), err.data(), decoded.data());
+        if (n_args == 4) decoder.decode(res.data(), err.data(), decoded.data());   // main.cpp:116
+        else decoder.decode(err.data(), decoded.data());                           // main.cpp:158 (file mode)
         printVec(decoded.data(), n);
         std::cout << (comparePoly(res.data(), n, decoded.data(), n) ? "Ok\n" : "Errors were not corrected!\n");
     } catch (const char *err) {

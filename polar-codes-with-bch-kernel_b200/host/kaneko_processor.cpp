@@ -44,8 +44,17 @@ void KanekoKernelProcessor::decode(const unsigned char *answer, const double *wo
     decodeBatch(word, 1, res);
 }
 
-void KanekoKernelProcessor::decode(const double *, unsigned char *) {
-    throw "KanekoKernelProcessor::decode(word,res): the file-mode flavour has no device implementation; use decode(answer,word,res)\n";
+void KanekoKernelProcessor::decode(const double *word, unsigned char *res) {
+    // file-mode flavour (:212-276): same kernels, different loop bound and counter bookkeeping
+    set(word);
+    if (pk_kaneko_set_variant(kan_, 1) != PK_OK) throw pk_last_error();
+    try {
+        decodeBatch(word, 1, res);
+    } catch (...) {
+        pk_kaneko_set_variant(kan_, 0);
+        throw;
+    }
+    pk_kaneko_set_variant(kan_, 0);
 }
 void KanekoKernelProcessor::decode(unsigned char *) {
     throw "KanekoKernelProcessor::decode(res): the DEBUG flavour reads an uninitialised flag in the reference and is not provided\n";

@@ -19,9 +19,9 @@ public:
 
     // decode(answer, word, res): the flavour fun() uses (KanekoKernelProcessor.cpp:335-407).
     void decode(const unsigned char *answer, const double *word, unsigned char *res);
-    // The 2-argument (file mode, :212-276) and 1-argument (DEBUG, :161-210) flavours follow
-    // different -- in the DEBUG case undefined -- rules and have no device implementation yet:
-    // they throw instead of silently answering with other semantics.
+    // decode(word, res): the file-mode flavour (:212-276), also on the device (pk_kaneko_set_variant).
+    // decode(res): the DEBUG flavour (:161-210) reads an uninitialised flag in the reference and is not
+    // provided -- it throws instead of silently answering with other semantics.
     void decode(const double *word, unsigned char *res);
     void decode(unsigned char *res);
     void set(const double *word) const;

@@ -170,3 +170,48 @@ def test_reference_infile_fixture(pk):
     assert np.array_equal(dec, z["infile_dec3"]) and tr[0] == z["infile_trials3"][0] == 15
     d, c, s = pk.counters_from_recs(recs, code.n)
     assert c[0] == z["infile_cmp3"][0] and s[0] == z["infile_sum3"][0]
+
+
+@pytest.mark.parametrize("m,t,snr,B", [(4, 3, 1.0, 4000), (4, 2, 2.0, 3000), (5, 3, 2.0, 2000), (5, 2, 3.0, 2000), (6, 4, 4.0, 300), (6, 6, 4.0, 200)])
+@pytest.mark.parametrize("lut", [True, False])
+def test_two_argument_flavour_matches_oracle(pk, oracle_mod, m, t, snr, B, lut):
+    """decode(word, res), the file-mode flavour (KanekoKernelProcessor.cpp:212-276): bound 1 << T, T unbounded until the
+    first improvement, no cap J, 2n+1 extra counter units.  Frames where the reference's own unbounded calcT loop runs past
+    its array (undefined behaviour there) carry PK_FLAG_REF_UNDEFINED and are left out of the comparison."""
+    code = pk.Code(m, t, device=0)
+    if lut and not code.uses_lut:
+        pytest.skip("no coset table for this code")
+    code.set_lut(lut)
+    o = oracle_mod.Oracle(m, t)
+    o.seed(33)
+    _, _, y = o.gen_frames(snr, B)
+    kan = pk.Kaneko(code, max_trials=1 << 16)
+    kan.set_variant(True)
+    g_dec, g_tr, recs, tot = kan.decode(y)
+    keep = (recs["flags"] & (pk.PK_FLAG_REF_UNDEFINED | pk.PK_FLAG_TRUNCATED)) == 0
+    assert keep.mean() > 0.9
+    dec, tr, cmp_, sum_ = o.kaneko_decode(y[keep], two_arg=True)
+    assert np.array_equal(g_tr[keep], tr)
+    assert np.array_equal(g_dec[keep], dec)
+    d, c, s = pk.counters_from_recs(recs, code.n)
+    assert np.array_equal(c[keep], cmp_) and np.array_equal(s[keep], sum_)
+    # back to the default flavour on the same handle
+    kan.set_variant(False)
+    dec3, tr3, *_ = o.kaneko_decode(y[:200])
+    g3, gt3, *_ = kan.decode(y[:200])
+    assert np.array_equal(g3, dec3) and np.array_equal(gt3, tr3)
+
+
+def test_reference_infile_fixture_two_argument(pk):
+    """in/infile.txt through the flavour main.cpp:158 really uses for it: 2048 trials and the transmitted word ("Ok")."""
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "infile_and_fun.npz"))
+    code = pk.Code(6, 4, device=0)
+    kan = pk.Kaneko(code)
+    kan.set_variant(True)
+    dec, tr, recs, tot = kan.decode(z["infile_y"])
+    assert np.array_equal(dec, z["infile_dec2"]) and np.array_equal(dec, z["infile_cw"])
+    assert tr[0] == z["infile_trials2"][0] == 2048
+    d, c, s = pk.counters_from_recs(recs, code.n)
+    assert c[0] == z["infile_cmp2"][0] and s[0] == z["infile_sum2"][0]

@@ -50,6 +50,22 @@ def test_cpp_cli_single_word_modes(pk, tmp_path):
     assert "Invalid values of arguments" in bad.stderr
 
 
+def test_cpp_cli_file_mode(pk, tmp_path):
+    """`kaneko 6 4 <snr> <file>` (main.cpp:125-166) on the reference's own in/infile.txt contents (kept as a golden
+    fixture): the 2-argument decode flavour restores the transmitted word -> "Ok"."""
+    exe = os.path.join(PKG, "kaneko_b200")
+    if not os.path.exists(exe):
+        pytest.skip("kaneko_b200 not built")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "infile_and_fun.npz"))
+    f = tmp_path / "infile.txt"
+    f.write_text(" ".join(str(int(b)) for b in z["infile_cw"][0]) + "\n" + " ".join(repr(float(v)) for v in z["infile_y"][0]) + "\n")
+    out = subprocess.run([exe, "6", "4", "3.0", str(f)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[-1] == "Ok"
+    assert lines[-2].split() == [str(int(b)) for b in z["infile_cw"][0]]
+
+
 def test_two_gpu_sweep_reproduces_one_gpu_csv(tmp_path):
     import torch
 
