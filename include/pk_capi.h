@@ -83,11 +83,16 @@ void pk_code_destroy(pk_code *code);
 int pk_code_info(const pk_code *code, int *n, int *k, int *d, int *gsize, uint8_t *g_out);
 /* antilogarithms[n], logarithms[n+1] exactly as main.cpp:63-78 builds them (log[0] = LONG_MAX) */
 int pk_code_tables(const pk_code *code, uint64_t *antilog_out, uint64_t *log_out);
-/* 1 if the algebraic decoder runs from the shared-memory coset table (n-k <= 16, t*m <= 15);
- * pk_code_set_lut(code, 0) forces the Berlekamp-Massey + Chien kernels instead (call before
- * pk_kaneko_create). */
+/* Which lookup table replaces the algebraic decoder (Decoder::decode, src/Decoder.cpp:298-321) in the searches:
+ * 1 = shared-memory coset table (n-k <= 16, t*m <= 15), 2 = cyclic-class table (bitmap + position table over the
+ * syndrome classes under cyclic shifts; (31,11,11), (31,6,15), (63,45,7) .. (63,30,13)), 0 = none.
+ * pk_code_set_lut(code, 0) forces the Berlekamp-Massey + Chien kernels instead (call before pk_kaneko_create);
+ * pk_code_set_lut(code, 1) goes back to the code's table. */
 int pk_code_uses_lut(const pk_code *code);
 int pk_code_set_lut(pk_code *code, int enable);
+/* Host-side differential self-check of the cyclic-class table against the algebraic decoder on `ntrials` random
+ * error patterns of weight 0 .. t+3; info[4] = key bits, log2 slots, entries, bitmap bytes (may be NULL). */
+int pk_code_class_table_check(const pk_code *code, uint64_t seed, long ntrials, long *mismatches, long *info);
 /* The coset table itself: entry r = up to t error positions (m bits each, n = none) of the
  * algebraic decoder's answer for syndrome r(x) = word mod g, 0xFFFF = decoding failure. */
 int pk_code_coset_table(const pk_code *code, uint16_t *out /*[2^(n-k)] or NULL*/, long *nentries);

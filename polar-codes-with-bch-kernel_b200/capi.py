@@ -29,7 +29,7 @@ POINT_FIELDS = ("frames", "frame_errors", "bit_errors", "trials", "cmp", "sum", 
 #: every symbol include/pk_capi.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = (
     "pk_last_error pk_device_count pk_code_create pk_code_create_host pk_code_destroy pk_code_info pk_code_tables "
-    "pk_code_uses_lut pk_code_set_lut pk_code_coset_table pk_encode_batch pk_bch_decode_batch pk_kaneko_create "
+    "pk_code_uses_lut pk_code_set_lut pk_code_class_table_check pk_code_coset_table pk_encode_batch pk_bch_decode_batch pk_kaneko_create "
     "pk_kaneko_destroy pk_kaneko_set_variant pk_kaneko_set_frames_per_grab pk_kaneko_set_phase_a_limit pk_kaneko_launch_geometry pk_kaneko_decode_batch "
     "pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames pk_generate_frames_dev "
     "pk_kaneko_run_point pk_make_kernel_matrix pk_launch_count pk_launch_count_reset "
@@ -64,6 +64,7 @@ def _load():
     lib.pk_code_tables.argtypes = [vp, vp, vp]
     lib.pk_code_uses_lut.argtypes = [vp]
     lib.pk_code_set_lut.argtypes = [vp, i]
+    lib.pk_code_class_table_check.argtypes = [vp, u64, l, C.POINTER(l), C.POINTER(l)]
     lib.pk_code_coset_table.argtypes = [vp, vp, C.POINTER(l)]
     lib.pk_encode_batch.argtypes = [vp, vp, l, vp]
     lib.pk_bch_decode_batch.argtypes = [vp, vp, l, vp, vp]
@@ -150,6 +151,18 @@ class Code:
     @property
     def uses_lut(self):
         return bool(lib.pk_code_uses_lut(self.h))
+
+    @property
+    def table_kind(self):
+        """0: algebraic decoding only, 1: coset table, 2: cyclic-class table."""
+        return int(lib.pk_code_uses_lut(self.h))
+
+    def class_table_check(self, seed=1, ntrials=100000):
+        """(mismatches, info dict) of the host-side class table against the algebraic decoder."""
+        bad = C.c_long(-1)
+        info = (C.c_long * 4)()
+        _check(lib.pk_code_class_table_check(self.h, int(seed), int(ntrials), C.byref(bad), info))
+        return bad.value, dict(key_bits=info[0], log2_slots=info[1], entries=info[2], bitmap_bytes=info[3])
 
     def set_lut(self, enable):
         _check(lib.pk_code_set_lut(self.h, int(bool(enable))))

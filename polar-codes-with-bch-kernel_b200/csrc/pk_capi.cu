@@ -49,6 +49,7 @@ int pk_set_error(int code, const std::string &msg) { return fail(code, msg); }
 struct pk_kaneko {
     pk_code *code = nullptr;
     PkKanekoParams kp{};
+    int mode = PK_MODE_ALG;    // fixed at creation from the code's table switches (pk_code_set_lut)
     PkLaunchGeom geom4[4]{};   // replay phase A/B, generation phase A/B
     cudaStream_t stream[2] = {nullptr, nullptr};
     // one control block + parked-frame list per concurrent launch slot:
@@ -118,6 +119,18 @@ int pk_code_create(int m, int t, int device, pk_code **out) {
         pk_code_destroy(c);
         return rc;
     }
+    if (c->ct) {
+        const PkClassTable &ct = *c->ct;
+        if ((rc = upload(c, ct.norm, &c->dev.ct_norm)) || (rc = upload(c, ct.logt, &c->dev.ct_log)) ||
+            (rc = upload(c, ct.bits, &c->dev.ct_bits)) ||
+            (rc = upload(c, ct.hash, reinterpret_cast<const uint64_t **>(&c->dev.ct_hash)))) {
+            pk_code_destroy(c);
+            return rc;
+        }
+        c->dev.ct_hshift = 32u - (uint32_t)ct.hbits;
+        c->dev.ct_hmask = (1u << ct.hbits) - 1u;
+        for (size_t i = 0; i < 8; ++i) c->dev.ct_mult[i] = i < ct.mult.size() ? ct.mult[i] : 0u;
+    }
     c->dev.k = c->k;
     c->dev.nk = c->nk;
     *out = c;
@@ -178,12 +191,44 @@ int pk_code_tables(const pk_code *c, uint64_t *antilog_out, uint64_t *log_out) {
     return PK_OK;
 }
 
-int pk_code_uses_lut(const pk_code *c) { return c && c->use_lut ? 1 : 0; }
+// 0: algebraic decoding only; 1: coset table (n-k <= 16); 2: cyclic-class table (wide search of the mid-size codes)
+int pk_code_uses_lut(const pk_code *c) { return !c ? 0 : c->use_lut ? 1 : c->use_ct ? 2 : 0; }
 
 int pk_code_set_lut(pk_code *c, int enable) {
     if (!c) return fail(PK_ERR_ARG, "code is NULL");
-    if (enable && c->lut.empty()) return fail(PK_ERR_UNSUPPORTED, "no coset table for this code (needs n-k <= 16, t*m <= 15)");
-    c->use_lut = enable != 0;
+    if (enable && c->lut.empty() && !c->ct)
+        return fail(PK_ERR_UNSUPPORTED, "no lookup table for this code (coset table: n-k <= 16, t*m <= 15; class table: see pk_code.h)");
+    c->use_lut = enable != 0 && !c->lut.empty();
+    c->use_ct = enable != 0 && !c->use_lut && (bool)c->ct;
+    return PK_OK;
+}
+
+// Differential self-check of the class table on the host: `ntrials` random error patterns of weight 0 .. t+3 through
+// PkClassTable::lookup and through the algebraic decoder (pk_alg_decode); *mismatches = patterns where verdict or
+// positions differ.  info[0..3] = key bits, log2 position-table slots, position-table entries, bitmap bytes.
+int pk_code_class_table_check(const pk_code *c, uint64_t seed, long ntrials, long *mismatches, long *info) {
+    if (!c) return fail(PK_ERR_ARG, "code is NULL");
+    if (!c->ct) return fail(PK_ERR_UNSUPPORTED, "no class table for this code");
+    const PkClassTable &ct = *c->ct;
+    if (info) { info[0] = ct.kb; info[1] = ct.hbits; info[2] = (long)ct.entries; info[3] = (long)(ct.bits.size() * 4); }
+    const int n = c->n, nw = (n + 31) / 32, per = 32 / c->m, nsw = (2 * c->t + per - 1) / per;
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    long bad = 0;
+    std::vector<uint32_t> sw(nsw), A1(nw), A2(nw);
+    for (long it = 0; it < ntrials; ++it) {
+        const int wgt = (int)(rnd() % (uint64_t)(c->t + 4));
+        std::fill(sw.begin(), sw.end(), 0u);
+        for (int i = 0; i < wgt; ++i) {   // repeated positions cancel: the weight is "at most wgt"
+            const int p = (int)(rnd() % (uint64_t)n);
+            for (int w = 0; w < nsw; ++w) sw[w] ^= c->hcol[(size_t)p * nsw + w];
+        }
+        std::fill(A1.begin(), A1.end(), 0u);
+        const bool ok1 = c->ks->host_alg_decode(sw.data(), c->mul.data(), c->xoff.data(), A1.data());
+        const bool ok2 = ct.lookup(c->m, c->t, sw.data(), A2.data());
+        if (ok1 != ok2 || (ok1 && A1 != A2)) ++bad;
+    }
+    if (mismatches) *mismatches = bad;
     return PK_OK;
 }
 
@@ -272,12 +317,13 @@ int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_
     // a narrow BM+Chien step (32 trials) costs about as much latency as a bit-sliced wide step (1024 trials),
     // so those frames move to phase B almost at once; coset-table steps are cheap and stay longer
     d->kp.limit_a = c->use_lut ? 256u : 64u;
+    d->mode = c->use_lut ? PK_MODE_LUT : c->use_ct ? PK_MODE_CLASS : PK_MODE_ALG;
     d->kp.big_span = 8192u;
     d->kp.variant = 0;
     d->kp.extra_ops = 0;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, c->device);
-    if (e == cudaSuccess) e = c->ks->geom_kaneko(c->use_lut, c->nk, prop.multiProcessorCount, d->geom4);
+    if (e == cudaSuccess) e = c->ks->geom_kaneko(d->mode, c->nk, prop.multiProcessorCount, d->geom4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream[0], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream[1], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&d->d_ctl, 3 * sizeof(PkPhaseCtl));
@@ -343,7 +389,7 @@ static int launch_pairs(pk_kaneko *d, int slot, bool gen, PkIo io, long B, cudaS
     const pk_code *c = d->code;
     const bool wide = d->geom4[gen ? 3 : 1].grid > 0;
     if (wide && !d->d_longs[slot]) PK_CUDA(cudaMalloc(&d->d_longs[slot], (size_t)d->long_cap * sizeof(PkLongRec)));
-    if (wide && !c->use_lut && (c->t + 1) * c->m > 56 && !d->d_zscr[slot]) {
+    if (wide && d->mode == PK_MODE_ALG && (c->t + 1) * c->m > 56 && !d->d_zscr[slot]) {
         const int gmax = std::max(d->geom4[1].grid, d->geom4[3].grid);
         PK_CUDA(cudaMalloc(&d->d_zscr[slot], (size_t)gmax * 4 * c->n * 32 * sizeof(uint32_t)));
     }
@@ -362,7 +408,7 @@ static int launch_pairs(pk_kaneko *d, int slot, bool gen, PkIo io, long B, cudaS
             if (io.trials) part.trials = io.trials + off;
         }
         if (io.recs) part.recs = io.recs + off;
-        PK_CUDA(c->ks->launch_kaneko(c->use_lut, gen, d->geom4, c->dev, d->kp, part, nb, d->d_ctl + slot,
+        PK_CUDA(c->ks->launch_kaneko(d->mode, gen, d->geom4, c->dev, d->kp, part, nb, d->d_ctl + slot,
                                      d->d_longs[slot], wide ? d->long_cap : 0, st));
     }
     return PK_OK;

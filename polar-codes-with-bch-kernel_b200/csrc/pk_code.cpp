@@ -7,6 +7,8 @@
 #include "pk_kernels.h"
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 
 namespace {
 
@@ -69,6 +71,184 @@ static Poly2 minimal_poly(const pk_code &c, int i) {
     Poly2 out(p.size());
     for (size_t d = 0; d < p.size(); ++d) out[d] = (uint8_t)(p[d] & 1);
     return out;
+}
+
+// ------------------------------------------------------------------ cyclic-class table (see PkClassTable)
+namespace {
+
+struct CtBuilder {
+    const pk_code &c;
+    PkClassTable &ct;
+    int m, n, t, Q, per, nsw;
+    std::vector<int> js;                       // 3, 5, .., 2t-1
+    std::vector<std::vector<uint8_t>> rank;    // per js: value -> rank in its subfield (0xFF: not in the subfield)
+    std::vector<int> pos;
+    std::vector<uint32_t> S;                   // S_1, S_3, .., S_{2t-1} of the current pattern
+    uint64_t posmask;
+
+    CtBuilder(const pk_code &c_, PkClassTable &ct_) : c(c_), ct(ct_), m(c_.m), n(c_.n), t(c_.t), Q(1 << c_.m) {}
+
+    uint32_t gmul(uint32_t a, int e) const {   // a * alpha^e
+        return a ? c.alog[(c.log[a] + (uint32_t)(((e % n) + n) % n)) % n] : 0u;
+    }
+    int coset_rep(int j, int *size) const {
+        int e = j % n, rep = e, sz = 0;
+        do { rep = std::min(rep, e); e = (2 * e) % n; ++sz; } while (e != j % n);
+        if (size) *size = sz;
+        return rep;
+    }
+    bool prepare() {
+        if (t < 2) return false;
+        std::vector<int> reps(1, coset_rep(1, nullptr));
+        std::vector<int> deg;
+        for (int j = 3; j < 2 * t; j += 2) {
+            int d;
+            const int rep = coset_rep(j, &d);
+            if (std::find(reps.begin(), reps.end(), rep) != reps.end()) continue;   // S_j is a power of an earlier syndrome
+            reps.push_back(rep);
+            js.push_back(j);
+            deg.push_back(d);
+        }
+        int kb = 0;
+        for (int d : deg) kb += d;
+        if (kb + 1 > 28 || t * m + kb + 1 > 64 || (int)js.size() > 8) return false;
+        ct.kb = kb;
+        ct.js = js;
+        // field offsets: S_3 on top (its table carries the S_1 = 0 flag one bit above its rank)
+        ct.mult.assign(js.size(), 0);
+        int sh = 0;
+        for (int i = (int)js.size() - 1; i >= 0; --i) { ct.mult[i] = 1u << sh; sh += deg[i]; }
+        rank.resize(js.size());
+        for (size_t i = 0; i < js.size(); ++i) {
+            const int sub = (1 << deg[i]) - 1, step = n / sub;
+            std::vector<uint32_t> el(1, 0u);
+            for (int e = 0; e < sub; ++e) el.push_back(c.alog[(e * step) % n]);
+            std::sort(el.begin(), el.end());
+            rank[i].assign(Q, 0xFF);
+            for (size_t r = 0; r < el.size(); ++r) rank[i][el[r]] = (uint8_t)r;
+        }
+        ct.logt.assign(Q, 0);
+        for (int v = 1; v < Q; ++v) ct.logt[v] = (uint8_t)c.log[v];
+        ct.norm.assign(js.size() * (size_t)Q * Q, 0);
+        for (size_t i = 0; i < js.size(); ++i)
+            for (int s1 = 0; s1 < Q; ++s1)
+                for (int v = 0; v < Q; ++v) {
+                    const uint32_t w = s1 ? gmul((uint32_t)v, -(int)((js[i] * (long)c.log[s1]) % n)) : (uint32_t)v;
+                    uint8_t r = rank[i][w];
+                    if (r == 0xFF) r = 0;   // not a syndrome value of this code
+                    if (!s1 && i == 0) r |= (uint8_t)(1u << deg[0]);
+                    ct.norm[(i * Q + s1) * Q + v] = r;
+                }
+        // capacity: about V(n,t)/n classes with S_1 != 0 and as many keys again with S_1 = 0
+        double vol = 0, binom = 1;
+        for (int w = 0; w <= t; ++w) { vol += binom; binom = binom * (n - w) / (w + 1); }
+        ct.hbits = 10;
+        while ((double)(1ull << ct.hbits) < 3.5 * vol / n) ++ct.hbits;
+        ct.hash.assign((size_t)1 << ct.hbits, ~0ull);
+        ct.bits.assign(((size_t)1 << (kb + 1)) / 32 + 1, 0u);
+        posmask = (t * m == 64) ? ~0ull : ((1ull << (t * m)) - 1);
+        return true;
+    }
+    uint32_t key_of(const std::vector<uint32_t> &Sv) const {
+        uint32_t key = 0;
+        for (size_t i = 0; i < js.size(); ++i) key += (uint32_t)ct.norm[(i * Q + Sv[0]) * Q + Sv[i + 1]] * ct.mult[i];
+        return key;
+    }
+    void insert(uint32_t key, uint64_t packed) {
+        ct.bits[key >> 5] |= 1u << (key & 31);
+        const uint32_t mask = (1u << ct.hbits) - 1;
+        uint32_t h = (uint32_t)(key * 0x9E3779B1u) >> (32 - ct.hbits);
+        for (;;) {
+            uint64_t &e = ct.hash[h];
+            if (e == ~0ull) { e = ((uint64_t)key << (t * m)) | packed; ++ct.entries; return; }
+            if ((uint32_t)(e >> (t * m)) == key && (e & posmask) != posmask) return;   // same class seen before
+            h = (h + 1) & mask;
+        }
+    }
+    std::vector<uint32_t> Sv;
+    void emit(int w) {
+        Sv = S;
+        auto pack = [&](int shift) {
+            uint64_t e = 0;
+            for (int i = 0; i < t; ++i) {
+                const uint64_t p = (i < w) ? (uint64_t)((pos[i] + shift) % n) : (uint64_t)n;
+                e |= p << (i * m);
+            }
+            return e;
+        };
+        if (S[0]) {
+            insert(key_of(Sv), pack(n - (int)c.log[S[0]]));
+        } else {
+            for (int r = 0; r < n; ++r) {
+                for (size_t i = 0; i < js.size(); ++i) Sv[i + 1] = gmul(S[i + 1], (int)((js[i] * (long)r) % n));
+                insert(key_of(Sv), pack(r));
+            }
+        }
+    }
+    void rec(int w) {
+        emit(w);
+        if (w == t) return;
+        for (int p = pos[w - 1] + 1; p < n; ++p) {
+            pos[w] = p;
+            S[0] ^= c.alog[p % n];
+            for (size_t i = 0; i < js.size(); ++i) S[i + 1] ^= c.alog[(js[i] * (long)p) % n];
+            rec(w + 1);
+            S[0] ^= c.alog[p % n];
+            for (size_t i = 0; i < js.size(); ++i) S[i + 1] ^= c.alog[(js[i] * (long)p) % n];
+        }
+    }
+    bool build() {
+        if (!prepare()) return false;
+        pos.assign(t, 0);
+        S.assign(js.size() + 1, 1u);   // the pattern {0}: every S_j = alpha^0
+        rec(1);
+        return true;
+    }
+};
+
+std::mutex g_ct_mutex;
+std::map<std::pair<int, int>, std::shared_ptr<const PkClassTable>> g_ct_cache;
+
+std::shared_ptr<const PkClassTable> class_table_for(const pk_code &c) {
+    std::lock_guard<std::mutex> lock(g_ct_mutex);
+    auto it = g_ct_cache.find({c.m, c.t});
+    if (it != g_ct_cache.end()) return it->second;
+    auto ct = std::make_shared<PkClassTable>();
+    CtBuilder b(c, *ct);
+    std::shared_ptr<const PkClassTable> out;
+    if (b.build()) out = ct;
+    g_ct_cache[{c.m, c.t}] = out;
+    return out;
+}
+
+}  // namespace
+
+bool PkClassTable::lookup(int m, int t, const uint32_t *packed, uint32_t *A) const {
+    const int n = (1 << m) - 1, Q = 1 << m, per = 32 / m, nw = (n + 31) / 32;
+    auto syn = [&](int j) { return (packed[(j - 1) / per] >> (((j - 1) % per) * m)) & (uint32_t)n; };
+    const uint32_t s1 = syn(1);
+    uint32_t key = 0;
+    for (size_t i = 0; i < mult.size(); ++i) key += (uint32_t)norm[(i * Q + s1) * Q + syn(js[i])] * mult[i];
+    for (int w = 0; w < nw; ++w) A[w] = 0;
+    if (!((bits[key >> 5] >> (key & 31)) & 1u)) return false;
+    const uint64_t posmask = (t * m == 64) ? ~0ull : ((1ull << (t * m)) - 1);
+    const uint32_t mask = (1u << hbits) - 1;
+    uint32_t h = (uint32_t)(key * 0x9E3779B1u) >> (32 - hbits);
+    for (;;) {
+        const uint64_t e = hash[h];
+        if (e == ~0ull) return false;   // cannot happen: the bitmap is exact
+        if ((uint32_t)(e >> (t * m)) == key && (e & posmask) != posmask) {
+            const int s = logt[s1];
+            for (int i = 0; i < t; ++i) {
+                int p = (int)((e >> (i * m)) & (uint64_t)n);
+                if (p == n) continue;
+                p = (p + s) % n;
+                A[p >> 5] |= 1u << (p & 31);
+            }
+            return true;
+        }
+        h = (h + 1) & mask;
+    }
 }
 
 std::string pk_code_build_host(pk_code &c, int m, int t) {
@@ -167,6 +347,13 @@ std::string pk_code_build_host(pk_code &c, int m, int t) {
             for (; cnt < t; ++cnt) e |= (uint32_t)n << (m * cnt);  // "no position" = n (all ones)
             c.lut[r] = (uint16_t)e;
         }
+    }
+
+    // ---- cyclic-class table for the codes whose wide search can run on it
+    c.use_ct = false;
+    if (c.ks && c.ks->has_class && !c.use_lut) {
+        c.ct = class_table_for(c);
+        c.use_ct = (bool)c.ct;
     }
     return "";
 }

@@ -80,11 +80,34 @@ struct PkTraits {
     static constexpr bool BS_OK = ((T + 1) * M <= 56) && !LUT_OK; // bit-sliced decoder fits the register file
     static constexpr bool BSM_OK = !LUT_OK && !BS_OK;             // bit-sliced decoder with its BM state in shared memory
     static constexpr int MINB = BSM_OK ? 2 : 3;                   // phase-B CTAs per SM the register budget is set for
+    // cyclic-class table (PkClassTable): key of n-k-m+1 <= 28 bits and key + t*m <= 64 bits, 2^(2m)-byte rank tables
+    static constexpr bool CT_OK = !LUT_OK && ((M == 5 && (T == 5 || T == 7)) || (M == 6 && T >= 3 && T <= 6));
+    static constexpr int MINB_CT = 4;
 };
 
+// Is S_j (odd j >= 3) an independent syndrome, i.e. is the cyclotomic coset of j new among 1, 3, .., j-2?
+__host__ __device__ constexpr int pk_ct_rep(int M, int j) {
+    const int n = (1 << M) - 1;
+    int e = j % n, rep = e;
+    for (int i = 0; i < M; ++i) { e = (2 * e) % n; rep = e < rep ? e : rep; }
+    return rep;
+}
+__host__ __device__ constexpr bool pk_ct_used(int M, int j) {
+    for (int i = 1; i < j; i += 2)
+        if (pk_ct_rep(M, i) == pk_ct_rep(M, j)) return false;
+    return true;
+}
+// number of key fields before S_j's
+__host__ __device__ constexpr int pk_ct_index(int M, int j) {
+    int c = 0;
+    for (int i = 3; i < j; i += 2) c += pk_ct_used(M, i) ? 1 : 0;
+    return c;
+}
+
 // ------------------------------------------------------------------ shared memory plan
-template <int M, int T, bool LUT>
+template <int M, int T, bool LUT, bool CT = false>
 struct PkSmem {
+    static_assert(!(LUT && CT), "coset-table and class-table modes are exclusive");
     typedef PkCfg<M, T> C;
     static constexpr int NP = C::NW * 32;             // padded length
     static constexpr int SW = LUT ? 1 : C::NSW;       // syndrome words per column
@@ -104,15 +127,15 @@ struct PkSmem {
     static constexpr size_t W_U = W_SIDX + (size_t)NP;                // uint32[NW+1] info bits (generation)
     static constexpr size_t W_SZ_A = pk_align16(W_U + (size_t)(C::NW + 1) * 4);
     // per warp, phase B extras
-    static constexpr size_t W_CM = W_SZ_A;                                          // uint32[2T*M] planes / [32] deltas
-    static constexpr size_t W_CM_SZ = pk_align16((size_t)(LUT ? 32 : 2 * T * M) * 4);
-    static constexpr size_t W_PB = W_CM + W_CM_SZ;                                  // uint32[32][NW] one-hot XORs (LUT)
-    static constexpr size_t W_PB_SZ = LUT ? pk_align16((size_t)32 * C::NW * 4) : 0;
-    static constexpr size_t W_WL = W_PB + W_PB_SZ;                                  // double[32] in-word pattern reliabilities (LUT)
-    static constexpr size_t W_WL_SZ = LUT ? 256 : 0;
+    static constexpr size_t W_CM = W_SZ_A;                                          // uint32[2T*M] planes / [32] deltas / [32][SW] (CT)
+    static constexpr size_t W_CM_SZ = pk_align16((size_t)(LUT ? 32 : CT ? 32 * SW : 2 * T * M) * 4);
+    static constexpr size_t W_PB = W_CM + W_CM_SZ;                                  // uint32[32][NW] one-hot XORs (LUT, CT)
+    static constexpr size_t W_PB_SZ = (LUT || CT) ? pk_align16((size_t)32 * C::NW * 4) : 0;
+    static constexpr size_t W_WL = W_PB + W_PB_SZ;                                  // double[32] in-word pattern reliabilities (LUT, CT)
+    static constexpr size_t W_WL_SZ = (LUT || CT) ? 256 : 0;
     static constexpr size_t W_Z = W_WL + W_WL_SZ;                                   // uint32[N][33] root words (bit-sliced)
-    static constexpr bool BSM = !LUT && ((T + 1) * M > 56);                         // BM state in shared memory, Z in global scratch
-    static constexpr size_t W_Z_SZ = (LUT || BSM) ? 0 : pk_align16((size_t)C::N * 33 * 4);
+    static constexpr bool BSM = !LUT && !CT && ((T + 1) * M > 56);                  // BM state in shared memory, Z in global scratch
+    static constexpr size_t W_Z_SZ = (LUT || CT || BSM) ? 0 : pk_align16((size_t)C::N * 33 * 4);
     static constexpr size_t W_ST = W_Z + W_Z_SZ;                                    // uint32[2][(T+1)*M][32] Lambda / B planes (BSM)
     static constexpr size_t W_ST_SZ = BSM ? (size_t)2 * (T + 1) * M * 32 * 4 : 0;
     static constexpr size_t W_SZ_B = W_ST + W_ST_SZ;
@@ -121,7 +144,13 @@ struct PkSmem {
     __host__ __device__ static constexpr size_t total_a(int nk) { return tables(nk) + (size_t)PK_WARPS_A * W_SZ_A; }
     // phase B of the bit-sliced codes needs neither the GF product table nor the Chien offsets: columns only
     static constexpr size_t B_COL_OFF = LUT ? COL_OFF : 0;
-    __host__ __device__ static constexpr size_t tables_b(int nk) { return LUT ? tables(nk) : COL_SZ; }
+    // class-table mode: rank tables (one 2^m x 2^m byte table per independent S_j) and log S_1 behind the columns
+    static constexpr int CT_NJ = CT ? pk_ct_index(M, 2 * T + 1) : 0;
+    static constexpr size_t CT_NORM_OFF = COL_SZ;
+    static constexpr size_t CT_NORM_SZ = (size_t)CT_NJ << (2 * M);
+    static constexpr size_t CT_LOG_OFF = CT_NORM_OFF + CT_NORM_SZ;
+    static constexpr size_t CT_LOG_SZ = CT ? pk_align16((size_t)1 << M) : 0;
+    __host__ __device__ static constexpr size_t tables_b(int nk) { return LUT ? tables(nk) : COL_SZ + CT_NORM_SZ + CT_LOG_SZ; }
     __host__ __device__ static constexpr size_t total_b(int nk) { return tables_b(nk) + (size_t)PK_WARPS_B * W_SZ_B; }
 };
 
@@ -134,10 +163,10 @@ __device__ __forceinline__ uint32_t pk_getbit(const uint32_t (&F)[NW], int p) {
 }
 
 // ------------------------------------------------------------------ one frame, one warp
-template <int M, int T, bool LUT>
+template <int M, int T, bool LUT, bool CT = false>
 struct KanekoWarp {
     typedef PkCfg<M, T> C;
-    typedef PkSmem<M, T, LUT> SM;
+    typedef PkSmem<M, T, LUT, CT> SM;
     static constexpr int N = C::N, NW = C::NW, SW = SM::SW, NA = SW + NW;
 
     struct Tables {      // CTA-shared tables
@@ -145,6 +174,12 @@ struct KanekoWarp {
         const uint16_t *xoff;
         const uint32_t *col;
         const uint16_t *lut;
+        // class-table mode: rank tables and log S_1 in shared memory, bitmap and position table in global memory
+        const uint8_t *ctn, *ctlog;
+        const uint32_t *ctbits;
+        const unsigned long long *cthash;
+        uint32_t cthshift, cthmask;
+        uint32_t ctmult[8];
     };
     struct WarpMem {     // per-warp shared scratch
         double *alpha, *skey, *pref;
@@ -389,6 +424,55 @@ struct KanekoWarp {
         return !(e & 0x8000u);
     }
 
+    // ---- class-table mode (PkClassTable): key of a packed syndrome, position-table probe, positions
+    template <int J>
+    __device__ static __forceinline__ void ct_key_term(const Tables &tb, const uint32_t (&w)[SW], uint32_t row, uint32_t &key) {
+        if constexpr (J < 2 * T) {
+            if constexpr (pk_ct_used(M, J)) {
+                constexpr int jj = pk_ct_index(M, J), wi = (J - 1) / C::PER, sh = ((J - 1) % C::PER) * M;
+                const uint32_t v = (w[wi] >> sh) & (uint32_t)N;
+                key += (uint32_t)tb.ctn[(jj << (2 * M)) + row + v] * tb.ctmult[jj];
+            }
+            ct_key_term<J + 2>(tb, w, row, key);
+        }
+    }
+    __device__ static __forceinline__ uint32_t ct_key(const Tables &tb, const uint32_t (&w)[SW]) {
+        uint32_t key = 0;
+        ct_key_term<3>(tb, w, (w[0] & (uint32_t)N) << M, key);
+        return key;
+    }
+    __device__ static __forceinline__ unsigned long long ct_find(const Tables &tb, uint32_t key) {
+        constexpr int TM = T * M;
+        constexpr unsigned long long PM = (TM >= 64) ? ~0ull : ((1ull << (TM & 63)) - 1ull);
+        uint32_t h = (key * 0x9E3779B1u) >> tb.cthshift;
+        for (;;) {
+            const unsigned long long e = __ldg(tb.cthash + h);
+            if (e == ~0ull || ((uint32_t)(e >> TM) == key && (e & PM) != PM)) return e;
+            h = (h + 1) & tb.cthmask;
+        }
+    }
+    // position j of a class entry, shifted back by s = log S_1; N = none
+    __device__ static __forceinline__ uint32_t ct_pos(unsigned long long e, int j, uint32_t s) {
+        uint32_t p = (uint32_t)(e >> (j * M)) & (uint32_t)N;
+        if (p != (uint32_t)N) {
+            p += s;
+            p = (p >= (uint32_t)N) ? p - (uint32_t)N : p;
+        }
+        return p;
+    }
+    __device__ static __forceinline__ void ct_positions(unsigned long long e, uint32_t s, uint32_t (&A)[NW]) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) A[w] = 0;
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            const uint32_t p = ct_pos(e, j, s);
+            if (p != (uint32_t)N) {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) A[w] |= ((p >> 5) == (uint32_t)w) ? (1u << (p & 31)) : 0u;
+            }
+        }
+    }
+
     // ---- narrow search: 32 patterns per step starting at trial base0 (multiple of 32).  Returns true when
     // the frame is finished, false when trial `limit` was reached and the frame must be parked (s holds the
     // state, *next = the next trial to run).
@@ -486,22 +570,28 @@ struct KanekoWarp {
         const int lane = threadIdx.x & 31;
         const uint32_t base0 = (start & ~1023u) + 1024u * (uint32_t)wi;
         // pattern bits 0..4 = bit index in the word: their column contributions are per-frame constants
-        if constexpr (LUT) {
-            // cm[q] = coset-index delta of in-word pattern q; pb[q][w] = its one-hot XOR
-            uint32_t c = 0, ph[NW];
+        if constexpr (LUT || CT) {
+            // cm[q][.] = coset-index / packed-syndrome delta of in-word pattern q; pb[q][w] = its one-hot XOR
+            uint32_t c[SW], ph[NW];
+#pragma unroll
+            for (int a = 0; a < SW; ++a) c[a] = 0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) ph[w] = 0;
 #pragma unroll
             for (int b = 0; b < 5; ++b) {
-                const uint32_t cc = __shfl_sync(PK_FULL, f.aug[0], b);
-                c ^= ((lane >> b) & 1) ? cc : 0u;
+#pragma unroll
+                for (int a = 0; a < SW; ++a) {
+                    const uint32_t cc = __shfl_sync(PK_FULL, f.aug[a], b);
+                    c[a] ^= ((lane >> b) & 1) ? cc : 0u;
+                }
 #pragma unroll
                 for (int w = 0; w < NW; ++w) {
                     const uint32_t pp = __shfl_sync(PK_FULL, f.aug[SW + w], b);
                     ph[w] ^= ((lane >> b) & 1) ? pp : 0u;
                 }
             }
-            wm.cm[lane] = c;
+#pragma unroll
+            for (int a = 0; a < SW; ++a) wm.cm[lane * SW + a] = c[a];
 #pragma unroll
             for (int w = 0; w < NW; ++w) wm.pb[lane * NW + w] = ph[w];
             // wl[q] = sum of the reliabilities flipped by in-word pattern q (for the approximate-l filter)
@@ -540,7 +630,7 @@ struct KanekoWarp {
             }
         }
         double lsum = 0.0;   // reliabilities flipped by pattern bits 5..9 (lane part)
-        if constexpr (LUT) {
+        if constexpr (LUT || CT) {
 #pragma unroll
             for (int b = 0; b < 5; ++b)
                 if (5 + b < N && ((lane >> b) & 1)) lsum += wm.skey[5 + b];
@@ -612,6 +702,53 @@ struct KanekoWarp {
                     }
                     if (!((la - s.l0) > 1e-9 * (lp + s.l0))) cand |= 1u << q;
                 }
+            } else if constexpr (CT) {
+                // one bitmap probe per pattern: does ANY error pattern of weight <= t have this syndrome class?
+                uint32_t ok = 0;
+#pragma unroll 8
+                for (int q = 0; q < 32; ++q) {
+                    uint32_t w[SW];
+#pragma unroll
+                    for (int a = 0; a < SW; ++a) w[a] = u[a] ^ wm.cm[q * SW + a];
+                    const uint32_t key = ct_key(tb, w);
+                    const uint32_t word = __ldg(tb.ctbits + (key >> 5));
+                    ok |= ((word >> (key & 31)) & 1u) << q;
+                }
+                ok &= vmask;
+                // the few decodable ones: positions from the class entry, approximate-l filter as in coset-table mode
+                double bsum = 0.0;
+                {
+                    uint32_t hb = base >> 10;
+                    while (hb) {
+                        const int b = __ffs(hb) - 1;
+                        hb &= hb - 1;
+                        bsum += wm.skey[10 + b];
+                    }
+                }
+                while (ok) {
+                    const int q = __ffs(ok) - 1;
+                    ok &= ok - 1;
+                    uint32_t w[SW];
+#pragma unroll
+                    for (int a = 0; a < SW; ++a) w[a] = u[a] ^ wm.cm[q * SW + a];
+                    const unsigned long long e = ct_find(tb, ct_key(tb, w));
+                    const uint32_t sh = tb.ctlog[w[0] & (uint32_t)N];
+                    const double lp = wm.wl[q] + lsum + bsum;
+                    double la = lp;
+#pragma unroll
+                    for (int j = 0; j < T; ++j) {
+                        const uint32_t p = ct_pos(e, j, sh);
+                        if (p != (uint32_t)N) {
+                            uint32_t pw = Ul[SW] ^ Ub[SW] ^ wm.pb[q * NW];
+#pragma unroll
+                            for (int w2 = 1; w2 < NW; ++w2)
+                                pw = ((p >> 5) == (uint32_t)w2) ? (Ul[SW + w2] ^ Ub[SW + w2] ^ wm.pb[q * NW + w2]) : pw;
+                            const double a = wm.alpha[p];
+                            la += ((pw >> (p & 31)) & 1u) ? -a : a;
+                        }
+                    }
+                    if (!((la - s.l0) > 1e-9 * (lp + s.l0))) cand |= 1u << q;
+                }
             } else {
                 auto getS = [&](int j, uint32_t *o) {   // j may be a run-time value (looped BM)
                     const int wi = (j - 1) / C::PER, sh = ((j - 1) % C::PER) * M;
@@ -635,6 +772,11 @@ struct KanekoWarp {
                 uint32_t A[NW];
                 if constexpr (LUT) {
                     lut_positions(tb.lut[usrc ^ wm.cm[q]], A);
+                } else if constexpr (CT) {
+                    uint32_t w[SW];
+#pragma unroll
+                    for (int a = 0; a < SW; ++a) w[a] = __shfl_sync(PK_FULL, u[a], src) ^ wm.cm[q * SW + a];
+                    ct_positions(ct_find(tb, ct_key(tb, w)), tb.ctlog[w[0] & (uint32_t)N], A);
                 } else {
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {
@@ -777,9 +919,9 @@ struct KanekoWarp {
 };
 
 // ------------------------------------------------------------------ table staging
-template <int M, int T, bool LUT>
+template <int M, int T, bool LUT, bool CT = false>
 __device__ __forceinline__ void pk_stage_tables(unsigned char *smem, const PkDevTables &tb, bool need_mul) {
-    typedef PkSmem<M, T, LUT> SM;
+    typedef PkSmem<M, T, LUT, CT> SM;
     typedef PkCfg<M, T> C;
     const int tid = threadIdx.x, nth = blockDim.x;
     if constexpr (!LUT) {
@@ -792,6 +934,12 @@ __device__ __forceinline__ void pk_stage_tables(unsigned char *smem, const PkDev
         }
         uint32_t *col = reinterpret_cast<uint32_t *>(smem + (need_mul ? SM::COL_OFF : SM::B_COL_OFF));
         for (int i = tid; i < C::N * SM::SW; i += nth) col[i] = tb.hcol[i];
+        if constexpr (CT) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(tb.ct_norm);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + SM::CT_NORM_OFF);
+            for (int i = tid; i < (int)(SM::CT_NORM_SZ / 4); i += nth) dst[i] = src[i];
+            for (int i = tid; i < (1 << M); i += nth) smem[SM::CT_LOG_OFF + i] = tb.ct_log[i];
+        }
     } else {
         uint32_t *col = reinterpret_cast<uint32_t *>(smem + SM::COL_OFF);
         for (int i = tid; i < C::N; i += nth) col[i] = tb.rcol[i];
@@ -1019,16 +1167,16 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
 }
 
 // ------------------------------------------------------------------ phase B
-template <int M, int T, bool LUT, bool GEN>
-__global__ void __launch_bounds__(PK_WARPS_B * 32, PkTraits<M, T>::MINB)
+template <int M, int T, bool LUT, bool GEN, bool CT = false>
+__global__ void __launch_bounds__(PK_WARPS_B * 32, CT ? PkTraits<M, T>::MINB_CT : PkTraits<M, T>::MINB)
 k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkLongRec *longs, long long_cap) {
-    typedef PkSmem<M, T, LUT> SM;
-    typedef KanekoWarp<M, T, LUT> KW;
+    typedef PkSmem<M, T, LUT, CT> SM;
+    typedef KanekoWarp<M, T, LUT, CT> KW;
     constexpr int NW = KW::NW;
     extern __shared__ __align__(16) unsigned char smem[];
     const unsigned long long n_long = ctl->n_long, n_big = ctl->n_big;
     if (n_long + n_big == 0) return;
-    pk_stage_tables<M, T, LUT>(smem, tb, false);
+    pk_stage_tables<M, T, LUT, CT>(smem, tb, false);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wb = smem + SM::tables_b(tb.nk) + (size_t)warp * SM::W_SZ_B;
     typename KW::WarpMem wm = KW::warp_mem(wb);
@@ -1038,6 +1186,16 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
     tabs.xoff = nullptr;
     tabs.col = reinterpret_cast<const uint32_t *>(smem + SM::B_COL_OFF);
     tabs.lut = reinterpret_cast<const uint16_t *>(smem + SM::LUT_OFF);
+    if constexpr (CT) {
+        tabs.ctn = smem + SM::CT_NORM_OFF;
+        tabs.ctlog = smem + SM::CT_LOG_OFF;
+        tabs.ctbits = tb.ct_bits;
+        tabs.cthash = tb.ct_hash;
+        tabs.cthshift = tb.ct_hshift;
+        tabs.cthmask = tb.ct_hmask;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tabs.ctmult[i] = tb.ct_mult[i];
+    }
     if constexpr (SM::BSM)   // root words of the bit-sliced Chien search go to a per-warp slice of global scratch
         wm.z = io.zscratch + ((size_t)blockIdx.x * PK_WARPS_B + warp) * (size_t)KW::N * 32;
     __shared__ typename KW::Search s_shared;
@@ -1184,7 +1342,7 @@ struct PkLaunch {
         return pk_alg_decode<M, T>(Sw, mul, xoff, A);
     }
 
-    template <bool LUT, bool GEN>
+    template <bool LUT, bool GEN, bool CT>
     static cudaError_t geom_one(int nk, int sm_count, PkLaunchGeom *ga, PkLaunchGeom *gb) {
         const size_t sa = PkSmem<M, T, LUT>::total_a(nk);
         cudaError_t e = cudaFuncSetAttribute(k_phase_a<M, T, LUT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
@@ -1196,34 +1354,39 @@ struct PkLaunch {
         ga->grid = sm_count * per;      // persistent: every resident slot of every SM
         ga->block = PK_WARPS_A * 32;
         ga->smem = sa;
-        gb->grid = 0; gb->block = PK_WARPS_B * 32; gb->smem = 0;
-        if constexpr (true) {
-            const size_t sb = PkSmem<M, T, LUT>::total_b(nk);
-            e = cudaFuncSetAttribute(k_phase_b<M, T, LUT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
-            if (e != cudaSuccess) return e;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_phase_b<M, T, LUT, GEN>, PK_WARPS_B * 32, sb);
-            if (e != cudaSuccess) return e;
-            if (per < 1) return cudaErrorLaunchOutOfResources;
-            gb->grid = sm_count * per;
-            gb->smem = sb;
-        }
+        const size_t sb = PkSmem<M, T, LUT, CT>::total_b(nk);
+        e = cudaFuncSetAttribute(k_phase_b<M, T, LUT, GEN, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_phase_b<M, T, LUT, GEN, CT>, PK_WARPS_B * 32, sb);
+        if (e != cudaSuccess) return e;
+        if (per < 1) return cudaErrorLaunchOutOfResources;
+        gb->grid = sm_count * per;
+        gb->block = PK_WARPS_B * 32;
+        gb->smem = sb;
         return cudaSuccess;
     }
     // out[0..1] = replay phase A / B, out[2..3] = generation phase A / B
-    static cudaError_t geom_kaneko(bool lut, int nk, int sm_count, PkLaunchGeom *out) {
+    static cudaError_t geom_kaneko(int mode, int nk, int sm_count, PkLaunchGeom *out) {
         cudaError_t e;
-        if constexpr (TR::LUT_OK) {
-            if (lut) {
-                e = geom_one<true, false>(nk, sm_count, out + 0, out + 1);
+        if (mode == PK_MODE_LUT) {
+            if constexpr (TR::LUT_OK) {
+                e = geom_one<true, false, false>(nk, sm_count, out + 0, out + 1);
                 if (e != cudaSuccess) return e;
-                return geom_one<true, true>(nk, sm_count, out + 2, out + 3);
+                return geom_one<true, true, false>(nk, sm_count, out + 2, out + 3);
             }
-        } else {
-            if (lut) return cudaErrorInvalidValue;
+            return cudaErrorInvalidValue;
         }
-        e = geom_one<false, false>(nk, sm_count, out + 0, out + 1);
+        if (mode == PK_MODE_CLASS) {
+            if constexpr (TR::CT_OK) {
+                e = geom_one<false, false, true>(nk, sm_count, out + 0, out + 1);
+                if (e != cudaSuccess) return e;
+                return geom_one<false, true, true>(nk, sm_count, out + 2, out + 3);
+            }
+            return cudaErrorInvalidValue;
+        }
+        e = geom_one<false, false, false>(nk, sm_count, out + 0, out + 1);
         if (e != cudaSuccess) return e;
-        return geom_one<false, true>(nk, sm_count, out + 2, out + 3);
+        return geom_one<false, true, false>(nk, sm_count, out + 2, out + 3);
     }
     static cudaError_t geom_bdd(int sm_count, PkLaunchGeom *out) {
         const size_t smem = PkSmem<M, T, false>::tables(0);
@@ -1239,7 +1402,7 @@ struct PkLaunch {
         return cudaSuccess;
     }
 
-    template <bool LUT, bool GEN>
+    template <bool LUT, bool GEN, bool CT>
     static cudaError_t run(const PkLaunchGeom *g, const PkDevTables &tb, const PkKanekoParams &kp, const PkIo &io, long B,
                            PkPhaseCtl *ctl, PkLongRec *longs, long long_cap, cudaStream_t st) {
         cudaError_t e = cudaMemsetAsync(ctl, 0, sizeof(PkPhaseCtl), st);
@@ -1249,24 +1412,30 @@ struct PkLaunch {
         ++g_pk_launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        if constexpr (true) {
-            if (wide_ok) {
-                k_phase_b<M, T, LUT, GEN><<<g[1].grid, g[1].block, g[1].smem, st>>>(tb, kp, io, ctl, longs, long_cap);
-                ++g_pk_launches;
-                e = cudaGetLastError();
-            }
+        if (wide_ok) {
+            k_phase_b<M, T, LUT, GEN, CT><<<g[1].grid, g[1].block, g[1].smem, st>>>(tb, kp, io, ctl, longs, long_cap);
+            ++g_pk_launches;
+            e = cudaGetLastError();
         }
         return e;
     }
-    static cudaError_t kaneko(bool lut, bool gen, const PkLaunchGeom *g4, const PkDevTables &tb, const PkKanekoParams &kp,
+    static cudaError_t kaneko(int mode, bool gen, const PkLaunchGeom *g4, const PkDevTables &tb, const PkKanekoParams &kp,
                               const PkIo &io, long B, PkPhaseCtl *ctl, PkLongRec *longs, long long_cap, cudaStream_t st) {
         const PkLaunchGeom *g = g4 + (gen ? 2 : 0);
-        if constexpr (TR::LUT_OK) {
-            if (lut) return gen ? run<true, true>(g, tb, kp, io, B, ctl, longs, long_cap, st)
-                                : run<true, false>(g, tb, kp, io, B, ctl, longs, long_cap, st);
+        if (mode == PK_MODE_LUT) {
+            if constexpr (TR::LUT_OK)
+                return gen ? run<true, true, false>(g, tb, kp, io, B, ctl, longs, long_cap, st)
+                           : run<true, false, false>(g, tb, kp, io, B, ctl, longs, long_cap, st);
+            return cudaErrorInvalidValue;
         }
-        return gen ? run<false, true>(g, tb, kp, io, B, ctl, longs, long_cap, st)
-                   : run<false, false>(g, tb, kp, io, B, ctl, longs, long_cap, st);
+        if (mode == PK_MODE_CLASS) {
+            if constexpr (TR::CT_OK)
+                return gen ? run<false, true, true>(g, tb, kp, io, B, ctl, longs, long_cap, st)
+                           : run<false, false, true>(g, tb, kp, io, B, ctl, longs, long_cap, st);
+            return cudaErrorInvalidValue;
+        }
+        return gen ? run<false, true, false>(g, tb, kp, io, B, ctl, longs, long_cap, st)
+                   : run<false, false, false>(g, tb, kp, io, B, ctl, longs, long_cap, st);
     }
 
     static cudaError_t bdd(const PkLaunchGeom &g, const PkDevTables &tb, const uint8_t *d_words, long B,
@@ -1286,6 +1455,6 @@ struct PkLaunch {
     }
 
     static constexpr PkKernelSet make() {
-        return PkKernelSet{M, T, !TR::LUT_OK, &host_alg, &geom_kaneko, &geom_bdd, &kaneko, &bdd, &encode};
+        return PkKernelSet{M, T, !TR::LUT_OK, TR::CT_OK, &host_alg, &geom_kaneko, &geom_bdd, &kaneko, &bdd, &encode};
     }
 };

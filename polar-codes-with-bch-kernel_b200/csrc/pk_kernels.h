@@ -61,6 +61,8 @@ struct PkPhaseCtl {
     unsigned long long n_big;       // parked big frames: longs[cap-1 .. cap-n_big] (filled from the top)
 };
 
+enum { PK_MODE_ALG = 0, PK_MODE_LUT = 1, PK_MODE_CLASS = 2 };
+
 struct PkLaunchGeom {
     int grid, block;
     size_t smem;
@@ -69,14 +71,16 @@ struct PkLaunchGeom {
 struct PkKernelSet {
     int m, t;
     bool has_bitsliced;   // phase B runs the bit-sliced decoder (pk_bs.cuh) for this code
+    bool has_class;       // phase B can run on a cyclic-class table (PkClassTable) instead
     // host instance of the algebraic decoder (coset-table construction)
     bool (*host_alg_decode)(const uint32_t *, const uint8_t *, const uint16_t *, uint32_t *);
     // geometry (queries the device once; sets the dynamic shared-memory attributes):
     // out[0..1] = replay phase A / B, out[2..3] = generation phase A / B (grid 0 = no such kernel)
-    cudaError_t (*geom_kaneko)(bool lut, int nk, int sm_count, PkLaunchGeom *out);
+    // mode: PK_MODE_ALG (BM+Chien / bit-sliced), PK_MODE_LUT (coset table) or PK_MODE_CLASS (cyclic-class table)
+    cudaError_t (*geom_kaneko)(int mode, int nk, int sm_count, PkLaunchGeom *out);
     cudaError_t (*geom_bdd)(int sm_count, PkLaunchGeom *out);
     // Kaneko decode of B frames: phase A (+ phase B when a wide kernel exists and long_cap > 0)
-    cudaError_t (*launch_kaneko)(bool lut, bool gen, const PkLaunchGeom *g4, const PkDevTables &tb,
+    cudaError_t (*launch_kaneko)(int mode, bool gen, const PkLaunchGeom *g4, const PkDevTables &tb,
                                  const PkKanekoParams &kp, const PkIo &io, long B, PkPhaseCtl *ctl, PkLongRec *longs,
                                  long long_cap, cudaStream_t st);
     // algebraic decoder alone, one thread per word

@@ -80,3 +80,17 @@ def test_unsupported_code_is_reported_not_emulated(pk):
     assert c.n == 255
     with pytest.raises(pk.PkError):
         pk.Kaneko(c)
+
+
+@pytest.mark.parametrize("m,t,kb", [(5, 5, 15), (5, 7, 20), (6, 3, 12), (6, 4, 18), (6, 5, 21), (6, 6, 27)])
+def test_class_table_equals_algebraic_decoder(pk, m, t, kb):
+    """The cyclic-class table (bitmap over syndrome classes + position table) the wide search of these codes reads
+    gives the verdict and the error positions of pk_alg_decode<M,T> on random patterns of weight 0 .. t+3
+    (pk_alg_decode itself is pinned to the oracle's Sugiyama decoder by the tests above and the GPU parity tests)."""
+    c = pk.Code(m, t, device=None)
+    bad, info = c.class_table_check(seed=7, ntrials=300000)
+    assert bad == 0
+    assert info["key_bits"] == kb == (c.n - c.k) - m
+    # one class per cyclic orbit of the patterns with S_1 != 0, one key per pattern with S_1 = 0
+    assert 0 < info["entries"] <= (1 << info["log2_slots"]) * 0.75
+    assert info["bitmap_bytes"] >= (1 << (kb + 1)) // 8

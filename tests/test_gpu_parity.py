@@ -20,6 +20,11 @@ CASES = [
     (6, 4, 9, 2.0, 300),
     (6, 2, 9, 3.0, 500),
     (6, 11, 9, 3.0, 100),
+    (5, 5, 12, 2.0, 300),
+    (5, 7, 10, 2.0, 200),
+    (6, 3, 12, 3.0, 400),
+    (6, 5, 12, 2.0, 200),
+    (6, 6, 15, 0.0, 24),
     (7, 10, 9, 4.5, 40),
     (8, 15, 9, 5.5, 16),
 ]
