@@ -121,7 +121,7 @@ int pk_code_create(int m, int t, int device, pk_code **out) {
     }
     if (c->ct) {
         const PkClassTable &ct = *c->ct;
-        if ((rc = upload(c, ct.norm, &c->dev.ct_norm)) || (rc = upload(c, ct.logt, &c->dev.ct_log)) ||
+        if ((rc = upload(c, ct.norm, &c->dev.ct_norm)) || (rc = upload(c, ct.col, &c->dev.ct_col)) || (rc = upload(c, ct.logt, &c->dev.ct_log)) ||
             (rc = upload(c, ct.bits, &c->dev.ct_bits)) ||
             (rc = upload(c, ct.hash, reinterpret_cast<const uint64_t **>(&c->dev.ct_hash)))) {
             pk_code_destroy(c);

@@ -137,8 +137,20 @@ struct CtBuilder {
                     uint8_t r = rank[i][w];
                     if (r == 0xFF) r = 0;   // not a syndrome value of this code
                     if (!s1 && i == 0) r |= (uint8_t)(1u << deg[0]);
-                    ct.norm[(i * Q + s1) * Q + v] = r;
+                    ct.norm[(i * Q + v) * Q + s1] = r;
                 }
+        // per-position columns in "pair" packing: field i of a column = alpha^p | alpha^{js[i] p} << m, two fields per
+        // 32-bit word -- the XOR of columns then carries (S_1, S_js[i]) side by side, i.e. the rank-table index itself
+        {
+            const int per = 32 / m, nsw = (2 * t + per - 1) / per;
+            ct.col.assign((size_t)n * nsw, 0u);
+            if ((int)(js.size() + 1) / 2 > nsw) return false;
+            for (int p = 0; p < n; ++p)
+                for (size_t i = 0; i < js.size(); ++i) {
+                    const uint32_t pair = c.alog[p % n] | (c.alog[(js[i] * (long)p) % n] << m);
+                    ct.col[(size_t)p * nsw + i / 2] |= pair << ((i % 2) * 2 * m);
+                }
+        }
         // capacity: about V(n,t)/n classes with S_1 != 0 and as many keys again with S_1 = 0
         double vol = 0, binom = 1;
         for (int w = 0; w <= t; ++w) { vol += binom; binom = binom * (n - w) / (w + 1); }
@@ -151,7 +163,7 @@ struct CtBuilder {
     }
     uint32_t key_of(const std::vector<uint32_t> &Sv) const {
         uint32_t key = 0;
-        for (size_t i = 0; i < js.size(); ++i) key += (uint32_t)ct.norm[(i * Q + Sv[0]) * Q + Sv[i + 1]] * ct.mult[i];
+        for (size_t i = 0; i < js.size(); ++i) key += (uint32_t)ct.norm[(i * Q + Sv[i + 1]) * Q + Sv[0]] * ct.mult[i];
         return key;
     }
     void insert(uint32_t key, uint64_t packed) {
@@ -228,7 +240,7 @@ bool PkClassTable::lookup(int m, int t, const uint32_t *packed, uint32_t *A) con
     auto syn = [&](int j) { return (packed[(j - 1) / per] >> (((j - 1) % per) * m)) & (uint32_t)n; };
     const uint32_t s1 = syn(1);
     uint32_t key = 0;
-    for (size_t i = 0; i < mult.size(); ++i) key += (uint32_t)norm[(i * Q + s1) * Q + syn(js[i])] * mult[i];
+    for (size_t i = 0; i < mult.size(); ++i) key += (uint32_t)norm[(i * Q + syn(js[i])) * Q + s1] * mult[i];
     for (int w = 0; w < nw; ++w) A[w] = 0;
     if (!((bits[key >> 5] >> (key & 31)) & 1u)) return false;
     const uint64_t posmask = (t * m == 64) ? ~0ull : ((1ull << (t * m)) - 1);

@@ -19,7 +19,8 @@ struct PkDevTables {
     int k;
     int nk;                // n - k
     // cyclic-class table (PkClassTable), class-table mode
-    const uint8_t *ct_norm;             // [(t-1)][2^m][2^m] rank of S_j * alpha^{-j log S_1}
+    const uint32_t *ct_col;             // [n][NSW] columns in pair packing: field i = alpha^p | alpha^{j_i p} << m
+    const uint8_t *ct_norm;             // [fields][2^m (S_j)][2^m (S_1)] rank of S_j * alpha^{-j log S_1}
     const uint8_t *ct_log;              // [2^m] log S_1 (0 for S_1 = 0)
     const uint32_t *ct_bits;            // [2^(kb+1) / 32] decodable-class bitmap
     const unsigned long long *ct_hash;  // [2^hbits] key << (t m) | t packed positions
@@ -42,7 +43,7 @@ struct PkClassTable {
     size_t entries = 0;
     std::vector<int> js;               // the odd j > 1 whose S_j is independent: one key field each (pk_ct_used)
     std::vector<uint8_t> norm, logt;
-    std::vector<uint32_t> mult, bits;
+    std::vector<uint32_t> mult, bits, col;
     std::vector<uint64_t> hash;
     // verdict and error positions (bit mask, nw words) for packed syndromes S_1..S_2t (hcol layout); host mirror of the device lookup
     bool lookup(int m, int t, const uint32_t *packed, uint32_t *A) const;

@@ -144,13 +144,13 @@ struct PkSmem {
     __host__ __device__ static constexpr size_t total_a(int nk) { return tables(nk) + (size_t)PK_WARPS_A * W_SZ_A; }
     // phase B of the bit-sliced codes needs neither the GF product table nor the Chien offsets: columns only
     static constexpr size_t B_COL_OFF = LUT ? COL_OFF : 0;
-    // class-table mode: rank tables (one 2^m x 2^m byte table per independent S_j) and log S_1 behind the columns
+    // class-table mode: log S_1 behind the columns; the rank tables (one 2^m x 2^m byte table per independent S_j)
+    // are STATIC shared memory (pk_ct_norm_smem) so that their address folds into the LDS immediate
     static constexpr int CT_NJ = CT ? pk_ct_index(M, 2 * T + 1) : 0;
-    static constexpr size_t CT_NORM_OFF = COL_SZ;
     static constexpr size_t CT_NORM_SZ = (size_t)CT_NJ << (2 * M);
-    static constexpr size_t CT_LOG_OFF = CT_NORM_OFF + CT_NORM_SZ;
+    static constexpr size_t CT_LOG_OFF = COL_SZ;
     static constexpr size_t CT_LOG_SZ = CT ? pk_align16((size_t)1 << M) : 0;
-    __host__ __device__ static constexpr size_t tables_b(int nk) { return LUT ? tables(nk) : COL_SZ + CT_NORM_SZ + CT_LOG_SZ; }
+    __host__ __device__ static constexpr size_t tables_b(int nk) { return LUT ? tables(nk) : COL_SZ + CT_LOG_SZ; }
     __host__ __device__ static constexpr size_t total_b(int nk) { return tables_b(nk) + (size_t)PK_WARPS_B * W_SZ_B; }
 };
 
@@ -160,6 +160,12 @@ __device__ __forceinline__ uint32_t pk_getbit(const uint32_t (&F)[NW], int p) {
 #pragma unroll
     for (int i = 1; i < NW; ++i) w = ((p >> 5) == i) ? F[i] : w;
     return (w >> (p & 31)) & 1u;
+}
+
+template <int M, int NJ>
+__device__ __forceinline__ uint8_t *pk_ct_norm_smem() {
+    __shared__ __align__(16) uint8_t tab[(size_t)(NJ > 0 ? NJ : 1) << (2 * M)];
+    return tab;
 }
 
 // ------------------------------------------------------------------ one frame, one warp
@@ -175,7 +181,7 @@ struct KanekoWarp {
         const uint32_t *col;
         const uint16_t *lut;
         // class-table mode: rank tables and log S_1 in shared memory, bitmap and position table in global memory
-        const uint8_t *ctn, *ctlog;
+        const uint8_t *ctlog;
         const uint32_t *ctbits;
         const unsigned long long *cthash;
         uint32_t cthshift, cthmask;
@@ -425,20 +431,19 @@ struct KanekoWarp {
     }
 
     // ---- class-table mode (PkClassTable): key of a packed syndrome, position-table probe, positions
-    template <int J>
-    __device__ static __forceinline__ void ct_key_term(const Tables &tb, const uint32_t (&w)[SW], uint32_t row, uint32_t &key) {
-        if constexpr (J < 2 * T) {
-            if constexpr (pk_ct_used(M, J)) {
-                constexpr int jj = pk_ct_index(M, J), wi = (J - 1) / C::PER, sh = ((J - 1) % C::PER) * M;
-                const uint32_t v = (w[wi] >> sh) & (uint32_t)N;
-                key += (uint32_t)tb.ctn[(jj << (2 * M)) + row + v] * tb.ctmult[jj];
-            }
-            ct_key_term<J + 2>(tb, w, row, key);
+    // w: XOR of pair-packed columns (PkClassTable::col): field i = S_1 | S_{j_i} << M at bit (i % 2) * 2M of word i / 2
+    template <int I>
+    __device__ static __forceinline__ void ct_key_term(const Tables &tb, const uint32_t (&w)[SW], uint32_t &key) {
+        if constexpr (I < SM::CT_NJ) {
+            const uint8_t *tab = pk_ct_norm_smem<M, SM::CT_NJ>();
+            const uint32_t idx = (I % 2) ? (w[I / 2] >> (2 * M)) : (w[I / 2] & ((1u << (2 * M)) - 1u));
+            key += (uint32_t)tab[(I << (2 * M)) + idx] * tb.ctmult[I];
+            ct_key_term<I + 1>(tb, w, key);
         }
     }
     __device__ static __forceinline__ uint32_t ct_key(const Tables &tb, const uint32_t (&w)[SW]) {
         uint32_t key = 0;
-        ct_key_term<3>(tb, w, (w[0] & (uint32_t)N) << M, key);
+        ct_key_term<0>(tb, w, key);
         return key;
     }
     __device__ static __forceinline__ unsigned long long ct_find(const Tables &tb, uint32_t key) {
@@ -728,6 +733,15 @@ struct KanekoWarp {
                 while (ok) {
                     const int q = __ffs(ok) - 1;
                     ok &= ok - 1;
+                    // A pattern whose flip set is within distance t of the best codeword's decodes to that codeword
+                    // again (bounded-distance decoding is unique): l == l0, never an improvement.  Most decodable
+                    // patterns of a low-SNR frame are of this kind.
+                    if (s.have) {
+                        int dist = 0;
+#pragma unroll
+                        for (int w2 = 0; w2 < NW; ++w2) dist += __popc(Ul[SW + w2] ^ Ub[SW + w2] ^ wm.pb[q * NW + w2] ^ s.bestF[w2]);
+                        if (dist <= T) continue;
+                    }
                     uint32_t w[SW];
 #pragma unroll
                     for (int a = 0; a < SW; ++a) w[a] = u[a] ^ wm.cm[q * SW + a];
@@ -933,12 +947,15 @@ __device__ __forceinline__ void pk_stage_tables(unsigned char *smem, const PkDev
             for (int i = tid; i < C::N; i += nth) xo[i] = tb.xoff[i];
         }
         uint32_t *col = reinterpret_cast<uint32_t *>(smem + (need_mul ? SM::COL_OFF : SM::B_COL_OFF));
-        for (int i = tid; i < C::N * SM::SW; i += nth) col[i] = tb.hcol[i];
         if constexpr (CT) {
+            // class-table search: pair-packed columns instead of the S_1..S_2t columns (the algebraic decoder is not used)
+            for (int i = tid; i < C::N * SM::SW; i += nth) col[i] = tb.ct_col[i];
             const uint32_t *src = reinterpret_cast<const uint32_t *>(tb.ct_norm);
-            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + SM::CT_NORM_OFF);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(pk_ct_norm_smem<M, SM::CT_NJ>());
             for (int i = tid; i < (int)(SM::CT_NORM_SZ / 4); i += nth) dst[i] = src[i];
             for (int i = tid; i < (1 << M); i += nth) smem[SM::CT_LOG_OFF + i] = tb.ct_log[i];
+        } else {
+            for (int i = tid; i < C::N * SM::SW; i += nth) col[i] = tb.hcol[i];
         }
     } else {
         uint32_t *col = reinterpret_cast<uint32_t *>(smem + SM::COL_OFF);
@@ -1187,7 +1204,6 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
     tabs.col = reinterpret_cast<const uint32_t *>(smem + SM::B_COL_OFF);
     tabs.lut = reinterpret_cast<const uint16_t *>(smem + SM::LUT_OFF);
     if constexpr (CT) {
-        tabs.ctn = smem + SM::CT_NORM_OFF;
         tabs.ctlog = smem + SM::CT_LOG_OFF;
         tabs.ctbits = tb.ct_bits;
         tabs.cthash = tb.ct_hash;
