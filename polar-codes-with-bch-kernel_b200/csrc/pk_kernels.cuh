@@ -651,6 +651,15 @@ struct KanekoWarp {
             }
         }
         __syncwarp();
+        // class-table mode: flip sets of the last codewords this lane looked up and found worse than l0.  Any later
+        // pattern within distance t of one of them decodes to that codeword again (never an improvement: l0 only
+        // decreases), so it needs no table probe.  All-ones = empty (farther than t from every pattern).
+        constexpr int KR = CT ? 2 : 1;
+        uint32_t rej[KR][NW];
+#pragma unroll
+        for (int k = 0; k < KR; ++k)
+#pragma unroll
+            for (int w = 0; w < NW; ++w) rej[k][w] = PK_FULL;
 
         for (uint32_t base = base0;; base += 1024u * G) {
             const uint32_t gbase = base - 1024u * (uint32_t)wi;   // first pattern of this group step
@@ -662,7 +671,108 @@ struct KanekoWarp {
             const uint32_t lane_first = base + 32u * lane;
             uint32_t vmask = (s.bound <= lane_first) ? 0u : ((s.bound - lane_first >= 32u) ? PK_FULL : ((1u << (s.bound - lane_first)) - 1u));
             if (lane_first < start) vmask = 0u;   // patterns below `start` were run by phase A (start is a multiple of 32)
-            uint32_t cand = 0;   // bit q: trial lane_first + q succeeded (and, LUT: its metric may still beat l0)
+            uint32_t cand = 0;   // bit q: trial lane_first + q succeeded (and, LUT / CT: its metric may still beat l0)
+            double bsum = 0.0;   // reliabilities flipped by pattern bits 10.. (base part)
+            if constexpr (LUT || CT) {
+                uint32_t hb = base >> 10;
+                while (hb) {
+                    const int b = __ffs(hb) - 1;
+                    hb &= hb - 1;
+                    bsum += wm.skey[10 + b];
+                }
+            }
+            // Per-lane filter of decodable trials (bits of `ok`) against the search state `st`, with an APPROXIMATE l
+            // (pattern part + located positions, any summation order).  It only discards trials whose l exceeds l0 by
+            // far more than the rounding slack, so the exact in-order test below sees every possible improvement
+            // (a stale l0 is conservative: l0 only decreases).  Run again on the not yet visited candidates
+            // whenever an improvement lowers l0 inside a step.
+            auto refine = [&](uint32_t ok, const Search &st) -> uint32_t {
+                uint32_t out = 0;
+                if constexpr (LUT) {
+                    while (ok) {
+                        const int q = __ffs(ok) - 1;
+                        ok &= ok - 1;
+                        const uint32_t e = tb.lut[u[0] ^ wm.cm[q]];
+                        const double lp = wm.wl[q] + lsum + bsum;
+                        double la = lp;
+#pragma unroll
+                        for (int j = 0; j < T; ++j) {
+                            const uint32_t p = (e >> (j * M)) & (uint32_t)N;
+                            if (p != (uint32_t)N) {
+                                uint32_t pw = Ul[SW] ^ Ub[SW] ^ wm.pb[q * NW];
+#pragma unroll
+                                for (int w = 1; w < NW; ++w)
+                                    pw = ((p >> 5) == (uint32_t)w) ? (Ul[SW + w] ^ Ub[SW + w] ^ wm.pb[q * NW + w]) : pw;
+                                const double a = wm.alpha[p];
+                                la += ((pw >> (p & 31)) & 1u) ? -a : a;
+                            }
+                        }
+                        if (!((la - st.l0) > 1e-9 * (lp + st.l0))) out |= 1u << q;
+                    }
+                } else if constexpr (CT) {
+                    while (ok) {
+                        const int q = __ffs(ok) - 1;
+                        ok &= ok - 1;
+                        uint32_t pat[NW];   // positions flipped by this pattern
+#pragma unroll
+                        for (int w2 = 0; w2 < NW; ++w2) pat[w2] = Ul[SW + w2] ^ Ub[SW + w2] ^ wm.pb[q * NW + w2];
+                        {
+                            // A pattern whose flip set is within distance t of a known codeword's decodes to that
+                            // codeword again (bounded-distance decoding is unique).  The best one: l == l0, never an
+                            // improvement -- most decodable patterns of a low-SNR frame are of this kind.
+                            int dist = st.have ? 0 : 99;
+#pragma unroll
+                            for (int w2 = 0; w2 < NW; ++w2) dist += __popc(pat[w2] ^ st.bestF[w2]);
+                            bool known = dist <= T;
+#pragma unroll
+                            for (int k = 0; k < KR; ++k) {
+                                int dk = 0;
+#pragma unroll
+                                for (int w2 = 0; w2 < NW; ++w2) dk += __popc(pat[w2] ^ rej[k][w2]);
+                                known = known || (dk <= T);
+                            }
+                            if (known) continue;
+                        }
+                        uint32_t w[SW];
+#pragma unroll
+                        for (int a = 0; a < SW; ++a) w[a] = u[a] ^ wm.cm[q * SW + a];
+                        const unsigned long long e = ct_find(tb, ct_key(tb, w));
+                        const uint32_t sh = tb.ctlog[w[0] & (uint32_t)N];
+                        const double lp = wm.wl[q] + lsum + bsum;
+                        double la = lp;
+                        uint32_t fl[NW];    // flip set of the decoded codeword = pattern ^ located positions
+#pragma unroll
+                        for (int w2 = 0; w2 < NW; ++w2) fl[w2] = pat[w2];
+#pragma unroll
+                        for (int j = 0; j < T; ++j) {
+                            const uint32_t p = ct_pos(e, j, sh);
+                            if (p != (uint32_t)N) {
+                                uint32_t pw = pat[0];
+#pragma unroll
+                                for (int w2 = 1; w2 < NW; ++w2) pw = ((p >> 5) == (uint32_t)w2) ? pat[w2] : pw;
+                                const double a = wm.alpha[p];
+                                la += ((pw >> (p & 31)) & 1u) ? -a : a;
+#pragma unroll
+                                for (int w2 = 0; w2 < NW; ++w2) fl[w2] ^= ((p >> 5) == (uint32_t)w2) ? (1u << (p & 31)) : 0u;
+                            }
+                        }
+                        if (!((la - st.l0) > 1e-9 * (lp + st.l0))) {
+                            out |= 1u << q;
+                        } else {
+#pragma unroll
+                            for (int k = KR - 1; k > 0; --k)
+#pragma unroll
+                                for (int w2 = 0; w2 < NW; ++w2) rej[k][w2] = rej[k - 1][w2];
+#pragma unroll
+                            for (int w2 = 0; w2 < NW; ++w2) rej[0][w2] = fl[w2];
+                        }
+                    }
+                } else {
+                    out = ok;   // bit-sliced mode: every decodable trial is evaluated exactly
+                }
+                return out;
+            };
+            const uint32_t nimpr0 = s.nimpr;
             if (base >= s.bound || base + 1024u <= start) {
                 // nothing to run in this block (G > 1: blocks past the bound; first step: blocks below `start`)
             } else if constexpr (LUT) {
@@ -672,41 +782,7 @@ struct KanekoWarp {
                     const uint32_t e = tb.lut[u[0] ^ wm.cm[q]];
                     ok |= (e & 0x8000u) ? 0u : (1u << q);
                 }
-                ok &= vmask;
-                cand = 0;
-                // Per-lane pre-filter with an APPROXIMATE l (pattern part + located positions, any summation
-                // order).  It only discards trials whose l exceeds l0 by far more than the rounding slack, so
-                // the exact in-order test below sees every possible improvement (a stale l0 is conservative:
-                // l0 only decreases).
-                double bsum = 0.0;
-                {
-                    uint32_t hb = base >> 10;
-                    while (hb) {
-                        const int b = __ffs(hb) - 1;
-                        hb &= hb - 1;
-                        bsum += wm.skey[10 + b];
-                    }
-                }
-                while (ok) {
-                    const int q = __ffs(ok) - 1;
-                    ok &= ok - 1;
-                    const uint32_t e = tb.lut[u[0] ^ wm.cm[q]];
-                    const double lp = wm.wl[q] + lsum + bsum;
-                    double la = lp;
-#pragma unroll
-                    for (int j = 0; j < T; ++j) {
-                        const uint32_t p = (e >> (j * M)) & (uint32_t)N;
-                        if (p != (uint32_t)N) {
-                            uint32_t pw = Ul[SW] ^ Ub[SW] ^ wm.pb[q * NW];
-#pragma unroll
-                            for (int w = 1; w < NW; ++w)
-                                pw = ((p >> 5) == (uint32_t)w) ? (Ul[SW + w] ^ Ub[SW + w] ^ wm.pb[q * NW + w]) : pw;
-                            const double a = wm.alpha[p];
-                            la += ((pw >> (p & 31)) & 1u) ? -a : a;
-                        }
-                    }
-                    if (!((la - s.l0) > 1e-9 * (lp + s.l0))) cand |= 1u << q;
-                }
+                cand = refine(ok & vmask, s);
             } else if constexpr (CT) {
                 // one bitmap probe per pattern: does ANY error pattern of weight <= t have this syndrome class?
                 uint32_t ok = 0;
@@ -719,50 +795,8 @@ struct KanekoWarp {
                     const uint32_t word = __ldg(tb.ctbits + (key >> 5));
                     ok |= ((word >> (key & 31)) & 1u) << q;
                 }
-                ok &= vmask;
-                // the few decodable ones: positions from the class entry, approximate-l filter as in coset-table mode
-                double bsum = 0.0;
-                {
-                    uint32_t hb = base >> 10;
-                    while (hb) {
-                        const int b = __ffs(hb) - 1;
-                        hb &= hb - 1;
-                        bsum += wm.skey[10 + b];
-                    }
-                }
-                while (ok) {
-                    const int q = __ffs(ok) - 1;
-                    ok &= ok - 1;
-                    // A pattern whose flip set is within distance t of the best codeword's decodes to that codeword
-                    // again (bounded-distance decoding is unique): l == l0, never an improvement.  Most decodable
-                    // patterns of a low-SNR frame are of this kind.
-                    if (s.have) {
-                        int dist = 0;
-#pragma unroll
-                        for (int w2 = 0; w2 < NW; ++w2) dist += __popc(Ul[SW + w2] ^ Ub[SW + w2] ^ wm.pb[q * NW + w2] ^ s.bestF[w2]);
-                        if (dist <= T) continue;
-                    }
-                    uint32_t w[SW];
-#pragma unroll
-                    for (int a = 0; a < SW; ++a) w[a] = u[a] ^ wm.cm[q * SW + a];
-                    const unsigned long long e = ct_find(tb, ct_key(tb, w));
-                    const uint32_t sh = tb.ctlog[w[0] & (uint32_t)N];
-                    const double lp = wm.wl[q] + lsum + bsum;
-                    double la = lp;
-#pragma unroll
-                    for (int j = 0; j < T; ++j) {
-                        const uint32_t p = ct_pos(e, j, sh);
-                        if (p != (uint32_t)N) {
-                            uint32_t pw = Ul[SW] ^ Ub[SW] ^ wm.pb[q * NW];
-#pragma unroll
-                            for (int w2 = 1; w2 < NW; ++w2)
-                                pw = ((p >> 5) == (uint32_t)w2) ? (Ul[SW + w2] ^ Ub[SW + w2] ^ wm.pb[q * NW + w2]) : pw;
-                            const double a = wm.alpha[p];
-                            la += ((pw >> (p & 31)) & 1u) ? -a : a;
-                        }
-                    }
-                    if (!((la - s.l0) > 1e-9 * (lp + s.l0))) cand |= 1u << q;
-                }
+                // the decodable ones: positions from the class entry, approximate-l filter as in coset-table mode
+                cand = refine(ok & vmask, s);
             } else {
                 auto getS = [&](int j, uint32_t *o) {   // j may be a run-time value (looped BM)
                     const int wi = (j - 1) / C::PER, sh = ((j - 1) % C::PER) * M;
@@ -814,10 +848,10 @@ struct KanekoWarp {
                 l = calc_l(wm, F);
                 return l < st.l0;
             };
-            if (G > 1) {
+            if (G > 1 && !(LUT || CT)) {
                 // cooperative search: every warp first thins its own candidates IN PARALLEL against the state
                 // at the start of the step (conservative: l0 only decreases), so that the ordered hand-over
-                // below only sees the rare real improvements
+                // below only sees the rare real improvements (table modes: refine() has done that already)
                 uint32_t keep = 0;
                 uint32_t lanes_with = __ballot_sync(PK_FULL, cand != 0);
                 while (lanes_with) {
@@ -856,15 +890,18 @@ struct KanekoWarp {
                     if (turn == wi) {
                         if (G > 1 && turn > 0) s = *shared;
                         bool stop = s.early;
-                        uint32_t lanes_with = __ballot_sync(PK_FULL, cand != 0);
-                        while (lanes_with && !stop) {
+                        if ((LUT || CT) && s.nimpr != nimpr0) cand = refine(cand, s);   // earlier warps of this step lowered l0
+                        while (!stop) {
+                            const uint32_t lanes_with = __ballot_sync(PK_FULL, cand != 0);
+                            if (!lanes_with) break;
                             const int src = __ffs(lanes_with) - 1;
-                            lanes_with &= lanes_with - 1;
                             uint32_t word = __shfl_sync(PK_FULL, cand, src);
                             const uint32_t usrc = __shfl_sync(PK_FULL, u[0], src);
+                            bool improved = false;
                             while (word) {
                                 const int q = __ffs(word) - 1;
                                 word &= word - 1;
+                                if (lane == src) cand &= ~(1u << q);   // visited
                                 const uint32_t is = base + 32u * src + q;
                                 if (is >= s.bound) { stop = true; break; }
                                 uint32_t F[NW];
@@ -873,8 +910,13 @@ struct KanekoWarp {
                                 if (eval(src, q, usrc, is, s, F, m, l)) {
                                     s.step_last = is + 1;
                                     if (commit(s, wm, kp, l, m, F, is)) { stop = true; break; }
+                                    improved = true;
+                                    break;
                                 }
                             }
+                            // l0 went down: filter what is left of the step again, all lanes in parallel, instead of
+                            // evaluating every stale candidate exactly one by one
+                            if ((LUT || CT) && improved && !stop) cand = refine(cand, s);
                         }
                         if (G > 1 && lane == 0) *shared = s;
                     }
@@ -1224,14 +1266,17 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
     // ~10 % throughput (hand-over barriers), so when there are far more big frames than CTAs only one round of
     // them is searched cooperatively and the rest go warp-per-frame below; with few big frames (the tail
     // regime of medium / high SNR launches) all of them are.
-    const unsigned long long n_coop = (n_big > 8ull * gridDim.x) ? (unsigned long long)gridDim.x : n_big;
+    // With fewer parked frames than CTAs (high SNR) the launch time is the latency of the longest search:
+    // then the small frames are searched by a whole CTA as well.
+    const bool all_coop = (n_long + n_big) <= (unsigned long long)gridDim.x;
+    const unsigned long long n_coop = all_coop ? n_big + n_long : (n_big > 8ull * gridDim.x) ? (unsigned long long)gridDim.x : n_big;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_idx = atomicAdd(&ctl->queue_big, 1ull);
         __syncthreads();
         const unsigned long long idx = s_idx;
         if (idx >= n_coop) break;
-        const PkLongRec *rec = longs + (long_cap - 1 - (long)idx);
+        const PkLongRec *rec = (idx < n_big) ? longs + (long_cap - 1 - (long)idx) : longs + (idx - n_big);
         const long f = (long)rec->frame;
         double yv[NW];
         uint32_t CW[NW];
@@ -1247,7 +1292,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
         }
     }
     // ---- small frames (and the big ones left over): one warp each
-    const unsigned long long n_solo = n_long + (n_big - n_coop);
+    const unsigned long long n_solo = all_coop ? 0ull : n_long + (n_big - n_coop);
     for (;;) {
         unsigned long long idx = 0;
         if (lane == 0) idx = atomicAdd(&ctl->queue_b, 1ull);
