@@ -35,7 +35,9 @@
 
 #define PK_FULL 0xFFFFFFFFu
 #define PK_WARPS_A 8        // warps per CTA, phase A
-#define PK_WARPS_B 4        // warps per CTA, phase B (the bit-sliced decoder needs ~170 registers)
+#define PK_WARPS_B 4        // warps per CTA, phase B, bit-sliced decoder (needs ~170 registers)
+#define PK_WARPS_B_LUT 16   // warps per CTA, phase B, coset-table mode: a whole CTA searches one long frame, 16K patterns per step
+                            // (the uncapped searches of these codes end in a few monster frames: latency matters)
 #ifndef PK_BS_LOOP
 #define PK_BS_LOOP true     // bit-sliced BM as one loop body (instruction-cache friendly)
 #endif
@@ -151,7 +153,8 @@ struct PkSmem {
     static constexpr size_t CT_LOG_OFF = COL_SZ;
     static constexpr size_t CT_LOG_SZ = CT ? pk_align16((size_t)1 << M) : 0;
     __host__ __device__ static constexpr size_t tables_b(int nk) { return LUT ? tables(nk) : COL_SZ + CT_LOG_SZ; }
-    __host__ __device__ static constexpr size_t total_b(int nk) { return tables_b(nk) + (size_t)PK_WARPS_B * W_SZ_B; }
+    static constexpr int WB = LUT ? PK_WARPS_B_LUT : PK_WARPS_B;                    // warps per phase-B CTA
+    __host__ __device__ static constexpr size_t total_b(int nk) { return tables_b(nk) + (size_t)WB * W_SZ_B; }
 };
 
 template <int NW>
@@ -654,7 +657,7 @@ struct KanekoWarp {
         // class-table mode: flip sets of the last codewords this lane looked up and found worse than l0.  Any later
         // pattern within distance t of one of them decodes to that codeword again (never an improvement: l0 only
         // decreases), so it needs no table probe.  All-ones = empty (farther than t from every pattern).
-        constexpr int KR = CT ? 2 : 1;
+        constexpr int KR = (LUT || CT) ? 2 : 1;
         uint32_t rej[KR][NW];
 #pragma unroll
         for (int k = 0; k < KR; ++k)
@@ -692,22 +695,52 @@ struct KanekoWarp {
                     while (ok) {
                         const int q = __ffs(ok) - 1;
                         ok &= ok - 1;
+                        uint32_t pat[NW];   // positions flipped by this pattern
+#pragma unroll
+                        for (int w2 = 0; w2 < NW; ++w2) pat[w2] = Ul[SW + w2] ^ Ub[SW + w2] ^ wm.pb[q * NW + w2];
+                        {   // within distance t of a known codeword: decodes to it again (see class-table mode below)
+                            int dist = st.have ? 0 : 99;
+#pragma unroll
+                            for (int w2 = 0; w2 < NW; ++w2) dist += __popc(pat[w2] ^ st.bestF[w2]);
+                            bool known = dist <= T;
+#pragma unroll
+                            for (int k = 0; k < KR; ++k) {
+                                int dk = 0;
+#pragma unroll
+                                for (int w2 = 0; w2 < NW; ++w2) dk += __popc(pat[w2] ^ rej[k][w2]);
+                                known = known || (dk <= T);
+                            }
+                            if (known) continue;
+                        }
                         const uint32_t e = tb.lut[u[0] ^ wm.cm[q]];
                         const double lp = wm.wl[q] + lsum + bsum;
                         double la = lp;
+                        uint32_t fl[NW];
+#pragma unroll
+                        for (int w2 = 0; w2 < NW; ++w2) fl[w2] = pat[w2];
 #pragma unroll
                         for (int j = 0; j < T; ++j) {
                             const uint32_t p = (e >> (j * M)) & (uint32_t)N;
                             if (p != (uint32_t)N) {
-                                uint32_t pw = Ul[SW] ^ Ub[SW] ^ wm.pb[q * NW];
+                                uint32_t pw = pat[0];
 #pragma unroll
-                                for (int w = 1; w < NW; ++w)
-                                    pw = ((p >> 5) == (uint32_t)w) ? (Ul[SW + w] ^ Ub[SW + w] ^ wm.pb[q * NW + w]) : pw;
+                                for (int w = 1; w < NW; ++w) pw = ((p >> 5) == (uint32_t)w) ? pat[w] : pw;
                                 const double a = wm.alpha[p];
                                 la += ((pw >> (p & 31)) & 1u) ? -a : a;
+#pragma unroll
+                                for (int w2 = 0; w2 < NW; ++w2) fl[w2] ^= ((p >> 5) == (uint32_t)w2) ? (1u << (p & 31)) : 0u;
                             }
                         }
-                        if (!((la - st.l0) > 1e-9 * (lp + st.l0))) out |= 1u << q;
+                        if (!((la - st.l0) > 1e-9 * (lp + st.l0))) {
+                            out |= 1u << q;
+                        } else {
+#pragma unroll
+                            for (int k = KR - 1; k > 0; --k)
+#pragma unroll
+                                for (int w2 = 0; w2 < NW; ++w2) rej[k][w2] = rej[k - 1][w2];
+#pragma unroll
+                            for (int w2 = 0; w2 < NW; ++w2) rej[0][w2] = fl[w2];
+                        }
                     }
                 } else if constexpr (CT) {
                     while (ok) {
@@ -1227,7 +1260,7 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
 
 // ------------------------------------------------------------------ phase B
 template <int M, int T, bool LUT, bool GEN, bool CT = false>
-__global__ void __launch_bounds__(PK_WARPS_B * 32, CT ? PkTraits<M, T>::MINB_CT : PkTraits<M, T>::MINB)
+__global__ void __launch_bounds__(PkSmem<M, T, LUT, CT>::WB * 32, CT ? PkTraits<M, T>::MINB_CT : LUT ? 2 : PkTraits<M, T>::MINB)
 k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkLongRec *longs, long long_cap) {
     typedef PkSmem<M, T, LUT, CT> SM;
     typedef KanekoWarp<M, T, LUT, CT> KW;
@@ -1255,10 +1288,10 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
         for (int i = 0; i < 8; ++i) tabs.ctmult[i] = tb.ct_mult[i];
     }
     if constexpr (SM::BSM)   // root words of the bit-sliced Chien search go to a per-warp slice of global scratch
-        wm.z = io.zscratch + ((size_t)blockIdx.x * PK_WARPS_B + warp) * (size_t)KW::N * 32;
+        wm.z = io.zscratch + ((size_t)blockIdx.x * SM::WB + warp) * (size_t)KW::N * 32;
     __shared__ typename KW::Search s_shared;
     __shared__ unsigned long long s_idx;
-    __shared__ uint32_t s_votes[2 * PK_WARPS_B];
+    __shared__ uint32_t s_votes[2 * SM::WB];
 
     PkWarpTotals tot;
     tot.clear();
@@ -1285,7 +1318,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
         typename KW::Search s;
         KW::setup(tabs, wm, yv, kp, fr);     // every warp keeps its own copy of the frame tables
         KW::unpark(s, rec);
-        KW::template wide<PK_WARPS_B>(tabs, wm, kp, fr, s, rec->base, &s_shared, s_votes, warp);
+        KW::template wide<SM::WB>(tabs, wm, kp, fr, s, rec->base, &s_shared, s_votes, warp);
         if (warp == 0) {
             KW::search_finish(s);
             pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot);
@@ -1418,11 +1451,11 @@ struct PkLaunch {
         const size_t sb = PkSmem<M, T, LUT, CT>::total_b(nk);
         e = cudaFuncSetAttribute(k_phase_b<M, T, LUT, GEN, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_phase_b<M, T, LUT, GEN, CT>, PK_WARPS_B * 32, sb);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_phase_b<M, T, LUT, GEN, CT>, PkSmem<M, T, LUT, CT>::WB * 32, sb);
         if (e != cudaSuccess) return e;
         if (per < 1) return cudaErrorLaunchOutOfResources;
         gb->grid = sm_count * per;
-        gb->block = PK_WARPS_B * 32;
+        gb->block = PkSmem<M, T, LUT, CT>::WB * 32;
         gb->smem = sb;
         return cudaSuccess;
     }
