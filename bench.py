@@ -310,33 +310,42 @@ def run_b200(a):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bytes_per_frame * B / (dom_ms * 1e-3) / 1e9
     dom_trials = int(tot_np[dom, :, 3].sum()) // max(1, world)
-    kname = (f"k_phase_a + k_phase_b<{dom_code.m},{dom_code.t},{'coset table' if dom_code.uses_lut else 'bit-sliced BM+Chien'}> "
-             "(one launch pair per SNR point; phase B is ~89 % of kernel time, profiles/r1_launches.md)")
+    mode = {0: "bit-sliced BM+Chien", 1: "coset table", 2: "cyclic-class table"}[dom_code.table_kind]
+    kname = (f"k_phase_a + k_phase_b<{dom_code.m},{dom_code.t},{mode}> "
+             "(one launch pair per SNR point; phase B is ~85 % of this code's kernel time, profiles/r1_launches.md)")
     sm_hz = (clocks["sm_mhz"] or 1965.0) * 1e6
     trials_per_s_dom = dom_trials / (by_code[dom] * a.steps * 1e-3)
-    # instructions per trial of the dominant kernel, from the committed ncu capture of this kernel
-    # (profiles/r1_ncu_summary.md: smsp__inst_executed.sum / trials, BCH(63,30,13) J=15 at 0 dB)
-    NCU_WARP_INST_PER_TRIAL = 13.3
-    NCU_ALU_PIPE_BUSY = 0.69
-    NCU_DRAM_BYTES_PER_LAUNCH = 9438208   # dram__bytes_read+write, 16384 frames of n=63 at 0 dB
+    # the 0 dB launch (throughput regime, 25 207 trials per frame) against the unit that binds the class-table search:
+    # the L1TEX data pipe (one 32-byte bitmap sector per trial from L2 + 5 byte lookups in shared memory per trial).
+    # Per-trial wavefront / sector / instruction counts are those of the committed ncu capture of this kernel
+    # (profiles/r1_ncu_summary.md, prof_r1d_ct_m6t6: BCH(63,30,13) J=15 at 0 dB, 16 384 frames).
+    NCU = {"wavefronts_per_trial": 0.867, "l2_sectors_per_trial": 1.02, "warp_inst_per_trial": 1.59,
+           "l1tex_throughput_pct": 88.7, "lts_throughput_pct": 71.4, "dram_bytes_per_launch": 125782528}
+    ms0 = share[(dom, 0)]
+    trials0 = int(tot_np[dom, 0, 3]) // max(1, world) // a.steps
+    tps0 = trials0 / (ms0 * 1e-3)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (dom_code.n == 63 and B == 16384) else None,
+        "traffic": NCU["dram_bytes_per_launch"] if (dom_code.n == 63 and B == 16384 and dom_code.table_kind == 2) else None,
         "algorithmic_bytes_per_launch": bytes_per_frame * B,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
         "kernel": kname, "avg_launch_ms": dom_ms, "share_of_step": by_code[dom] / step_ms,
-        "note": ("integer search kernel: neither HBM- nor tensor-bound (SURVEY 8d, DRAM traffic == algorithmic bytes); "
-                 "the binding unit is the INT ALU pipe (LOP3 of the bit-sliced decoder) -- see issue_slot"),
-        "issue_slot": {
-            "trials_per_s": trials_per_s_dom,
+        "note": ("integer search kernel: neither HBM- nor tensor-bound (SURVEY 8d).  `traffic` is the ncu DRAM traffic of the "
+                 "0 dB launch with a cold L2 (ncu flushes it): frames (9.4 MB) + first touch of the 32 MB class bitmap and "
+                 "32 MB position table, which stay L2-resident between launches.  The binding unit is the L1TEX data pipe "
+                 "(random 32-byte L2 sector gathers + shared-memory byte lookups) -- see l1tex"),
+        "l1tex": {
+            "launch": "0 dB point of the dominant code", "launch_ms": ms0, "trials_per_s": tps0,
+            "wavefronts_per_trial_ncu": NCU["wavefronts_per_trial"],
+            "achieved_wavefronts_per_s": tps0 * NCU["wavefronts_per_trial"],
+            "peak_wavefronts_per_s": 148 * sm_hz,   # one L1TEX data-pipe wavefront per SM per clock
+            "frac": tps0 * NCU["wavefronts_per_trial"] / (148 * sm_hz),
+            "l2_sectors_per_trial_ncu": NCU["l2_sectors_per_trial"],
+            "warp_inst_per_trial_ncu": NCU["warp_inst_per_trial"],
+            "ncu_l1tex_throughput_pct": NCU["l1tex_throughput_pct"], "ncu_lts_throughput_pct": NCU["lts_throughput_pct"],
+            "whole_code_trials_per_s": trials_per_s_dom,
             "algorithmic_gf_macs_per_trial": 2 * dom_code.t * 2 + 2 * dom_code.t ** 2 + dom_code.n * dom_code.t,
-            "warp_inst_per_trial": NCU_WARP_INST_PER_TRIAL,
-            "achieved_warp_inst_per_s": trials_per_s_dom * NCU_WARP_INST_PER_TRIAL,
-            "peak_warp_inst_per_s": 148 * 4 * sm_hz,
-            "frac": trials_per_s_dom * NCU_WARP_INST_PER_TRIAL / (148 * 4 * sm_hz),
-            "alu_pipe_peak_warp_inst_per_s": 148 * 4 * 0.5 * sm_hz,
-            "alu_pipe_busy_ncu": NCU_ALU_PIPE_BUSY,
-            "source": "profiles/r1_ncu_summary.md (prof_r1b_phaseb_m6t6)",
+            "source": "profiles/r1_ncu_summary.md (prof_r1d_ct_m6t6)",
         },
     }
 

@@ -316,7 +316,7 @@ int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_
     d->kp.frames_per_grab = 2;
     // a narrow BM+Chien step (32 trials) costs about as much latency as a bit-sliced wide step (1024 trials),
     // so those frames move to phase B almost at once; coset-table steps are cheap and stay longer
-    d->kp.limit_a = c->use_lut ? 256u : c->use_ct ? 32u : 64u;
+    d->kp.limit_a = c->use_lut ? 256u : c->use_ct ? 128u : 64u;
     d->mode = c->use_lut ? PK_MODE_LUT : c->use_ct ? PK_MODE_CLASS : PK_MODE_ALG;
     d->kp.big_span = 8192u;
     d->kp.variant = 0;

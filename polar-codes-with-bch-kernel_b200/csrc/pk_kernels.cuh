@@ -143,7 +143,8 @@ struct PkSmem {
     static constexpr size_t W_SZ_B = W_ST + W_ST_SZ;
     static constexpr int ZS = BSM ? 32 : 33;                                        // stride of the root-word buffer
     __host__ __device__ static constexpr size_t tables(int nk) { return LUT_OFF + pk_align16(lut_sz(nk)); }
-    __host__ __device__ static constexpr size_t total_a(int nk) { return tables(nk) + (size_t)PK_WARPS_A * W_SZ_A; }
+    __host__ __device__ static constexpr size_t tables_a(int nk) { return CT ? COL_SZ + pk_align16((size_t)1 << M) : tables(nk); }
+    __host__ __device__ static constexpr size_t total_a(int nk) { return tables_a(nk) + (size_t)PK_WARPS_A * W_SZ_A; }
     // phase B of the bit-sliced codes needs neither the GF product table nor the Chien offsets: columns only
     static constexpr size_t B_COL_OFF = LUT ? COL_OFF : 0;
     // class-table mode: log S_1 behind the columns; the rank tables (one 2^m x 2^m byte table per independent S_j)
@@ -517,6 +518,12 @@ struct KanekoWarp {
             bool succ;
             if constexpr (LUT) {
                 succ = lut_positions(tb.lut[Sx[0]], A);
+            } else if constexpr (CT) {
+                const uint32_t key = ct_key(tb, Sx);
+                succ = ((__ldg(tb.ctbits + (key >> 5)) >> (key & 31)) & 1u) != 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) A[w] = 0;
+                if (succ) ct_positions(ct_find(tb, key), tb.ctlog[Sx[0] & (uint32_t)N], A);
             } else {
                 succ = pk_alg_decode<M, T>(Sx, tb.mul, tb.xoff, A);
             }
@@ -1195,23 +1202,32 @@ __device__ __forceinline__ void pk_emit(const PkIo &io, long f, const uint32_t (
 }
 
 // ------------------------------------------------------------------ phase A
-template <int M, int T, bool LUT, bool GEN>
+template <int M, int T, bool LUT, bool GEN, bool CT = false>
 __global__ void __launch_bounds__(PK_WARPS_A * 32)
 k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, PkLongRec *longs, long long_cap) {
-    typedef PkSmem<M, T, LUT> SM;
-    typedef KanekoWarp<M, T, LUT> KW;
+    typedef PkSmem<M, T, LUT, CT> SM;
+    typedef KanekoWarp<M, T, LUT, CT> KW;
     constexpr int NW = KW::NW;
     extern __shared__ __align__(16) unsigned char smem[];
-    pk_stage_tables<M, T, LUT>(smem, tb, true);
+    pk_stage_tables<M, T, LUT, CT>(smem, tb, !CT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *wb = smem + SM::tables(tb.nk) + (size_t)warp * SM::W_SZ_A;
+    unsigned char *wb = smem + SM::tables_a(tb.nk) + (size_t)warp * SM::W_SZ_A;
     typename KW::WarpMem wm = KW::warp_mem(wb);
     uint32_t *w_u = reinterpret_cast<uint32_t *>(wb + SM::W_U);
     typename KW::Tables tabs;
     tabs.mul = smem + SM::MUL_OFF;
     tabs.xoff = reinterpret_cast<const uint16_t *>(smem + SM::XOFF_OFF);
-    tabs.col = reinterpret_cast<const uint32_t *>(smem + SM::COL_OFF);
+    tabs.col = reinterpret_cast<const uint32_t *>(smem + (CT ? SM::B_COL_OFF : SM::COL_OFF));
     tabs.lut = reinterpret_cast<const uint16_t *>(smem + SM::LUT_OFF);
+    if constexpr (CT) {   // class-table mode: the narrow search probes the class table as well
+        tabs.ctlog = smem + SM::CT_LOG_OFF;
+        tabs.ctbits = tb.ct_bits;
+        tabs.cthash = tb.ct_hash;
+        tabs.cthshift = tb.ct_hshift;
+        tabs.cthmask = tb.ct_hmask;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tabs.ctmult[i] = tb.ct_mult[i];
+    }
     // frames are parked only when a wide kernel exists for this code (long_cap > 0 says so)
     const uint32_t limit = (long_cap > 0) ? kp.limit_a : 0xFFFFFFFFu;
 
@@ -1438,11 +1454,11 @@ struct PkLaunch {
 
     template <bool LUT, bool GEN, bool CT>
     static cudaError_t geom_one(int nk, int sm_count, PkLaunchGeom *ga, PkLaunchGeom *gb) {
-        const size_t sa = PkSmem<M, T, LUT>::total_a(nk);
-        cudaError_t e = cudaFuncSetAttribute(k_phase_a<M, T, LUT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+        const size_t sa = PkSmem<M, T, LUT, CT>::total_a(nk);
+        cudaError_t e = cudaFuncSetAttribute(k_phase_a<M, T, LUT, GEN, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
         if (e != cudaSuccess) return e;
         int per = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_phase_a<M, T, LUT, GEN>, PK_WARPS_A * 32, sa);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_phase_a<M, T, LUT, GEN, CT>, PK_WARPS_A * 32, sa);
         if (e != cudaSuccess) return e;
         if (per < 1) return cudaErrorLaunchOutOfResources;
         ga->grid = sm_count * per;      // persistent: every resident slot of every SM
@@ -1502,7 +1518,7 @@ struct PkLaunch {
         cudaError_t e = cudaMemsetAsync(ctl, 0, sizeof(PkPhaseCtl), st);
         if (e != cudaSuccess) return e;
         const bool wide_ok = g[1].grid > 0 && long_cap > 0 && !(GEN && io.dump_only);
-        k_phase_a<M, T, LUT, GEN><<<g[0].grid, g[0].block, g[0].smem, st>>>(tb, kp, io, B, ctl, longs, wide_ok ? long_cap : 0);
+        k_phase_a<M, T, LUT, GEN, CT><<<g[0].grid, g[0].block, g[0].smem, st>>>(tb, kp, io, B, ctl, longs, wide_ok ? long_cap : 0);
         ++g_pk_launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
