@@ -131,6 +131,14 @@ int pk_kaneko_decode_batch(pk_kaneko *dec, const double *y /*[B][n]*/, long B, u
                            uint32_t *trials /*[B] or NULL*/, pk_frame_rec *recs /*[B] or NULL*/,
                            pk_point_result *totals /*or NULL*/);
 
+/* The same without waiting: the batch is enqueued on the handle's two streams and the call returns.  Several batches
+ * may be enqueued back to back (their copies overlap the kernels of the batches before them); pk_kaneko_wait blocks
+ * until all of them are finished and returns the totals accumulated over them.  The host buffers must stay valid
+ * until then, and must be page-locked (cudaHostAlloc / cudaHostRegister) for the copies to overlap. */
+int pk_kaneko_decode_batch_async(pk_kaneko *dec, const double *y /*[B][n]*/, long B, uint8_t *decided /*[B][n]*/,
+                                 uint32_t *trials /*[B] or NULL*/, pk_frame_rec *recs /*[B] or NULL*/);
+int pk_kaneko_wait(pk_kaneko *dec, pk_point_result *totals /*or NULL*/);
+
 /* Replay mode, device-resident buffers, asynchronous on `stream` (a cudaStream_t, NULL =
  * the handle's own stream).  d_totals (8 x u64, pk_point_result layout) is ACCUMULATED
  * into, the caller zeroes it. */

@@ -31,7 +31,7 @@ SYMBOLS = (
     "pk_last_error pk_device_count pk_code_create pk_code_create_host pk_code_destroy pk_code_info pk_code_tables "
     "pk_code_uses_lut pk_code_set_lut pk_code_class_table_check pk_code_coset_table pk_encode_batch pk_bch_decode_batch pk_kaneko_create "
     "pk_kaneko_destroy pk_kaneko_set_variant pk_kaneko_set_frames_per_grab pk_kaneko_set_phase_a_limit pk_kaneko_launch_geometry pk_kaneko_decode_batch "
-    "pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames pk_generate_frames_dev "
+    "pk_kaneko_decode_batch_async pk_kaneko_wait pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames pk_generate_frames_dev "
     "pk_kaneko_run_point pk_make_kernel_matrix pk_launch_count pk_launch_count_reset "
     "pk_polar_create pk_polar_destroy pk_polar_info pk_polar_trellis_profile pk_make_ebch_kernel pk_polar_encode_batch "
     "pk_polar_kernel_llrs pk_polar_decode_batch pk_polar_decode_batch_dev"
@@ -76,6 +76,8 @@ def _load():
     lib.pk_kaneko_set_variant.argtypes = [vp, i]
     lib.pk_kaneko_launch_geometry.argtypes = [vp, ip, ip, C.POINTER(l)]
     lib.pk_kaneko_decode_batch.argtypes = [vp, vp, l, vp, vp, vp, vp]
+    lib.pk_kaneko_decode_batch_async.argtypes = [vp, vp, l, vp, vp, vp]
+    lib.pk_kaneko_wait.argtypes = [vp, vp]
     lib.pk_kaneko_decode_batch_dev.argtypes = [vp, vp, l, vp, vp, vp, vp, vp]
     lib.pk_kaneko_run_frames_dev.argtypes = [vp, d, i, u64, u64, l, vp, vp, vp]
     lib.pk_kaneko_run_frames.argtypes = [vp, d, i, u64, u64, l, vp, vp]
@@ -246,6 +248,16 @@ class Kaneko:
     def decode_ptr(self, y_ptr, B, decided_ptr, trials_ptr=None, recs_ptr=None, totals_ptr=None):
         """Host pointers given as ints (e.g. pinned torch tensors' data_ptr())."""
         _check(lib.pk_kaneko_decode_batch(self.h, y_ptr, B, decided_ptr, trials_ptr, recs_ptr, totals_ptr))
+
+    def decode_async_ptr(self, y_ptr, B, decided_ptr, trials_ptr=None, recs_ptr=None):
+        """Enqueue a batch (page-locked host pointers as ints) and return; wait() collects."""
+        _check(lib.pk_kaneko_decode_batch_async(self.h, y_ptr, B, decided_ptr, trials_ptr, recs_ptr))
+
+    def wait(self):
+        """Block until every enqueued batch is finished; totals accumulated over them."""
+        tot = np.zeros(8, np.uint64)
+        _check(lib.pk_kaneko_wait(self.h, _np_ptr(tot)))
+        return dict(zip(POINT_FIELDS, (int(v) for v in tot)))
 
     # ---- replay mode, device pointers (ints), asynchronous on `stream`
     def decode_dev(self, d_y, B, d_decided, d_trials=None, d_recs=None, d_totals=None, stream=None):

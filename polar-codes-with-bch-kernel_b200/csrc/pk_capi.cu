@@ -62,6 +62,9 @@ struct pk_kaneko {
     unsigned long long *h_totals = nullptr;   // pinned [8]
     // host-batch pipeline, one set per stream
     long chunk = 0;
+    int next_slot = 0;          // stream / buffer set of the next chunk (alternates across calls as well)
+    bool pending = false;       // asynchronous batches enqueued since the last pk_kaneko_wait
+    cudaEvent_t ev_zero = nullptr;
     double *d_y[2] = {nullptr, nullptr};
     uint8_t *d_dec[2] = {nullptr, nullptr};
     uint32_t *d_tr[2] = {nullptr, nullptr};
@@ -350,6 +353,7 @@ void pk_kaneko_destroy(pk_kaneko *d) {
     cudaFree(d->d_grec);
     if (d->h_totals) cudaFreeHost(d->h_totals);
     if (d->h_grec) cudaFreeHost(d->h_grec);
+    if (d->ev_zero) cudaEventDestroy(d->ev_zero);
     delete d;
 }
 
@@ -453,20 +457,22 @@ static int ensure_pipeline(pk_kaneko *d) {
     return PK_OK;
 }
 
-int pk_kaneko_decode_batch(pk_kaneko *d, const double *y, long B, uint8_t *decided, uint32_t *trials,
-                           pk_frame_rec *recs, pk_point_result *totals) {
-    if (!d || B < 0 || (B && (!y || !decided))) return fail(PK_ERR_ARG, "bad arguments");
-    if (totals) std::memset(totals, 0, sizeof(*totals));
-    if (!B) return PK_OK;
-    PK_CUDA(cudaSetDevice(d->code->device));
+// Chunked, double-buffered: H2D(y) -> kernels -> D2H(results) on alternating streams; nothing here waits for the device.
+static int enqueue_batch(pk_kaneko *d, const double *y, long B, uint8_t *decided, uint32_t *trials, pk_frame_rec *recs) {
     int rc = ensure_pipeline(d);
     if (rc) return rc;
     const int n = d->code->n;
-    PK_CUDA(cudaMemsetAsync(d->d_totals, 0, 8 * sizeof(unsigned long long), d->stream[0]));
-    PK_CUDA(cudaStreamSynchronize(d->stream[0]));
-    // chunked, double-buffered: H2D(y) -> kernel -> D2H(results) on alternating streams
-    int s = 0;
-    for (long off = 0; off < B; off += d->chunk, s ^= 1) {
+    if (!d->pending) {
+        // first batch since the last wait: zero the device totals ahead of both streams
+        if (!d->ev_zero) PK_CUDA(cudaEventCreateWithFlags(&d->ev_zero, cudaEventDisableTiming));
+        PK_CUDA(cudaMemsetAsync(d->d_totals, 0, 8 * sizeof(unsigned long long), d->stream[0]));
+        PK_CUDA(cudaEventRecord(d->ev_zero, d->stream[0]));
+        PK_CUDA(cudaStreamWaitEvent(d->stream[1], d->ev_zero, 0));
+        d->pending = true;
+    }
+    for (long off = 0; off < B; off += d->chunk) {
+        const int s = d->next_slot;
+        d->next_slot ^= 1;
         const long nb = std::min(d->chunk, B - off);
         cudaStream_t st = d->stream[s];
         PK_CUDA(cudaMemcpyAsync(d->d_y[s], y + off * n, (size_t)nb * n * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -481,13 +487,41 @@ int pk_kaneko_decode_batch(pk_kaneko *d, const double *y, long B, uint8_t *decid
         if (recs)
             PK_CUDA(cudaMemcpyAsync(recs + off, d->d_rec[s], (size_t)nb * sizeof(pk_frame_rec), cudaMemcpyDeviceToHost, st));
     }
+    return PK_OK;
+}
+
+int pk_kaneko_wait(pk_kaneko *d, pk_point_result *totals) {
+    if (!d) return fail(PK_ERR_ARG, "NULL handle");
+    if (totals) std::memset(totals, 0, sizeof(*totals));
+    PK_CUDA(cudaSetDevice(d->code->device));
     PK_CUDA(cudaStreamSynchronize(d->stream[0]));
     PK_CUDA(cudaStreamSynchronize(d->stream[1]));
-    if (totals) {
+    if (d->pending && totals) {
         PK_CUDA(cudaMemcpy(d->h_totals, d->d_totals, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         std::memcpy(totals, d->h_totals, sizeof(*totals));
     }
+    d->pending = false;
     return PK_OK;
+}
+
+int pk_kaneko_decode_batch_async(pk_kaneko *d, const double *y, long B, uint8_t *decided, uint32_t *trials,
+                                 pk_frame_rec *recs) {
+    if (!d || B < 0 || (B && (!y || !decided))) return fail(PK_ERR_ARG, "bad arguments");
+    if (!B) return PK_OK;
+    PK_CUDA(cudaSetDevice(d->code->device));
+    return enqueue_batch(d, y, B, decided, trials, recs);
+}
+
+int pk_kaneko_decode_batch(pk_kaneko *d, const double *y, long B, uint8_t *decided, uint32_t *trials,
+                           pk_frame_rec *recs, pk_point_result *totals) {
+    if (!d || B < 0 || (B && (!y || !decided))) return fail(PK_ERR_ARG, "bad arguments");
+    if (totals) std::memset(totals, 0, sizeof(*totals));
+    if (d->pending) return fail(PK_ERR_ARG, "asynchronous batches are pending on this handle: call pk_kaneko_wait first");
+    if (!B) return PK_OK;
+    PK_CUDA(cudaSetDevice(d->code->device));
+    int rc = enqueue_batch(d, y, B, decided, trials, recs);
+    if (rc) { d->pending = false; return rc; }
+    return pk_kaneko_wait(d, totals);
 }
 
 // ------------------------------------------------------------------ generation mode

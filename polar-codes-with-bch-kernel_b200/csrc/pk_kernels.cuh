@@ -26,6 +26,7 @@
 // collapse into a handful of XORs.
 #pragma once
 #include <cfloat>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "pk_alg.cuh"
@@ -36,6 +37,9 @@
 #define PK_FULL 0xFFFFFFFFu
 #define PK_WARPS_A 8        // warps per CTA, phase A
 #define PK_WARPS_B 4        // warps per CTA, phase B, bit-sliced decoder (needs ~170 registers)
+#ifndef PK_WARPS_B_CT
+#define PK_WARPS_B_CT 4     // warps per CTA, phase B, class-table mode (8: no faster in bulk, slower tails at mid SNR)
+#endif
 #define PK_WARPS_B_LUT 16   // warps per CTA, phase B, coset-table mode: a whole CTA searches one long frame, 16K patterns per step
                             // (the uncapped searches of these codes end in a few monster frames: latency matters)
 #ifndef PK_BS_LOOP
@@ -84,7 +88,7 @@ struct PkTraits {
     static constexpr int MINB = BSM_OK ? 2 : 3;                   // phase-B CTAs per SM the register budget is set for
     // cyclic-class table (PkClassTable): key of n-k-m+1 <= 28 bits and key + t*m <= 64 bits, 2^(2m)-byte rank tables
     static constexpr bool CT_OK = !LUT_OK && ((M == 5 && (T == 5 || T == 7)) || (M == 6 && T >= 3 && T <= 6));
-    static constexpr int MINB_CT = 4;
+    static constexpr int MINB_CT = 16 / PK_WARPS_B_CT;           // 16 warps of 128 registers per SM
 };
 
 // Is S_j (odd j >= 3) an independent syndrome, i.e. is the cyclotomic coset of j new among 1, 3, .., j-2?
@@ -154,7 +158,7 @@ struct PkSmem {
     static constexpr size_t CT_LOG_OFF = COL_SZ;
     static constexpr size_t CT_LOG_SZ = CT ? pk_align16((size_t)1 << M) : 0;
     __host__ __device__ static constexpr size_t tables_b(int nk) { return LUT ? tables(nk) : COL_SZ + CT_LOG_SZ; }
-    static constexpr int WB = LUT ? PK_WARPS_B_LUT : PK_WARPS_B;                    // warps per phase-B CTA
+    static constexpr int WB = LUT ? PK_WARPS_B_LUT : CT ? PK_WARPS_B_CT : PK_WARPS_B;   // warps per phase-B CTA
     __host__ __device__ static constexpr size_t total_b(int nk) { return tables_b(nk) + (size_t)WB * W_SZ_B; }
 };
 
@@ -1452,28 +1456,37 @@ struct PkLaunch {
         return pk_alg_decode<M, T>(Sw, mul, xoff, A);
     }
 
-    template <bool LUT, bool GEN, bool CT>
-    static cudaError_t geom_one(int nk, int sm_count, PkLaunchGeom *ga, PkLaunchGeom *gb) {
-        const size_t sa = PkSmem<M, T, LUT, CT>::total_a(nk);
-        cudaError_t e = cudaFuncSetAttribute(k_phase_a<M, T, LUT, GEN, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+    // One shared-memory / L1 split for every Kaneko kernel: kernels of different handles (codes) run concurrently on the
+    // same SMs, and a CTA that becomes resident next to CTAs of a kernel with a larger carveout inherits that carveout
+    // for its whole (persistent) life.  The class-table search needs >= 64 KB of L1 to keep its bitmap gathers in flight
+    // (1.7 ms vs 3.1 ms per launch with 32 KB), so every kernel asks for the 164 KB configuration and sizes its grid for
+    // it; only kernels whose single CTA does not fit take the maximum.
+    template <class K>
+    static cudaError_t fit(K kernel, int threads, size_t dyn, int sm_count, PkLaunchGeom *g) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, kernel);
+        if (e != cudaSuccess) return e;
+        const size_t budget = (size_t)164 << 10, per_cta = dyn + fa.sharedSizeBytes + 1024;
+        const bool fits = per_cta <= budget;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, fits ? 70 : 100);
         if (e != cudaSuccess) return e;
         int per = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_phase_a<M, T, LUT, GEN, CT>, PK_WARPS_A * 32, sa);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, threads, dyn);
         if (e != cudaSuccess) return e;
+        if (fits && per > (int)(budget / per_cta)) per = (int)(budget / per_cta);
         if (per < 1) return cudaErrorLaunchOutOfResources;
-        ga->grid = sm_count * per;      // persistent: every resident slot of every SM
-        ga->block = PK_WARPS_A * 32;
-        ga->smem = sa;
-        const size_t sb = PkSmem<M, T, LUT, CT>::total_b(nk);
-        e = cudaFuncSetAttribute(k_phase_b<M, T, LUT, GEN, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_phase_b<M, T, LUT, GEN, CT>, PkSmem<M, T, LUT, CT>::WB * 32, sb);
-        if (e != cudaSuccess) return e;
-        if (per < 1) return cudaErrorLaunchOutOfResources;
-        gb->grid = sm_count * per;
-        gb->block = PkSmem<M, T, LUT, CT>::WB * 32;
-        gb->smem = sb;
+        g->grid = sm_count * per;      // persistent: every resident slot of every SM
+        g->block = threads;
+        g->smem = dyn;
         return cudaSuccess;
+    }
+    template <bool LUT, bool GEN, bool CT>
+    static cudaError_t geom_one(int nk, int sm_count, PkLaunchGeom *ga, PkLaunchGeom *gb) {
+        cudaError_t e = fit(k_phase_a<M, T, LUT, GEN, CT>, PK_WARPS_A * 32, PkSmem<M, T, LUT, CT>::total_a(nk), sm_count, ga);
+        if (e != cudaSuccess) return e;
+        return fit(k_phase_b<M, T, LUT, GEN, CT>, PkSmem<M, T, LUT, CT>::WB * 32, PkSmem<M, T, LUT, CT>::total_b(nk), sm_count, gb);
     }
     // out[0..1] = replay phase A / B, out[2..3] = generation phase A / B
     static cudaError_t geom_kaneko(int mode, int nk, int sm_count, PkLaunchGeom *out) {

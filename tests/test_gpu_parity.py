@@ -220,3 +220,33 @@ def test_reference_infile_fixture_two_argument(pk):
     assert tr[0] == z["infile_trials2"][0] == 2048
     d, c, s = pk.counters_from_recs(recs, code.n)
     assert c[0] == z["infile_cmp2"][0] and s[0] == z["infile_sum2"][0]
+
+
+def test_async_batches_equal_blocking_calls(pk, oracle_mod):
+    """pk_kaneko_decode_batch_async x N + pk_kaneko_wait == N blocking pk_kaneko_decode_batch calls (results and totals)."""
+    import torch
+
+    code = pk.Code(5, 3, device=0)
+    kan = pk.Kaneko(code)
+    o = oracle_mod.Oracle(5, 3)
+    o.seed(3)
+    ys, refs = [], []
+    for snr in (1.0, 3.0, 5.0):
+        _, _, y = o.gen_frames(snr, 3000)
+        ys.append(y)
+        refs.append(kan.decode(y))
+    hy = [torch.from_numpy(y).pin_memory() for y in ys]
+    hd = [torch.zeros((3000, code.n), dtype=torch.uint8).pin_memory() for _ in ys]
+    ht = [torch.zeros(3000, dtype=torch.int32).pin_memory() for _ in ys]
+    for y, d, t in zip(hy, hd, ht):
+        kan.decode_async_ptr(y.data_ptr(), 3000, d.data_ptr(), t.data_ptr())
+    with pytest.raises(pk.PkError):   # a blocking call may not be mixed into pending asynchronous batches
+        kan.decode(ys[0])
+    tot = kan.wait()
+    for (dec, tr, recs, rt), d, t in zip(refs, hd, ht):
+        assert np.array_equal(d.numpy(), dec) and np.array_equal(t.numpy().astype(np.uint32), tr)
+    for key in ("frames", "trials", "cmp", "sum"):
+        assert tot[key] == sum(r[3][key] for r in refs)
+    assert kan.wait()["frames"] == 0   # nothing pending
+    dec, tr, *_ = kan.decode(ys[1])    # blocking calls work again
+    assert np.array_equal(dec, refs[1][0])
