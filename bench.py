@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-point", type=int, default=1 << 14, help="frames per (code, SNR point) per GPU per step")
+    ap.add_argument("--frames-per-point", type=int, default=1 << 16, help="frames per (code, SNR point) per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=12, help="frames per (code, point) for the single-core CPU baseline")
     ap.add_argument("--ref-frames", type=int, default=3, help="--impl reference: frames per (code, point) per process per step")
     ap.add_argument("--seed", type=int, default=1)
@@ -331,21 +331,22 @@ def run_b200(a):
     # the 0 dB launch (throughput regime, 25 207 trials per frame) against the unit that binds the class-table search:
     # the L1TEX data pipe (one 32-byte bitmap sector per trial from L2 + 5 byte lookups in shared memory per trial).
     # Per-trial wavefront / sector / instruction counts are those of the committed ncu capture of this kernel
-    # (profiles/r1_ncu_summary.md, prof_r1d_ct_m6t6: BCH(63,30,13) J=15 at 0 dB, 16 384 frames).
-    NCU = {"wavefronts_per_trial": 0.867, "l2_sectors_per_trial": 1.02, "warp_inst_per_trial": 1.59,
-           "l1tex_throughput_pct": 88.7, "lts_throughput_pct": 71.4, "dram_bytes_per_launch": 125782528}
+    # (profiles/r1_ncu_summary.md, prof_r1e_ct_m6t6_64k: BCH(63,30,13) J=15 at 0 dB, 65 536 frames).
+    NCU = {"wavefronts_per_trial": 0.876, "l2_sectors_per_trial": 1.013, "warp_inst_per_trial": 1.545,
+           "l1tex_throughput_pct": 94.9, "lts_throughput_pct": 76.2, "dram_bytes_per_launch": 320889344}
     ms0 = share[(dom, 0)]
     trials0 = int(tot_np[dom, 0, 3]) // max(1, world) // a.steps
     tps0 = trials0 / (ms0 * 1e-3)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": NCU["dram_bytes_per_launch"] if (dom_code.n == 63 and B == 16384 and dom_code.table_kind == 2) else None,
+        "traffic": NCU["dram_bytes_per_launch"] if (dom_code.n == 63 and B == 65536 and dom_code.table_kind == 2) else None,
         "algorithmic_bytes_per_launch": bytes_per_frame * B,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
         "kernel": kname, "avg_launch_ms": dom_ms, "share_of_step": by_code[dom] / step_ms,
         "note": ("integer search kernel: neither HBM- nor tensor-bound (SURVEY 8d).  `traffic` is the ncu DRAM traffic of the "
-                 "0 dB launch with a cold L2 (ncu flushes it): frames (9.4 MB) + first touch of the 32 MB class bitmap and "
-                 "32 MB position table, which stay L2-resident between launches.  The binding unit is the L1TEX data pipe "
+                 "0 dB launch (cold L2, ncu flushes it): 37 MB of frames, the first touch of the 32 MB class bitmap and the 32 MB "
+                 "position table, and the ~1 % of bitmap gathers that miss L2 while the frames stream through it -- 53 GB/s, "
+                 "0.8 % of the HBM roof, not a limiter.  The binding unit is the L1TEX data pipe "
                  "(random 32-byte L2 sector gathers + shared-memory byte lookups) -- see l1tex"),
         "l1tex": {
             "launch": "0 dB point of the dominant code", "launch_ms": ms0, "trials_per_s": tps0,
@@ -358,7 +359,7 @@ def run_b200(a):
             "ncu_l1tex_throughput_pct": NCU["l1tex_throughput_pct"], "ncu_lts_throughput_pct": NCU["lts_throughput_pct"],
             "whole_code_trials_per_s": trials_per_s_dom,
             "algorithmic_gf_macs_per_trial": 2 * dom_code.t * 2 + 2 * dom_code.t ** 2 + dom_code.n * dom_code.t,
-            "source": "profiles/r1_ncu_summary.md (prof_r1d_ct_m6t6)",
+            "source": "profiles/r1_ncu_summary.md (prof_r1e_ct_m6t6_64k)",
         },
     }
 
