@@ -183,6 +183,8 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL_DEBUG=VERSION prints a banner on stdout; rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = a.frames_per_point
     # a real (non-default) stream: its handle goes through the C ABI, and every torch op and
