@@ -135,8 +135,8 @@ struct PkSmem {
     // per warp, phase B extras
     static constexpr size_t W_CM = W_SZ_A;                                          // uint32[2T*M] planes / [32] deltas / [32][SW] (CT)
     static constexpr size_t W_CM_SZ = pk_align16((size_t)(LUT ? 32 : CT ? 32 * SW : 2 * T * M) * 4);
-    static constexpr size_t W_PB = W_CM + W_CM_SZ;                                  // uint32[32][NW] one-hot XORs (LUT, CT)
-    static constexpr size_t W_PB_SZ = (LUT || CT) ? pk_align16((size_t)32 * C::NW * 4) : 0;
+    static constexpr size_t W_PB = W_CM + W_CM_SZ;                                  // uint32[32][NW] one-hot XORs of the in-word patterns
+    static constexpr size_t W_PB_SZ = pk_align16((size_t)32 * C::NW * 4);
     static constexpr size_t W_WL = W_PB + W_PB_SZ;                                  // double[32] in-word pattern reliabilities (LUT, CT)
     static constexpr size_t W_WL_SZ = (LUT || CT) ? 256 : 0;
     static constexpr size_t W_Z = W_WL + W_WL_SZ;                                   // uint32[N][33] root words (bit-sliced)
@@ -635,6 +635,20 @@ struct KanekoWarp {
                 }
                 wm.cm[si] = plane;
             }
+            // pb[q][w] = positions flipped by in-word pattern q (known-codeword test of the candidates)
+            uint32_t ph[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) ph[w] = 0;
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const uint32_t pp = __shfl_sync(PK_FULL, f.aug[SW + w], b);
+                    ph[w] ^= ((lane >> b) & 1) ? pp : 0u;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < NW; ++w) wm.pb[lane * NW + w] = ph[w];
         }
         // pattern bits 5..9 = lane index
         uint32_t Ul[NA], Ub[NA];
@@ -665,10 +679,11 @@ struct KanekoWarp {
             }
         }
         __syncwarp();
-        // class-table mode: flip sets of the last codewords this lane looked up and found worse than l0.  Any later
-        // pattern within distance t of one of them decodes to that codeword again (never an improvement: l0 only
-        // decreases), so it needs no table probe.  All-ones = empty (farther than t from every pattern).
-        constexpr int KR = (LUT || CT) ? 2 : 1;
+        // Flip sets of the last codewords found worse than l0 (table modes: by this lane's look-ups; bit-sliced mode: by
+        // the warp's exact evaluations, identical in all lanes).  Any later pattern within distance t of one of them
+        // decodes to that codeword again (never an improvement: l0 only decreases), so it needs no probe / evaluation.
+        // All-ones = empty (farther than t from every pattern).
+        constexpr int KR = 2;
         uint32_t rej[KR][NW];
 #pragma unroll
         for (int k = 0; k < KR; ++k)
@@ -812,7 +827,21 @@ struct KanekoWarp {
                         }
                     }
                 } else {
-                    out = ok;   // bit-sliced mode: every decodable trial is evaluated exactly
+                    // bit-sliced mode: drop the decodable trials that fall back on a known codeword, the rest is
+                    // evaluated exactly
+                    while (ok) {
+                        const int q = __ffs(ok) - 1;
+                        ok &= ok - 1;
+                        int dist = st.have ? 0 : 99, d0 = 0, d1 = 0;
+#pragma unroll
+                        for (int w2 = 0; w2 < NW; ++w2) {
+                            const uint32_t pat = Ul[SW + w2] ^ Ub[SW + w2] ^ wm.pb[q * NW + w2];
+                            dist += __popc(pat ^ st.bestF[w2]);
+                            d0 += __popc(pat ^ rej[0][w2]);
+                            d1 += __popc(pat ^ rej[1][w2]);
+                        }
+                        if (!(dist <= T || d0 <= T || d1 <= T)) out |= 1u << q;
+                    }
                 }
                 return out;
             };
@@ -855,13 +884,28 @@ struct KanekoWarp {
                     cand = pk_bs_decode_mem<M, T>(getS, wm.st + lane, 32, wm.z + lane, SM::ZS) & vmask;
                 else
                     cand = pk_bs_decode<M, T, PK_BS_LOOP>(getS, wm.z + lane, SM::ZS) & vmask;
+                cand = refine(cand, s);
             }
             __syncwarp();
 
             // exact evaluation of candidate (lane src, bit q) against state st: true iff its metric beats st.l0
             auto eval = [&](int src, int q, uint32_t usrc, uint32_t is, const Search &st, uint32_t (&F)[NW], int &m,
                             double &l) -> bool {
-                uint32_t A[NW];
+                uint32_t A[NW], P[NW];
+                const bool sel = (lane < 31) && ((is >> lane) & 1u);
+#pragma unroll
+                for (int w = 0; w < NW; ++w) P[w] = __reduce_xor_sync(PK_FULL, sel ? f.aug[SW + w] : 0u);
+                if constexpr (!LUT && !CT) {
+                    // falls back on a known codeword (the best one or one rejected since the step began)?
+                    int dist = st.have ? 0 : 99, d0 = 0, d1 = 0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        dist += __popc(P[w] ^ st.bestF[w]);
+                        d0 += __popc(P[w] ^ rej[0][w]);
+                        d1 += __popc(P[w] ^ rej[1][w]);
+                    }
+                    if (dist <= T || d0 <= T || d1 <= T) return false;
+                }
                 if constexpr (LUT) {
                     lut_positions(tb.lut[usrc ^ wm.cm[q]], A);
                 } else if constexpr (CT) {
@@ -877,20 +921,28 @@ struct KanekoWarp {
                         A[w] = __ballot_sync(PK_FULL, zb);
                     }
                 }
-                const bool sel = (lane < 31) && ((is >> lane) & 1u);
                 m = 0;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) {
-                    F[w] = __reduce_xor_sync(PK_FULL, sel ? f.aug[SW + w] : 0u) ^ A[w];
+                    F[w] = P[w] ^ A[w];
                     m += __popc(F[w]);
                 }
-                if (!may_improve(wm, m, st.l0)) return false;
                 bool same = st.have;   // same codeword as the current best: l == l0 exactly, no improvement
 #pragma unroll
                 for (int w = 0; w < NW; ++w) same = same && (F[w] == st.bestF[w]);
                 if (same) return false;
-                l = calc_l(wm, F);
-                return l < st.l0;
+                bool better = false;
+                if (may_improve(wm, m, st.l0)) {
+                    l = calc_l(wm, F);
+                    better = l < st.l0;
+                }
+                if constexpr (!LUT && !CT) {
+                    if (!better) {   // remember the rejected codeword (uniform across the warp)
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) { rej[1][w] = rej[0][w]; rej[0][w] = F[w]; }
+                    }
+                }
+                return better;
             };
             if (G > 1 && !(LUT || CT)) {
                 // cooperative search: every warp first thins its own candidates IN PARALLEL against the state
@@ -934,7 +986,7 @@ struct KanekoWarp {
                     if (turn == wi) {
                         if (G > 1 && turn > 0) s = *shared;
                         bool stop = s.early;
-                        if ((LUT || CT) && s.nimpr != nimpr0) cand = refine(cand, s);   // earlier warps of this step lowered l0
+                        if (s.nimpr != nimpr0) cand = refine(cand, s);   // earlier warps of this step lowered l0
                         while (!stop) {
                             const uint32_t lanes_with = __ballot_sync(PK_FULL, cand != 0);
                             if (!lanes_with) break;
@@ -960,7 +1012,7 @@ struct KanekoWarp {
                             }
                             // l0 went down: filter what is left of the step again, all lanes in parallel, instead of
                             // evaluating every stale candidate exactly one by one
-                            if ((LUT || CT) && improved && !stop) cand = refine(cand, s);
+                            if (improved && !stop) cand = refine(cand, s);
                         }
                         if (G > 1 && lane == 0) *shared = s;
                     }
