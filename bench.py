@@ -417,6 +417,37 @@ def run_b200(a):
     except Exception as ex:   # the polar side measurement must never break the headline line
         polar = {"error": str(ex)}
 
+    # ---- side measurement (not part of `value`): the large codes of BASELINE configs[4], J = 15
+    large = None
+    try:
+        large = {}
+        for (m_, t_, label) in ((7, 10, "BCH(127,64,21)"), (8, 15, "BCH(255,139,31)")):
+            c_ = pk.Code(m_, t_, device=local)
+            k_ = pk.Kaneko(c_, J=15, max_trials=1 << 16)   # bounds the pre-first-success search of hopeless frames
+            Bl = 4096
+            yl = torch.empty((Bl, c_.n), dtype=torch.float64, device=dev)
+            dl = torch.zeros((Bl, c_.n), dtype=torch.uint8, device=dev)
+            tl = torch.zeros(Bl, dtype=torch.int32, device=dev)
+            totl = torch.zeros(8, dtype=torch.int64, device=dev)
+            entry = {}
+            for snr_ in (3.0, 4.0, 5.0):
+                k_.generate_frames_dev(snr_, int(round(2 * snr_)), a.seed, 0, Bl, yl.data_ptr(), stream=sp)
+                best = None
+                for _ in range(2):
+                    totl.zero_()
+                    q0 = torch.cuda.Event(enable_timing=True); q1 = torch.cuda.Event(enable_timing=True)
+                    q0.record(stream)
+                    k_.decode_dev(yl.data_ptr(), Bl, dl.data_ptr(), tl.data_ptr(), None, totl.data_ptr(), sp)
+                    q1.record(stream)
+                    torch.cuda.synchronize()
+                    t_ms = q0.elapsed_time(q1)
+                    best = t_ms if best is None else min(best, t_ms)
+                entry[f"{snr_:.0f}dB"] = {"frames_per_s": Bl / best * 1e3, "trials_per_s": int(totl[3].item()) / best * 1e3,
+                                          "trials_per_frame": int(totl[3].item()) / Bl}
+            large[label + " J=15, 4096 frames per launch, searches capped at 65536 trials"] = entry
+    except Exception as ex:
+        large = {"error": str(ex)}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -435,6 +466,7 @@ def run_b200(a):
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "per_code_ms_per_step": {CODES[c][3]: by_code[c] for c in range(len(CODES))},
         "polar_side_measurement": polar,
+        "large_code_side_measurement": large,
     }
     if a.detail:
         for ci in range(len(CODES)):
