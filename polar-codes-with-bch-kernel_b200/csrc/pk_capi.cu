@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -322,6 +323,7 @@ int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_
     d->kp.limit_a = c->use_lut ? 256u : c->use_ct ? 128u : 64u;
     d->mode = c->use_lut ? PK_MODE_LUT : c->use_ct ? PK_MODE_CLASS : PK_MODE_ALG;
     d->kp.big_span = 8192u;
+    d->kp.huge_span = 65536u;
     d->kp.variant = 0;
     d->kp.extra_ops = 0;
     cudaDeviceProp prop;
@@ -392,7 +394,7 @@ int pk_kaneko_launch_geometry(const pk_kaneko *d, int *grid, int *block, long *s
 static int launch_pairs(pk_kaneko *d, int slot, bool gen, PkIo io, long B, cudaStream_t st) {
     const pk_code *c = d->code;
     const bool wide = d->geom4[gen ? 3 : 1].grid > 0;
-    if (wide && !d->d_longs[slot]) PK_CUDA(cudaMalloc(&d->d_longs[slot], (size_t)d->long_cap * sizeof(PkLongRec)));
+    if (wide && !d->d_longs[slot]) PK_CUDA(cudaMalloc(&d->d_longs[slot], (size_t)(d->long_cap + PK_HUGE_CAP) * sizeof(PkLongRec)));
     if (wide && d->mode == PK_MODE_ALG && (c->t + 1) * c->m > 56 && !d->d_zscr[slot]) {
         const int gmax = std::max(d->geom4[1].grid, d->geom4[3].grid);
         PK_CUDA(cudaMalloc(&d->d_zscr[slot], (size_t)gmax * 4 * c->n * 32 * sizeof(uint32_t)));

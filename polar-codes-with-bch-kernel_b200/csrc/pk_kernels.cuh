@@ -1313,8 +1313,16 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
                 long slot = -1;
                 if (lane == 0) {
                     if ((long)atomicAdd(&ctl->n_total, 1ull) < long_cap) {
-                        const bool big = (s.bound > next) && (s.bound - next >= kp.big_span);
-                        slot = big ? long_cap - 1 - (long)atomicAdd(&ctl->n_big, 1ull) : (long)atomicAdd(&ctl->n_long, 1ull);
+                        const uint32_t span = (s.bound > next) ? s.bound - next : 0u;
+                        // "huge" frames (uncapped searches: up to 2^31 patterns) get their own short list behind the
+                        // main one and are always searched by a whole CTA, however many big frames there are
+                        if (s.have && span >= kp.huge_span) {   // (no decision yet: the bound is still the initial one, not a measure of the work left)
+                            const unsigned long long h = atomicAdd(&ctl->n_huge, 1ull);
+                            if (h < (unsigned long long)PK_HUGE_CAP) slot = long_cap + (long)h;
+                        }
+                        if (slot < 0)
+                            slot = (span >= kp.big_span) ? long_cap - 1 - (long)atomicAdd(&ctl->n_big, 1ull)
+                                                         : (long)atomicAdd(&ctl->n_long, 1ull);
                         KW::park(s, (uint32_t)f, next, longs + slot);
                     }
                 }
@@ -1339,7 +1347,8 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
     constexpr int NW = KW::NW;
     extern __shared__ __align__(16) unsigned char smem[];
     const unsigned long long n_long = ctl->n_long, n_big = ctl->n_big;
-    if (n_long + n_big == 0) return;
+    const unsigned long long n_huge = ctl->n_huge < (unsigned long long)PK_HUGE_CAP ? ctl->n_huge : (unsigned long long)PK_HUGE_CAP;
+    if (n_long + n_big + n_huge == 0) return;
     pk_stage_tables<M, T, LUT, CT>(smem, tb, false);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wb = smem + SM::tables_b(tb.nk) + (size_t)warp * SM::W_SZ_B;
@@ -1373,15 +1382,17 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
     // regime of medium / high SNR launches) all of them are.
     // With fewer parked frames than CTAs (high SNR) the launch time is the latency of the longest search:
     // then the small frames are searched by a whole CTA as well.
-    const bool all_coop = (n_long + n_big) <= (unsigned long long)gridDim.x;
+    // The huge frames (own list behind the main one) come first and are always cooperative.
+    const bool all_coop = (n_long + n_big + n_huge) <= (unsigned long long)gridDim.x;
     const unsigned long long n_coop = all_coop ? n_big + n_long : (n_big > 8ull * gridDim.x) ? (unsigned long long)gridDim.x : n_big;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_idx = atomicAdd(&ctl->queue_big, 1ull);
         __syncthreads();
-        const unsigned long long idx = s_idx;
-        if (idx >= n_coop) break;
-        const PkLongRec *rec = (idx < n_big) ? longs + (long_cap - 1 - (long)idx) : longs + (idx - n_big);
+        if (s_idx >= n_huge + n_coop) break;
+        const unsigned long long idx = s_idx - (s_idx < n_huge ? 0ull : n_huge);
+        const PkLongRec *rec = (s_idx < n_huge) ? longs + (long_cap + (long)idx)
+                               : (idx < n_big) ? longs + (long_cap - 1 - (long)idx) : longs + (idx - n_big);
         const long f = (long)rec->frame;
         double yv[NW];
         uint32_t CW[NW];

@@ -15,6 +15,7 @@ struct PkKanekoParams {
     int frames_per_grab;  // frames a warp takes from the queue per atomic
     uint32_t limit_a;     // trials (multiple of 32) a frame may spend in the narrow phase A before it is parked
     uint32_t big_span;    // parked frames with at least this many patterns left are searched by a whole CTA
+    uint32_t huge_span;   // ... and with at least this many go to the separate "huge" list (always cooperative)
     int variant;          // 0: decode(answer, word, res) (:335-407); 1: decode(word, res), the file-mode flavour (:212-276)
     uint32_t extra_ops;   // per-frame constant added to both synthetic counters (2n+1 sort cost of the file-mode flavour, :221-224)
 };
@@ -59,9 +60,12 @@ struct PkPhaseCtl {
     unsigned long long n_total;     // parked frames of both kinds (capacity check)
     unsigned long long queue_big;   // next parked "big" frame (one CTA each)
     unsigned long long n_big;       // parked big frames: longs[cap-1 .. cap-n_big] (filled from the top)
+    unsigned long long n_huge;      // parked huge frames: longs[cap .. cap+n_huge) (may count past PK_HUGE_CAP: the overflow went to the big list)
 };
 
 enum { PK_MODE_ALG = 0, PK_MODE_LUT = 1, PK_MODE_CLASS = 2 };
+
+#define PK_HUGE_CAP 4096   // records behind the main parked-frame list for the huge frames
 
 struct PkLaunchGeom {
     int grid, block;

@@ -250,3 +250,14 @@ def test_async_batches_equal_blocking_calls(pk, oracle_mod):
     assert kan.wait()["frames"] == 0   # nothing pending
     dec, tr, *_ = kan.decode(ys[1])    # blocking calls work again
     assert np.array_equal(dec, refs[1][0])
+
+
+def test_uncapped_search_with_huge_frames(pk, oracle_mod):
+    """Uncapped BCH(31,16,7) at 0 dB: a few frames keep 2^16 .. 2^19 patterns after their last improvement; they travel
+    through the separate "huge" list of the parked frames (always searched by a whole CTA) and still match the oracle."""
+    code = pk.Code(5, 3, device=0)
+    o, info, cw, y, dec, tr, cmp_, sum_ = _oracle_frames(oracle_mod, 5, 3, -1, 0.0, 2500, seed=77)
+    assert (tr >= 65536 + 256).any(), "sample has no huge frame: pick another seed"
+    kan = pk.Kaneko(code)
+    g_dec, g_tr, recs, tot = kan.decode(y)
+    _compare(pk, code, recs, g_dec, g_tr, tot, dec, tr, cmp_, sum_, 2500)
