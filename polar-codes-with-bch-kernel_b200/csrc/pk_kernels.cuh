@@ -294,10 +294,23 @@ struct KanekoWarp {
         __syncwarp();
         // prefix sums of the sorted reliabilities: pref[m] <= l of ANY flip set of weight m (used only to
         // skip exact l computations that cannot beat l0; never decides anything by itself)
-        if (lane == 0) {
-            double acc = 0.0;
-            wm.pref[0] = 0.0;
-            for (int r = 0; r < N; ++r) { acc += wm.skey[r]; wm.pref[r + 1] = acc; }
+        // (a warp scan: the summation order differs from a sequential sum by a few ulp, far inside the 1e-9 margin)
+        {
+            double carry = 0.0;
+            if (lane == 0) wm.pref[0] = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const int r = lane + 32 * w;
+                double v = (r < N) ? wm.skey[r] : 0.0;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const double t = __shfl_up_sync(PK_FULL, v, off);
+                    if (lane >= off) v += t;
+                }
+                v += carry;
+                if (r < N) wm.pref[r + 1] = v;
+                carry = __shfl_sync(PK_FULL, v, 31);
+            }
         }
         // syndrome of yH (Decoder::findSyndromPoly, Decoder.cpp:184-207): XOR of columns
         {
