@@ -254,38 +254,71 @@ struct KanekoWarp {
         // (== std::sort for n <= 16, where libstdc++ runs a plain, stable insertion sort).  For n > 16 a frame
         // with equal keys is re-sorted by a literal replay of libstdc++'s introsort (pk_stdsort.cuh).
         {
+            // fast pass: rank = number of strictly smaller keys (one fp64 compare per pair: the keys are non-negative
+            // doubles, so the fp order is the order of the bit patterns).  Equal keys collide on a rank -- the loser
+            // finds somebody else's index in its slot -- and send the frame to the exact pass below.
             int rank[NW];
-            bool tie = false;
 #pragma unroll
             for (int w = 0; w < NW; ++w) rank[w] = 0;
-            const unsigned long long *ak = reinterpret_cast<const unsigned long long *>(wm.alpha);
-#pragma unroll 4
-            for (int q = 0; q < N; ++q) {
-                const unsigned long long kq = ak[q];
+            double keyd[NW];
 #pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    const int p = lane + 32 * w;
-                    const bool eq = (kq == keyb[w]);
-                    rank[w] += (kq < keyb[w] || (eq && q < p)) ? 1 : 0;
-                    tie |= eq && (q != p) && (p < N);
-                }
+            for (int w = 0; w < NW; ++w) keyd[w] = __longlong_as_double((long long)keyb[w]);
+#pragma unroll 8
+            for (int q = 0; q < N; ++q) {
+                const double kq = wm.alpha[q];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) rank[w] += (kq < keyd[w]) ? 1 : 0;
             }
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const int p = lane + 32 * w;
                 if (p < N) {
-                    wm.skey[rank[w]] = __longlong_as_double((long long)keyb[w]);
+                    wm.skey[rank[w]] = keyd[w];
                     wm.sidx[rank[w]] = (uint8_t)p;
                 }
             }
-            if (__any_sync(PK_FULL, tie)) {
-                f.flags |= PK_FLAG_SORT_TIE;
-                if (N > 16) {
-                    // equal keys: std::sort's order is an artefact of libstdc++'s introsort -- replay it on one lane
-                    __syncwarp();
-                    if (lane == 0) {
-                        for (int i = 0; i < N; ++i) { wm.skey[i] = wm.alpha[i]; wm.sidx[i] = (uint8_t)i; }
-                        pk_stdsort::sort(wm.skey, wm.sidx, N);
+            __syncwarp();
+            bool clash = false;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const int p = lane + 32 * w;
+                if (p < N) clash |= (wm.sidx[rank[w]] != (uint8_t)p);
+            }
+            if (__any_sync(PK_FULL, clash)) {
+                // exact pass: integer compares of the bit patterns, ties broken by position
+                __syncwarp();
+                bool tie = false;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) rank[w] = 0;
+                const unsigned long long *ak = reinterpret_cast<const unsigned long long *>(wm.alpha);
+#pragma unroll 4
+                for (int q = 0; q < N; ++q) {
+                    const unsigned long long kq = ak[q];
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        const int p = lane + 32 * w;
+                        const bool eq = (kq == keyb[w]);
+                        rank[w] += (kq < keyb[w] || (eq && q < p)) ? 1 : 0;
+                        tie |= eq && (q != p) && (p < N);
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const int p = lane + 32 * w;
+                    if (p < N) {
+                        wm.skey[rank[w]] = keyd[w];
+                        wm.sidx[rank[w]] = (uint8_t)p;
+                    }
+                }
+                if (__any_sync(PK_FULL, tie)) {
+                    f.flags |= PK_FLAG_SORT_TIE;
+                    if (N > 16) {
+                        // equal keys: std::sort's order is an artefact of libstdc++'s introsort -- replay it on one lane
+                        __syncwarp();
+                        if (lane == 0) {
+                            for (int i = 0; i < N; ++i) { wm.skey[i] = wm.alpha[i]; wm.sidx[i] = (uint8_t)i; }
+                            pk_stdsort::sort(wm.skey, wm.sidx, N);
+                        }
                     }
                 }
             }
