@@ -327,7 +327,7 @@ def run_b200(a):
     dom_trials = int(tot_np[dom, :, 3].sum()) // max(1, world)
     mode = {0: "bit-sliced BM+Chien", 1: "coset table", 2: "cyclic-class table"}[dom_code.table_kind]
     kname = (f"k_phase_a + k_phase_b<{dom_code.m},{dom_code.t},{mode}> "
-             "(one launch pair per SNR point; phase B is ~85 % of this code's kernel time, profiles/r1_launches.md)")
+             "(one launch pair per SNR point; phase B is ~92 % of this code's kernel time, profiles/r1_launches.md)")
     sm_hz = (clocks["sm_mhz"] or 1965.0) * 1e6
     trials_per_s_dom = dom_trials / (by_code[dom] * a.steps * 1e-3)
     # the 0 dB launch (throughput regime, 25 207 trials per frame) against the unit that binds the class-table search:
