@@ -183,9 +183,19 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL_DEBUG=VERSION prints a banner on stdout; rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created (NCCL_DEBUG >= VERSION);
+        # rank 0 must print ONE JSON line, so stdout points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     B = a.frames_per_point
     # a real (non-default) stream: its handle goes through the C ABI, and every torch op and
     # CUDA event below is issued on the same stream the kernels are launched on
