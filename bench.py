@@ -4,13 +4,14 @@
 Workload (BASELINE.json configs[1]): BCH(31,16,7) with the HEAD (uncapped) test-pattern rule
 and BCH(63,30,13) with the J=15 cap, every Eb/N0 point of the reference grid 0..5 dB step 0.5,
 the same number of frames per point and code.  One "step" = one pass of the decoder over that
-whole batch (2 codes x 11 points = 22 kernel launches).  Inputs are channel outputs y (f64)
+whole batch (2 codes x 11 points = 22 launch pairs: narrow phase A + wide phase B, 65 536 frames each).  Inputs are channel outputs y (f64)
 drawn once by the device-side Philox generator.
 
   value  : frames/s with y resident in HBM, timed with CUDA events on the launching stream
-  e2e    : frames/s through pk_kaneko_decode_batch (the C-ABI call a reference-side binding
-           makes) with pinned HOST buffers: H2D of y and D2H of decisions + trial counts inside
-           the timed region
+  e2e    : frames/s through the C-ABI batch call a reference-side binding makes, with pinned HOST
+           buffers: H2D of y and D2H of decisions + trial counts inside the timed region
+           (pk_kaneko_decode_batch_async per batch + pk_kaneko_wait per step; the blocking
+           pk_kaneko_decode_batch number is reported next to it as e2e.sync_call_value)
   --impl reference : the compiled reference (oracle/_ref) on all host cores, same codes/grid
 
 Multi-GPU: frames are independent, so each rank decodes its own frames (weak scaling); the
