@@ -40,8 +40,10 @@
 #ifndef PK_WARPS_B_CT
 #define PK_WARPS_B_CT 4     // warps per CTA, phase B, class-table mode (8: no faster in bulk, slower tails at mid SNR)
 #endif
+#ifndef PK_WARPS_B_LUT
 #define PK_WARPS_B_LUT 16   // warps per CTA, phase B, coset-table mode: a whole CTA searches one long frame, 16K patterns per step
                             // (the uncapped searches of these codes end in a few monster frames: latency matters)
+#endif
 #ifndef PK_BS_LOOP
 #define PK_BS_LOOP true     // bit-sliced BM as one loop body (instruction-cache friendly)
 #endif
