@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-point", type=int, default=1 << 16, help="frames per (code, SNR point) per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=12, help="frames per (code, point) for the single-core CPU baseline")
-    ap.add_argument("--ref-frames", type=int, default=3, help="--impl reference: frames per (code, point) per process per step")
+    ap.add_argument("--ref-frames", type=int, default=16, help="--impl reference: frames per (code, point) per process per step")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--detail", action="store_true", help="print per-code / per-SNR numbers to stderr")
     return ap.parse_args()
