@@ -341,12 +341,13 @@ def run_b200(a):
              "(one launch pair per SNR point; phase B is ~92 % of this code's kernel time, profiles/r1_launches.md)")
     sm_hz = (clocks["sm_mhz"] or 1965.0) * 1e6
     trials_per_s_dom = dom_trials / (by_code[dom] * a.steps * 1e-3)
-    # the 0 dB launch (throughput regime, 25 207 trials per frame) against the unit that binds the class-table search:
-    # the L1TEX data pipe (one 32-byte bitmap sector per trial from L2 + 5 byte lookups in shared memory per trial).
-    # Per-trial wavefront / sector / instruction counts are those of the committed ncu capture of this kernel
-    # (profiles/r1_ncu_summary.md, prof_r1e_ct_m6t6_64k: BCH(63,30,13) J=15 at 0 dB, 65 536 frames).
-    NCU = {"wavefronts_per_trial": 0.876, "l2_sectors_per_trial": 1.013, "warp_inst_per_trial": 1.545,
-           "l1tex_throughput_pct": 94.9, "lts_throughput_pct": 76.2, "dram_bytes_per_launch": 320889344}
+    # the 0 dB launch (throughput regime, 25 000 trials per frame) against the unit that binds the class-table search:
+    # the L1TEX -> XBAR request port, ONE L2 sector request per SM per clock (every trial gathers one random 32-byte
+    # sector of the 32 MB class bitmap from L2; 32 lanes = 32 requests).  Per-trial counts are those of the committed
+    # ncu capture of this kernel (profiles/r1_ncu_summary.md, prof_r1g_ct_tex: BCH(63,30,13) J=15 at 0 dB, 65 536 frames).
+    NCU = {"l2_sectors_per_trial": 1.0124, "warp_inst_per_trial": 1.495, "xbar_req_cycles_active_pct": 96.2,
+           "l1tex_throughput_pct": 96.2, "lts_throughput_pct": 77.4, "tex_data_pipe_pct": 57.2, "lsu_data_pipe_pct": 36.5,
+           "dram_bytes_per_launch": 320465664}
     ms0 = share[(dom, 0)]
     trials0 = int(tot_np[dom, 0, 3]) // max(1, world) // a.steps
     tps0 = trials0 / (ms0 * 1e-3)
@@ -359,20 +360,21 @@ def run_b200(a):
         "note": ("integer search kernel: neither HBM- nor tensor-bound (SURVEY 8d).  `traffic` is the ncu DRAM traffic of the "
                  "0 dB launch (cold L2, ncu flushes it): 37 MB of frames, the first touch of the 32 MB class bitmap and the 32 MB "
                  "position table, and the ~1 % of bitmap gathers that miss L2 while the frames stream through it -- 53 GB/s, "
-                 "0.8 % of the HBM roof, not a limiter.  The binding unit is the L1TEX data pipe "
-                 "(random 32-byte L2 sector gathers + shared-memory byte lookups) -- see l1tex"),
-        "l1tex": {
+                 "0.8 % of the HBM roof, not a limiter.  The binding unit is the L1TEX -> XBAR request port (one L2 sector "
+                 "request per SM per clock) -- see l2_request_port"),
+        "l2_request_port": {
             "launch": "0 dB point of the dominant code", "launch_ms": ms0, "trials_per_s": tps0,
-            "wavefronts_per_trial_ncu": NCU["wavefronts_per_trial"],
-            "achieved_wavefronts_per_s": tps0 * NCU["wavefronts_per_trial"],
-            "peak_wavefronts_per_s": 148 * sm_hz,   # one L1TEX data-pipe wavefront per SM per clock
-            "frac": tps0 * NCU["wavefronts_per_trial"] / (148 * sm_hz),
             "l2_sectors_per_trial_ncu": NCU["l2_sectors_per_trial"],
-            "warp_inst_per_trial_ncu": NCU["warp_inst_per_trial"],
+            "achieved_sector_requests_per_s": tps0 * NCU["l2_sectors_per_trial"],
+            "peak_sector_requests_per_s": 148 * sm_hz,   # one request per SM per clock
+            "frac": tps0 * NCU["l2_sectors_per_trial"] / (148 * sm_hz),
+            "ncu_l1tex2xbar_req_cycles_active_pct": NCU["xbar_req_cycles_active_pct"],
             "ncu_l1tex_throughput_pct": NCU["l1tex_throughput_pct"], "ncu_lts_throughput_pct": NCU["lts_throughput_pct"],
+            "ncu_tex_data_pipe_pct": NCU["tex_data_pipe_pct"], "ncu_lsu_data_pipe_pct": NCU["lsu_data_pipe_pct"],
+            "warp_inst_per_trial_ncu": NCU["warp_inst_per_trial"],
             "whole_code_trials_per_s": trials_per_s_dom,
             "algorithmic_gf_macs_per_trial": 2 * dom_code.t * 2 + 2 * dom_code.t ** 2 + dom_code.n * dom_code.t,
-            "source": "profiles/r1_ncu_summary.md (prof_r1e_ct_m6t6_64k)",
+            "source": "profiles/r1_ncu_summary.md (prof_r1g_ct_tex)",
         },
     }
 

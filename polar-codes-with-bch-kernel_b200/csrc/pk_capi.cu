@@ -131,6 +131,22 @@ int pk_code_create(int m, int t, int device, pk_code **out) {
             pk_code_destroy(c);
             return rc;
         }
+        {
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = const_cast<uint32_t *>(c->dev.ct_bits);
+            rd.res.linear.desc = cudaCreateChannelDesc<unsigned int>();
+            rd.res.linear.sizeInBytes = ct.bits.size() * sizeof(uint32_t);
+            cudaTextureDesc td{};
+            td.readMode = cudaReadModeElementType;
+            cudaTextureObject_t tex = 0;
+            cudaError_t te = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+            if (te != cudaSuccess) {
+                pk_code_destroy(c);
+                return fail(PK_ERR_CUDA, std::string("cudaCreateTextureObject: ") + cudaGetErrorString(te));
+            }
+            c->dev.ct_tex = (unsigned long long)tex;
+        }
         c->dev.ct_hshift = 32u - (uint32_t)ct.hbits;
         c->dev.ct_hmask = (1u << ct.hbits) - 1u;
         for (size_t i = 0; i < 8; ++i) c->dev.ct_mult[i] = i < ct.mult.size() ? ct.mult[i] : 0u;
@@ -162,6 +178,7 @@ void pk_code_destroy(pk_code *c) {
     if (!c) return;
     if (c->device >= 0) {
         cudaSetDevice(c->device);
+        if (c->dev.ct_tex) cudaDestroyTextureObject((cudaTextureObject_t)c->dev.ct_tex);
         for (void *p : c->dev_allocs) cudaFree(p);
     }
     delete c;

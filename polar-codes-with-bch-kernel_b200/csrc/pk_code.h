@@ -25,6 +25,7 @@ struct PkDevTables {
     const uint32_t *ct_bits;            // [2^(kb+1) / 32] decodable-class bitmap
     const unsigned long long *ct_hash;  // [2^hbits] key << (t m) | t packed positions
     uint32_t ct_hshift, ct_hmask;       // slot = (key * 0x9E3779B1) >> hshift, linear probing under hmask
+    unsigned long long ct_tex;          // cudaTextureObject_t over ct_bits (u32 texels): the bitmap gathers of the wide search go through the TEX path
     uint32_t ct_mult[8];                // 1 << (field offset in the key) per independent syndrome
 };
 
