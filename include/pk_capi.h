@@ -140,8 +140,10 @@ int pk_kaneko_decode_batch_async(pk_kaneko *dec, const double *y /*[B][n]*/, lon
 int pk_kaneko_wait(pk_kaneko *dec, pk_point_result *totals /*or NULL*/);
 
 /* Replay mode, device-resident buffers, asynchronous on `stream` (a cudaStream_t, NULL =
- * the handle's own stream).  d_totals (8 x u64, pk_point_result layout) is ACCUMULATED
- * into, the caller zeroes it. */
+ * the handle's own NON-BLOCKING stream: work the caller queued elsewhere -- e.g. the fill that
+ * zeroes d_totals -- is not ordered before it, synchronise first or pass your stream).
+ * d_totals (8 x u64, pk_point_result layout) is ACCUMULATED into, the caller zeroes it.
+ * One launch in flight per handle on caller streams (they share one control block). */
 int pk_kaneko_decode_batch_dev(pk_kaneko *dec, const double *d_y, long B, uint8_t *d_decided,
                                uint32_t *d_trials /*or NULL*/, pk_frame_rec *d_recs /*or NULL*/,
                                uint64_t *d_totals /*or NULL*/, void *stream);

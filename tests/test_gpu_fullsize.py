@@ -66,3 +66,33 @@ def test_empty_and_single_frame_batches(pk):
     dec, tr, recs, tot = kan.decode(y)
     assert not dec.any() and tot["frames"] == 1 and tr[0] >= 1
     assert code.encode(np.zeros((0, 5), np.uint8)).shape == (0, 15)
+
+
+@pytest.mark.parametrize("m,t,J,snr,frames", [(6, 6, 15, 0.5, 65_536), (6, 6, 15, 3.0, 262_144), (6, 4, 12, 1.0, 131_072), (5, 5, 12, 1.0, 131_072),
+                                               (5, 3, -1, 1.0, 262_144)])
+def test_table_search_equals_algebraic_search_at_bench_size(pk, m, t, J, snr, frames):
+    """Two independent device implementations of the algebraic decoder inside the same search -- lookup tables
+    (cyclic-class table / coset table) vs Berlekamp-Massey + Chien (table-driven in the narrow phase, bit-sliced in the
+    wide phase) -- give identical decisions, trial counts and counters on a bench-size batch (1.6e9 trials for the first case)."""
+    import torch
+
+    out = []
+    for tables in (True, False):
+        code = pk.Code(m, t, device=0)
+        assert code.uses_lut
+        code.set_lut(tables)
+        kan = pk.Kaneko(code, J=J)
+        y = torch.empty((frames, code.n), dtype=torch.float64, device="cuda")
+        kan.generate_frames_dev(snr, int(round(2 * snr)), 9, 0, frames, y.data_ptr())
+        dec = torch.zeros((frames, code.n), dtype=torch.uint8, device="cuda")
+        tr = torch.zeros(frames, dtype=torch.int32, device="cuda")
+        tot = torch.zeros(8, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()   # the handle launches on its own stream: torch's fills must have landed
+        kan.decode_dev(y.data_ptr(), frames, dec.data_ptr(), tr.data_ptr(), None, tot.data_ptr())
+        torch.cuda.synchronize()
+        out.append((dec.cpu(), tr.cpu(), tot.cpu()))
+        del kan, code
+    assert torch.equal(out[0][1], out[1][1]), "trial counts differ"
+    assert torch.equal(out[0][0], out[1][0]), "decisions differ"
+    assert torch.equal(out[0][2][:6], out[1][2][:6]), "totals differ"
+    assert int(out[0][2][0]) == frames
