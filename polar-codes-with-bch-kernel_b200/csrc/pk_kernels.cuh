@@ -1020,23 +1020,26 @@ struct KanekoWarp {
                 cand = keep;
             }
             // ---- candidates in pattern order (for G > 1: warp 0's block first, then warp 1's, ...)
-            bool handover = true;
+            uint32_t turns = 1u;   // bit g: warp g has candidates and takes a turn in the ordered hand-over
             if (G > 1) {
                 // most steps leave no candidate in any warp: one barrier settles that and the state is unchanged
                 volatile uint32_t *fl = votes + (((gbase >> 10) / G) & 1u) * G;   // double-buffered by step parity
                 const uint32_t mine = __ballot_sync(PK_FULL, cand != 0);
                 if (lane == 0) fl[wi] = mine ? 1u : 0u;
                 __syncthreads();
-                uint32_t anyc = 0;
+                turns = 0;
 #pragma unroll
-                for (int g = 0; g < G; ++g) anyc |= fl[g];
-                handover = anyc != 0;
+                for (int g = 0; g < G; ++g) turns |= (fl[g] ? 1u : 0u) << g;
             }
-            if (handover) {
+            if (turns) {
+                // only the warps that have candidates take a turn (one barrier each): late in a long search that is
+                // one warp in sixteen
+                bool first = true;
 #pragma unroll 1
-                for (int turn = 0; turn < G; ++turn) {
+                for (uint32_t mk = turns; mk; mk &= mk - 1) {
+                    const int turn = __ffs(mk) - 1;
                     if (turn == wi) {
-                        if (G > 1 && turn > 0) s = *shared;
+                        if (G > 1 && !first) s = *shared;
                         bool stop = s.early;
                         if (s.nimpr != nimpr0) cand = refine(cand, s);   // earlier warps of this step lowered l0
                         while (!stop) {
@@ -1068,6 +1071,7 @@ struct KanekoWarp {
                         }
                         if (G > 1 && lane == 0) *shared = s;
                     }
+                    first = false;
                     if (G > 1) __syncthreads();
                 }
                 if (G > 1) {
