@@ -143,7 +143,8 @@ int pk_kaneko_wait(pk_kaneko *dec, pk_point_result *totals /*or NULL*/);
  * the handle's own NON-BLOCKING stream: work the caller queued elsewhere -- e.g. the fill that
  * zeroes d_totals -- is not ordered before it, synchronise first or pass your stream).
  * d_totals (8 x u64, pk_point_result layout) is ACCUMULATED into, the caller zeroes it.
- * One launch in flight per handle on caller streams (they share one control block). */
+ * ANY non-NULL `stream` -- including one of the handle's own -- uses the one control block / parked-frame list
+ * reserved for caller streams: at most one launch in flight per handle across all caller streams. */
 int pk_kaneko_decode_batch_dev(pk_kaneko *dec, const double *d_y, long B, uint8_t *d_decided,
                                uint32_t *d_trials /*or NULL*/, pk_frame_rec *d_recs /*or NULL*/,
                                uint64_t *d_totals /*or NULL*/, void *stream);
@@ -171,11 +172,10 @@ int pk_generate_frames(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t s
 int pk_generate_frames_dev(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame,
                            long nframes, uint8_t *d_info, uint8_t *d_cw, double *d_y, void *stream);
 
-/* One whole SNR point with fun()'s stop rule `count < p && countErr < e`
- * (dataForPlot.cpp:43), evaluated in frame order on the per-frame records so the result
- * equals a sequential run over the same Philox frames.  Frames [rank, world) are
- * interleaved in blocks of `chunk`; the caller reduces *out across ranks when world > 1
- * and e is unlimited (e <= 0).  With world == 1 the stop rule is exact. */
+/* One whole SNR point on ONE device with fun()'s stop rule `count < p && countErr < e` (dataForPlot.cpp:43): frames
+ * 0, 1, 2, .. of the Philox stream are decoded in growing chunks and the per-frame records are scanned in frame order,
+ * so the totals equal a sequential run over the same frames (e <= 0: exactly p frames, no records needed).  Sharding a
+ * point over several GPUs is pk_comm_run_point (below) or, per process, pk_kaneko_run_frames on a frame sub-range. */
 int pk_kaneko_run_point(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t seed, long p, long e,
                         pk_point_result *out);
 

@@ -12,7 +12,7 @@
 // Horner Chien search whose multiplier row is warp-uniform (bank-conflict free).
 //
 // Exhaustive (n-k <= 15) and randomised differential tests against the compiled
-// reference are in tests/test_bch_decode.py.
+// reference are in tests/test_gpu_parity.py (test_bch_decode_matches_oracle, test_bch_decode_exhaustive_cosets) and tests/test_capi_host.py.
 #pragma once
 #include <stdint.h>
 

@@ -509,6 +509,22 @@ static int enqueue_batch(pk_kaneko *d, const double *y, long B, uint8_t *decided
     return PK_OK;
 }
 
+// An enqueue failed part-way (e.g. a workspace allocation): kernels and D2H copies already queued still write into
+// the caller's buffers, so nothing may return before both streams are idle.  The error message survives.
+static void drain_after_error(pk_kaneko *d) {
+    const std::string keep = g_err;
+    cudaStreamSynchronize(d->stream[0]);
+    cudaStreamSynchronize(d->stream[1]);
+    d->pending = false;
+    g_err = keep;
+}
+// The generation-mode entry points zero / read the handle's totals on stream[0]: not while asynchronous batches
+// (pk_kaneko_decode_batch_async) are outstanding.
+static int reject_pending(const pk_kaneko *d) {
+    if (d->pending) return fail(PK_ERR_ARG, "asynchronous batches are pending on this handle: call pk_kaneko_wait first");
+    return PK_OK;
+}
+
 int pk_kaneko_wait(pk_kaneko *d, pk_point_result *totals) {
     if (!d) return fail(PK_ERR_ARG, "NULL handle");
     if (totals) std::memset(totals, 0, sizeof(*totals));
@@ -528,7 +544,9 @@ int pk_kaneko_decode_batch_async(pk_kaneko *d, const double *y, long B, uint8_t 
     if (!d || B < 0 || (B && (!y || !decided))) return fail(PK_ERR_ARG, "bad arguments");
     if (!B) return PK_OK;
     PK_CUDA(cudaSetDevice(d->code->device));
-    return enqueue_batch(d, y, B, decided, trials, recs);
+    int rc = enqueue_batch(d, y, B, decided, trials, recs);
+    if (rc) drain_after_error(d);
+    return rc;
 }
 
 int pk_kaneko_decode_batch(pk_kaneko *d, const double *y, long B, uint8_t *decided, uint32_t *trials,
@@ -539,7 +557,7 @@ int pk_kaneko_decode_batch(pk_kaneko *d, const double *y, long B, uint8_t *decid
     if (!B) return PK_OK;
     PK_CUDA(cudaSetDevice(d->code->device));
     int rc = enqueue_batch(d, y, B, decided, trials, recs);
-    if (rc) { d->pending = false; return rc; }
+    if (rc) { drain_after_error(d); return rc; }
     return pk_kaneko_wait(d, totals);
 }
 
@@ -577,6 +595,7 @@ static int ensure_grec(pk_kaneko *d, long cap) {
 int pk_kaneko_run_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame,
                          long nframes, pk_frame_rec *recs, pk_point_result *totals) {
     if (!d || nframes < 0 || !totals) return fail(PK_ERR_ARG, "bad arguments");
+    if (int rp = reject_pending(d)) return rp;
     if (!nframes) return PK_OK;
     PK_CUDA(cudaSetDevice(d->code->device));
     cudaStream_t st = d->stream[0];
@@ -624,6 +643,7 @@ int pk_generate_frames_dev(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t
 int pk_generate_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
                        uint8_t *info, uint8_t *cw, double *y) {
     if (!d || nframes < 0) return fail(PK_ERR_ARG, "bad arguments");
+    if (int rp = reject_pending(d)) return rp;
     if (!nframes) return PK_OK;
     const pk_code *c = d->code;
     PK_CUDA(cudaSetDevice(c->device));
@@ -658,6 +678,7 @@ int pk_generate_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t see
 int pk_kaneko_run_point(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t seed, long p, long e,
                         pk_point_result *out) {
     if (!d || !out || p <= 0) return fail(PK_ERR_ARG, "Invalid values of arguments");
+    if (int rp = reject_pending(d)) return rp;
     std::memset(out, 0, sizeof(*out));
     if (e <= 0) return pk_kaneko_run_frames(d, ebn0_db, snr_index, seed, 0, p, nullptr, out);
     const int n = d->code->n;

@@ -580,7 +580,9 @@ struct KanekoWarp {
             } else {
                 succ = pk_alg_decode<M, T>(Sx, tb.mul, tb.xoff, A);
             }
-            succ = succ && (i < s.bound);
+            // `succ` is the decoder's verdict alone: whether trial i is inside the loop bound is tested against the LIVE
+            // bound at every ballot below, because an improvement may also RAISE the bound (a larger m shrinks calcT's
+            // border sum), which admits patterns of this step that the bound at step start excluded.
             // m = d_H(yH, x) (calcM :89-97), l = sum_{yH != x} alpha in index order (calcL :69-77)
             int m = 0;
 #pragma unroll
@@ -595,7 +597,7 @@ struct KanekoWarp {
             // in-order commit of improvements (:372-399)
             bool impr_here = false;
             uint32_t last_is = 0;
-            uint32_t cand = __ballot_sync(PK_FULL, succ && (l < s.l0));
+            uint32_t cand = __ballot_sync(PK_FULL, succ && (i < s.bound) && (l < s.l0));
             while (cand) {
                 const int src = __ffs(cand) - 1;
                 const double ls = __shfl_sync(PK_FULL, l, src);
@@ -739,16 +741,21 @@ struct KanekoWarp {
 #pragma unroll
             for (int w = 0; w < NW; ++w) rej[k][w] = PK_FULL;
 
-        for (uint32_t base = base0;; base += 1024u * G) {
+        // lo: patterns of the current step below it are not to be run -- `start` in the first step (phase A ran them), and
+        // on a RE-RUN of a step the bound the step was first masked with (see the end of the loop body)
+        uint32_t lo = start;
+        bool rerun = false;
+        for (uint32_t base = base0;;) {
             const uint32_t gbase = base - 1024u * (uint32_t)wi;   // first pattern of this group step
             if (gbase >= kp.max_trials) { s.trials = gbase; s.flags |= PK_FLAG_TRUNCATED; return; }
-            s.step_last = 0;
+            if (!rerun) s.step_last = 0;
+            const uint32_t bound0 = s.bound;   // the bound this pass masks its patterns with (identical in all G warps)
             uint32_t u[SW];
 #pragma unroll
             for (int q = 0; q < SW; ++q) u[q] = f.S0[q] ^ Ul[q] ^ Ub[q];
             const uint32_t lane_first = base + 32u * lane;
             uint32_t vmask = (s.bound <= lane_first) ? 0u : ((s.bound - lane_first >= 32u) ? PK_FULL : ((1u << (s.bound - lane_first)) - 1u));
-            if (lane_first < start) vmask = 0u;   // patterns below `start` were run by phase A (start is a multiple of 32)
+            if (lo > lane_first) vmask &= (lo - lane_first >= 32u) ? 0u : (PK_FULL << (lo - lane_first));
             uint32_t cand = 0;   // bit q: trial lane_first + q succeeded (and, LUT / CT: its metric may still beat l0)
             double bsum = 0.0;   // reliabilities flipped by pattern bits 10.. (base part)
             if constexpr (LUT || CT) {
@@ -895,8 +902,8 @@ struct KanekoWarp {
                 return out;
             };
             const uint32_t nimpr0 = s.nimpr;
-            if (base >= s.bound || base + 1024u <= start) {
-                // nothing to run in this block (G > 1: blocks past the bound; first step: blocks below `start`)
+            if (base >= s.bound || base + 1024u <= lo) {
+                // nothing to run in this block (G > 1: blocks past the bound; first step / re-run: blocks below `lo`)
             } else if constexpr (LUT) {
                 uint32_t ok = 0;
 #pragma unroll 8
@@ -1080,11 +1087,22 @@ struct KanekoWarp {
                 }
             }
             if (s.early) return;
+            // An improvement may RAISE the bound (T = j can grow when a larger m shrinks calcT's border sum).  If the bound
+            // this pass was masked with ended inside the step, the patterns [bound0, min(new bound, end of step)) have not
+            // been looked at yet although the sequential loop runs them: re-run the step for exactly those.
+            if (s.bound > bound0 && bound0 < gbase + 1024u * G) {
+                lo = bound0;
+                rerun = true;
+                __syncwarp();
+                continue;
+            }
             if (s.bound <= gbase + 1024u * G) {
                 s.trials = s.bound;
                 if (s.step_last > s.trials) s.trials = s.step_last;
                 return;
             }
+            lo = 0;
+            rerun = false;
             {   // next base: bits 10.. change
                 uint32_t diff = ((base + 1024u * G) ^ base) >> 10;
                 while (diff) {
@@ -1094,6 +1112,7 @@ struct KanekoWarp {
                     for (int a = 0; a < NA; ++a) Ub[a] ^= __shfl_sync(PK_FULL, f.aug[a], 10 + b);
                 }
             }
+            base += 1024u * G;
             __syncwarp();
         }
     }

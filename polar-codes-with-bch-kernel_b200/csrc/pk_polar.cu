@@ -625,7 +625,16 @@ int pk_polar_create(const char *spec_text, int L, int device, pk_polar **out) {
         const size_t frame_sz = ((sizeof(ListCtl) + 15) & ~(size_t)15) + (size_t)d.N0 * 4 + (size_t)L * path_sz;
         h->fpc = std::max(1, 8 / L);   // at least 8 warps per CTA share the staged trellis tables
         h->smem_decode = polar_table_bytes(d) + (size_t)h->fpc * frame_sz + (size_t)h->fpc * L * polar_met_floats(d.max_ab) * 4;
-        e = cudaFuncSetAttribute(k_polar_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_decode);
+        int smem_max = 0;
+        e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        if (e == cudaSuccess && h->smem_decode > (size_t)smem_max) {
+            for (void *p : h->allocs) cudaFree(p);
+            cudaStreamDestroy(h->stream);
+            const std::string msg = "polar decoder needs " + std::to_string(h->smem_decode) + " bytes of shared memory per CTA (list size x code length x trellis states), the device offers " + std::to_string(smem_max);
+            delete h;
+            return pk_set_error(PK_ERR_UNSUPPORTED, msg);
+        }
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_polar_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_decode);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_polar_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2 * d.N0);
     }
     if (e != cudaSuccess) {

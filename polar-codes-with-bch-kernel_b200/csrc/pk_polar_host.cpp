@@ -85,7 +85,9 @@ std::string pk_polar_build_trellis(PkKernelTrellis &k) {
             for (int r : cur)
                 if (r != ending) next.push_back(r);
             const int nb_cur = (int)cur.size(), nb_next = (int)next.size();
-            if (nb_next > 15) return "Kernel trellis has too many states";
+            // a predecessor half is (state | branch bit << 15) with 0xFFFF = "no branch": 15 state bits would let state
+            // 0x7FFF with branch bit 1 collide with that marker, and the decoder's DUMMY state 1 << max_ab with bit 15
+            if (nb_next > 14) return "Kernel trellis has too many states";
             k.off[(size_t)p * l + j] = (uint32_t)k.pred.size();
             k.pred.resize(k.pred.size() + ((size_t)1 << nb_next), 0xFFFFFFFFu);
             uint32_t *tab = &k.pred[k.off[(size_t)p * l + j]];

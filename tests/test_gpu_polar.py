@@ -79,3 +79,42 @@ def test_against_committed_golden_vectors(pk):
         assert np.array_equal(cnt, z[k + "_count"])
         assert np.array_equal(met.view(np.uint32), z[k + "_metric"].view(np.uint32))
         assert np.array_equal(np.packbits(inf, axis=2), z[k + "_inf"])
+
+
+# ---- the dynamic-frozen and the shortened + punctured specifications (tests/golden/make_polar_specs.py)
+SPECS2 = [("dyn", "polar_256_128_ebch16_dyn.spec.in"), ("sp", "polar_240_114_ebch16_sp.spec.in")]
+
+
+@pytest.mark.parametrize("tag,name", SPECS2)
+@pytest.mark.parametrize("L,B,snr", [(1, 300, 2.5), (8, 120, 2.0), (32, 40, 1.5)])
+def test_dynamic_frozen_and_shortened_specs_match_reference(pk, need_ref, tag, name, L, B, snr):
+    """MixedKernelEncoder.cpp:115-139 (Shorten), :148-159 (dynamic frozen symbols), :179-203 (LoadLLRs) and the
+    dynamic-frozen branch of ContinuePathsFrozen, bit-exact against the reference library."""
+    spec = pk.load_spec(name)
+    ref = need_ref.PolarReference(spec, L)
+    p = pk.Polar(spec, L=L, device=0)
+    assert (p.N, p.K, p.N0) == (ref.N, ref.K, ref.N0)
+    info, cw, llr = _frames(ref, B, snr, 40 + L)
+    assert np.array_equal(p.encode(info), cw)
+    r_cnt, r_inf, r_cw, r_met = ref.decode(llr)
+    g_cnt, g_inf, g_cw, g_met = p.decode(llr)
+    assert np.array_equal(g_cnt, r_cnt)
+    assert np.array_equal(g_met.view(np.uint32), r_met.view(np.uint32)), "path metrics differ"
+    assert np.array_equal(g_inf, r_inf) and np.array_equal(g_cw, r_cw)
+    assert (g_inf[:, 0, :] == info).all(1).mean() > 0.5
+
+
+@pytest.mark.parametrize("tag,name", SPECS2)
+def test_extra_specs_against_committed_golden_vectors(pk, tag, name):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "polar_vectors2.npz"))
+    spec = pk.load_spec(name)
+    for L in (1, 8, 32):
+        p = pk.Polar(spec, L=L, device=0)
+        k = f"{tag}_L{L}"
+        info = np.unpackbits(z[k + "_info"], axis=1)[:, : p.K]
+        assert np.array_equal(np.packbits(p.encode(info), axis=1), z[k + "_cw"])
+        cnt, inf, cw, met = p.decode(z[k + "_llr"])
+        assert np.array_equal(cnt, z[k + "_count"])
+        assert np.array_equal(met.view(np.uint32), z[k + "_metric"].view(np.uint32))
+        assert np.array_equal(np.packbits(inf, axis=2), z[k + "_inf"])
+        assert np.array_equal(np.packbits(cw, axis=2), z[k + "_cwl"])

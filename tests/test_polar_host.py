@@ -56,3 +56,21 @@ def test_trellis_profile_equals_reference_processor(pk, oracle_mod):
         pytest.skip("oracle/_ref/libpolar_ref.so not built")
     _, ab = oracle_mod.polar_ref_trellis_llrs(os.path.join(pk.SPEC_DIR, "ebch16.kernel"), np.ones(16, np.float32), np.zeros(16, np.uint8))
     assert np.array_equal(ab, pk.Polar(pk.load_spec(), device=None).trellis_profile(0))
+
+
+def test_dynamic_frozen_and_shortened_specs_parse(pk):
+    """Host handles of the two extra specifications (tests/golden/make_polar_specs.py)."""
+    p = pk.Polar(pk.load_spec("polar_256_128_ebch16_dyn.spec.in"), L=8, device=None)
+    assert (p.N, p.K, p.N0, p.layers) == (256, 128, 256, 2)
+    p = pk.Polar(pk.load_spec("polar_240_114_ebch16_sp.spec.in"), L=1, device=None)
+    assert (p.N, p.K, p.N0, p.layers) == (240, 114, 256, 2)
+    # a shortened index outside the code and a constraint that is not ascending are rejected like the reference does
+    bad = pk.load_spec("polar_240_114_ebch16_sp.spec.in").replace("248 249", "248 300", 1)
+    with pytest.raises(pk.PkError):
+        pk.Polar(bad, device=None)
+    dyn = pk.load_spec("polar_256_128_ebch16_dyn.spec.in").split("\n")
+    i = next(k for k, ln in enumerate(dyn) if ln.split() and ln.split()[0] == "3")
+    t = dyn[i].split()
+    dyn[i] = " ".join([t[0], t[2], t[1], t[3]])
+    with pytest.raises(pk.PkError):
+        pk.Polar("\n".join(dyn), device=None)
