@@ -179,6 +179,42 @@ int pk_generate_frames_dev(pk_kaneko *dec, double ebn0_db, int snr_index, uint64
 int pk_kaneko_run_point(pk_kaneko *dec, double ebn0_db, int snr_index, uint64_t seed, long p, long e,
                         pk_point_result *out);
 
+/* ======================================================================================================
+ * Multi-GPU: the frames of an SNR point are independent, so they are sharded over the GPUs of the box
+ * by global frame index and the per-point counters are combined by ONE NCCL all-reduce over NVLink.  The reference
+ * has no counterpart (src/dataForPlot.cpp:41-95 is one sequential loop); results do not depend on the GPU count.
+ * NCCL is bound at run time (dlopen libnccl.so.2); a communicator of one rank needs none.
+ * ====================================================================================================== */
+typedef struct pk_comm pk_comm;
+typedef struct pk_comm_kaneko pk_comm_kaneko;
+
+/* One process driving ndev devices (devices = NULL: ordinals 0 .. ndev-1): ncclCommInitAll, one stream per device. */
+int pk_comm_create(int ndev, const int *devices, pk_comm **out);
+/* One process per GPU (torchrun, mpirun): rank 0 draws an id (pk_comm_unique_id), the caller hands it to the other
+ * processes, every process calls pk_comm_create_rank(world, rank, id, device).  world == 1 ignores id. */
+int pk_comm_unique_id(uint8_t *id128 /*[128]*/);
+int pk_comm_create_rank(int world, int rank, const uint8_t *id128, int device, pk_comm **out);
+void pk_comm_destroy(pk_comm *comm);
+int pk_comm_size(const pk_comm *comm);            /* ranks of the whole job */
+int pk_comm_rank(const pk_comm *comm);            /* global rank of this process' first device */
+int pk_comm_local_devices(const pk_comm *comm);   /* devices this process drives */
+void *pk_comm_stream(const pk_comm *comm, int local_device);   /* cudaStream_t the collectives of that device run on */
+/* In-place reduction over all ranks of the pk_point_result each local device holds at d_results[local] (device
+ * memory): sum of frames / frame_errors / bit_errors / trials / cmp / sum, maximum of max_trials_seen, OR of flags_or.
+ * Enqueued on the communicator's streams (asynchronous); pk_comm_sync waits for them. */
+int pk_allreduce_point(pk_comm *comm, pk_point_result *const *d_results /*[local devices]*/);
+int pk_comm_sync(pk_comm *comm);
+/* A Kaneko decoder on every local device of the communicator (pk_code_create + pk_kaneko_create per device). */
+int pk_comm_kaneko_create(pk_comm *comm, int m, int t, double llr_snr_db, long J, long max_trials, pk_comm_kaneko **out);
+void pk_comm_kaneko_destroy(pk_comm_kaneko *dec);
+pk_kaneko *pk_comm_kaneko_local(pk_comm_kaneko *dec, int local_device);
+/* fun()'s SNR point (dataForPlot.cpp:43-95) sharded over the communicator.  e <= 0: exactly p frames, contiguous share
+ * per rank, ONE all-reduce.  e > 0: the stop rule `count < p && countErr < e` in global frame order (rounds of
+ * world x chunk frames; per round the error counts of the chunks are exchanged, the chunk holding the e-th error is cut
+ * right after it): *out equals pk_kaneko_run_point on one device, on every rank. */
+int pk_comm_run_point(pk_comm_kaneko *dec, double ebn0_db, int snr_index, uint64_t seed, long p, long e,
+                      pk_point_result *out);
+
 /* n x n nested-BCH polarisation kernel, makeMatrix (src/bchCoder.cpp:317-345); row-major bytes. */
 int pk_make_kernel_matrix(const pk_code *code, uint8_t *out /*[n][n]*/);
 

@@ -34,7 +34,9 @@ SYMBOLS = (
     "pk_kaneko_decode_batch_async pk_kaneko_wait pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames pk_generate_frames_dev "
     "pk_kaneko_run_point pk_make_kernel_matrix pk_launch_count pk_launch_count_reset "
     "pk_polar_create pk_polar_destroy pk_polar_info pk_polar_trellis_profile pk_make_ebch_kernel pk_polar_encode_batch "
-    "pk_polar_kernel_llrs pk_polar_decode_batch pk_polar_decode_batch_dev"
+    "pk_polar_kernel_llrs pk_polar_decode_batch pk_polar_decode_batch_dev "
+    "pk_comm_create pk_comm_unique_id pk_comm_create_rank pk_comm_destroy pk_comm_size pk_comm_rank pk_comm_local_devices pk_comm_stream "
+    "pk_allreduce_point pk_comm_sync pk_comm_kaneko_create pk_comm_kaneko_destroy pk_comm_kaneko_local pk_comm_run_point"
 ).split()
 
 
@@ -95,6 +97,24 @@ def _load():
     lib.pk_polar_kernel_llrs.argtypes = [vp, i, vp, vp, l, vp]
     lib.pk_polar_decode_batch.argtypes = [vp, vp, l, vp, vp, vp, vp]
     lib.pk_polar_decode_batch_dev.argtypes = [vp, vp, l, vp, vp, vp, vp, vp]
+    lib.pk_comm_create.argtypes = [i, vp, pp]
+    lib.pk_comm_unique_id.argtypes = [vp]
+    lib.pk_comm_create_rank.argtypes = [i, i, vp, i, pp]
+    lib.pk_comm_destroy.argtypes = [vp]
+    lib.pk_comm_destroy.restype = None
+    lib.pk_comm_size.argtypes = [vp]
+    lib.pk_comm_rank.argtypes = [vp]
+    lib.pk_comm_local_devices.argtypes = [vp]
+    lib.pk_comm_stream.argtypes = [vp, i]
+    lib.pk_comm_stream.restype = vp
+    lib.pk_allreduce_point.argtypes = [vp, vp]
+    lib.pk_comm_sync.argtypes = [vp]
+    lib.pk_comm_kaneko_create.argtypes = [vp, i, i, d, l, l, pp]
+    lib.pk_comm_kaneko_destroy.argtypes = [vp]
+    lib.pk_comm_kaneko_destroy.restype = None
+    lib.pk_comm_kaneko_local.argtypes = [vp, i]
+    lib.pk_comm_kaneko_local.restype = vp
+    lib.pk_comm_run_point.argtypes = [vp, d, i, u64, l, l, vp]
     lib.pk_launch_count.restype = u64
     lib.pk_launch_count_reset.restype = None
     return lib
@@ -286,6 +306,76 @@ class Kaneko:
     def run_point(self, ebn0_db, snr_index, seed, p, e):
         tot = np.zeros(8, np.uint64)
         _check(lib.pk_kaneko_run_point(self.h, float(ebn0_db), int(snr_index), int(seed), int(p), int(e), _np_ptr(tot)))
+        return dict(zip(POINT_FIELDS, (int(v) for v in tot)))
+
+
+class Comm:
+    """pk_comm: the GPUs of one box.  Comm(ndev=N) drives N devices from this process; Comm.from_rank(world, rank, id,
+    device) is one rank of a job with one process per GPU (the id comes from Comm.unique_id() on rank 0)."""
+
+    def __init__(self, ndev=1, devices=None, _h=None):
+        if _h is not None:
+            self.h = _h
+        else:
+            h = C.c_void_p()
+            arr = None if devices is None else (C.c_int * ndev)(*devices)
+            _check(lib.pk_comm_create(int(ndev), arr, C.byref(h)))
+            self.h = h
+        self.world = lib.pk_comm_size(self.h)
+        self.rank = lib.pk_comm_rank(self.h)
+        self.local_devices = lib.pk_comm_local_devices(self.h)
+
+    @staticmethod
+    def unique_id():
+        buf = np.zeros(128, np.uint8)
+        _check(lib.pk_comm_unique_id(_np_ptr(buf)))
+        return buf
+
+    @classmethod
+    def from_rank(cls, world, rank, uid, device):
+        h = C.c_void_p()
+        uid = None if uid is None else np.ascontiguousarray(uid, np.uint8)
+        _check(lib.pk_comm_create_rank(int(world), int(rank), _np_ptr(uid), int(device), C.byref(h)))
+        return cls(_h=h)
+
+    def close(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib.pk_comm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def stream(self, local=0):
+        return lib.pk_comm_stream(self.h, local)
+
+    def allreduce_point(self, d_result_ptrs):
+        """d_result_ptrs: one device pointer (int) per local device, each to a pk_point_result."""
+        arr = (C.c_void_p * len(d_result_ptrs))(*d_result_ptrs)
+        _check(lib.pk_allreduce_point(self.h, arr))
+
+    def sync(self):
+        _check(lib.pk_comm_sync(self.h))
+
+
+class CommKaneko:
+    """pk_comm_kaneko: one Kaneko decoder per local device of a Comm; run_point shards an SNR point over all ranks."""
+
+    def __init__(self, comm, m, t, J=-1, llr_snr_db=0.5, max_trials=0):
+        self.comm = comm
+        h = C.c_void_p()
+        _check(lib.pk_comm_kaneko_create(comm.h, int(m), int(t), float(llr_snr_db), int(J), int(max_trials), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib.pk_comm_kaneko_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def run_point(self, ebn0_db, snr_index, seed, p, e):
+        tot = np.zeros(8, np.uint64)
+        _check(lib.pk_comm_run_point(self.h, float(ebn0_db), int(snr_index), int(seed), int(p), int(e), _np_ptr(tot)))
         return dict(zip(POINT_FIELDS, (int(v) for v in tot)))
 
 

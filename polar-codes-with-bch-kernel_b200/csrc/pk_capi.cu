@@ -55,8 +55,10 @@ struct pk_kaneko {
     cudaStream_t stream[2] = {nullptr, nullptr};
     // one control block + parked-frame list per concurrent launch slot:
     // slots 0/1 = the handle's two pipeline streams, slot 2 = caller-supplied streams
-    PkPhaseCtl *d_ctl = nullptr;              // [3]
-    PkLongRec *d_longs[3] = {nullptr, nullptr, nullptr};
+    PkPhaseBlock *d_ctl = nullptr;            // [3]: control words + mega slots, zeroed before every launch pair
+    PkLongRec *d_longs[3] = {nullptr, nullptr, nullptr};   // parked frames: [long_cap] main, [PK_HUGE_CAP] huge, [PK_LATE_CAP] late
+    uint32_t *d_mega_bits[3] = {nullptr, nullptr, nullptr};   // clean-chunk bitmaps of the mega slots
+    uint32_t epoch = 0;                       // launch counter (PkKanekoParams::epoch)
     uint32_t *d_zscr[3] = {nullptr, nullptr, nullptr};   // root-word scratch of the large-code phase B
     long long_cap = 1L << 18;                 // frames per launch pair (and capacity of a list)
     unsigned long long *d_totals = nullptr;   // [8]
@@ -341,6 +343,14 @@ int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_
     d->mode = c->use_lut ? PK_MODE_LUT : c->use_ct ? PK_MODE_CLASS : PK_MODE_ALG;
     d->kp.big_span = 8192u;
     d->kp.huge_span = 65536u;
+    {   // long searches shared by the grid: chunk = a few cooperative steps (1024 patterns per warp per step)
+        const uint32_t step = 1024u * (uint32_t)(d->mode == PK_MODE_LUT ? PK_WARPS_B_LUT : d->mode == PK_MODE_CLASS ? PK_WARPS_B_CT : PK_WARPS_B);
+        d->kp.mega_chunk = d->mode == PK_MODE_LUT ? 2 * step : d->mode == PK_MODE_CLASS ? 4 * step : step;
+        d->kp.mega_span = 8 * d->kp.mega_chunk;
+        d->kp.mega_after = d->mode == PK_MODE_LUT ? 4 * step : 8 * step;
+        d->kp.solo_patterns = d->mode == PK_MODE_ALG ? 16384u : 65536u;
+        d->kp.epoch = 0;
+    }
     d->kp.variant = 0;
     d->kp.extra_ops = 0;
     cudaDeviceProp prop;
@@ -348,7 +358,7 @@ int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_
     if (e == cudaSuccess) e = c->ks->geom_kaneko(d->mode, c->nk, prop.multiProcessorCount, d->geom4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream[0], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream[1], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&d->d_ctl, 3 * sizeof(PkPhaseCtl));
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_ctl, 3 * sizeof(PkPhaseBlock));
     if (e == cudaSuccess) e = cudaMalloc(&d->d_totals, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&d->h_totals, 8 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
@@ -367,7 +377,7 @@ void pk_kaneko_destroy(pk_kaneko *d) {
         cudaFree(d->d_y[s]); cudaFree(d->d_dec[s]); cudaFree(d->d_tr[s]); cudaFree(d->d_rec[s]);
     }
     cudaFree(d->d_ctl);
-    for (int i = 0; i < 3; ++i) { cudaFree(d->d_longs[i]); cudaFree(d->d_zscr[i]); }
+    for (int i = 0; i < 3; ++i) { cudaFree(d->d_longs[i]); cudaFree(d->d_zscr[i]); cudaFree(d->d_mega_bits[i]); }
     cudaFree(d->d_totals);
     cudaFree(d->d_grec);
     if (d->h_totals) cudaFreeHost(d->h_totals);
@@ -411,15 +421,25 @@ int pk_kaneko_launch_geometry(const pk_kaneko *d, int *grid, int *block, long *s
 static int launch_pairs(pk_kaneko *d, int slot, bool gen, PkIo io, long B, cudaStream_t st) {
     const pk_code *c = d->code;
     const bool wide = d->geom4[gen ? 3 : 1].grid > 0;
-    if (wide && !d->d_longs[slot]) PK_CUDA(cudaMalloc(&d->d_longs[slot], (size_t)(d->long_cap + PK_HUGE_CAP) * sizeof(PkLongRec)));
+    if (wide && !d->d_longs[slot]) {
+        const size_t bytes = (size_t)(d->long_cap + PK_HUGE_CAP + PK_LATE_CAP) * sizeof(PkLongRec);
+        PK_CUDA(cudaMalloc(&d->d_longs[slot], bytes));
+        PK_CUDA(cudaMemsetAsync(d->d_longs[slot], 0, bytes, st));   // late-list records carry the launch epoch (never 0)
+        PK_CUDA(cudaMalloc(&d->d_mega_bits[slot], (size_t)PK_MEGA_SLOTS * PK_MEGA_WORDS * sizeof(uint32_t)));
+    }
     if (wide && d->mode == PK_MODE_ALG && (c->t + 1) * c->m > 56 && !d->d_zscr[slot]) {
         const int gmax = std::max(d->geom4[1].grid, d->geom4[3].grid);
         PK_CUDA(cudaMalloc(&d->d_zscr[slot], (size_t)gmax * 4 * c->n * 32 * sizeof(uint32_t)));
     }
     io.zscratch = d->d_zscr[slot];
+    io.mega = d->d_ctl[slot].mega;
+    io.mega_bits = d->d_mega_bits[slot];
     for (long off = 0; off < B; off += d->long_cap) {
         const long nb = std::min(d->long_cap, B - off);
         PkIo part = io;
+        PkKanekoParams kp = d->kp;
+        if (++d->epoch == 0) d->epoch = 1;
+        kp.epoch = d->epoch;
         if (gen) {
             part.gp.first_frame = io.gp.first_frame + (uint64_t)off;
             if (io.d_info) part.d_info = io.d_info + off * c->k;
@@ -431,7 +451,7 @@ static int launch_pairs(pk_kaneko *d, int slot, bool gen, PkIo io, long B, cudaS
             if (io.trials) part.trials = io.trials + off;
         }
         if (io.recs) part.recs = io.recs + off;
-        PK_CUDA(c->ks->launch_kaneko(d->mode, gen, d->geom4, c->dev, d->kp, part, nb, d->d_ctl + slot,
+        PK_CUDA(c->ks->launch_kaneko(d->mode, gen, d->geom4, c->dev, kp, part, nb, &d->d_ctl[slot].ctl,
                                      d->d_longs[slot], wide ? d->long_cap : 0, st));
     }
     return PK_OK;

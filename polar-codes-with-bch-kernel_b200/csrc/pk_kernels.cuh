@@ -36,14 +36,7 @@
 
 #define PK_FULL 0xFFFFFFFFu
 #define PK_WARPS_A 8        // warps per CTA, phase A
-#define PK_WARPS_B 4        // warps per CTA, phase B, bit-sliced decoder (needs ~170 registers)
-#ifndef PK_WARPS_B_CT
-#define PK_WARPS_B_CT 4     // warps per CTA, phase B, class-table mode (8: no faster in bulk, slower tails at mid SNR)
-#endif
-#ifndef PK_WARPS_B_LUT
-#define PK_WARPS_B_LUT 16   // warps per CTA, phase B, coset-table mode: a whole CTA searches one long frame, 16K patterns per step
-                            // (the uncapped searches of these codes end in a few monster frames: latency matters)
-#endif
+// PK_WARPS_B, PK_WARPS_B_CT, PK_WARPS_B_LUT (warps per phase-B CTA): pk_kernels.h
 #ifndef PK_BS_LOOP
 #define PK_BS_LOOP true     // bit-sliced BM as one loop body (instruction-cache friendly)
 #endif
@@ -634,9 +627,18 @@ struct KanekoWarp {
     // G = warps of the CTA cooperating on this frame (warp wi takes block gbase + 1024 wi of every group step);
     // for G > 1 the search state travels through `shared` in warp order (baton passing), so improvements are
     // still committed in pattern order.  All G warps return with identical s.
+    //
+    // stop_at (a group-step boundary of this search, or 0xFFFFFFFF): the search pauses there and PK_W_STOPPED is returned
+    // with s ready to be resumed at `start = stop_at`.
+    // dry (helpers of a mega frame, G > 1): nothing is committed; s is a SNAPSHOT of (l0, have, bestF) with the bound wide
+    // open, and the answer is PK_W_DIRTY as soon as any pattern of [start, stop_at) survives the candidate filters
+    // against it, else PK_W_STOPPED = "no pattern of this range can improve on that state or on any later one"
+    // (l0 only decreases, and every former best codeword stays a non-improvement).
+    enum { PK_W_FINISHED = 0, PK_W_STOPPED = 1, PK_W_DIRTY = 2 };
     template <int G>
-    __device__ static void wide(const Tables &tb, const WarpMem &wm, const PkKanekoParams &kp, const Frame &f,
-                                Search &s, uint32_t start, Search *shared, uint32_t *votes, int wi) {
+    __device__ static int wide(const Tables &tb, const WarpMem &wm, const PkKanekoParams &kp, const Frame &f,
+                               Search &s, uint32_t start, Search *shared, uint32_t *votes, int wi,
+                               uint32_t stop_at = 0xFFFFFFFFu, bool dry = false) {
         const int lane = threadIdx.x & 31;
         const uint32_t base0 = (start & ~1023u) + 1024u * (uint32_t)wi;
         // pattern bits 0..4 = bit index in the word: their column contributions are per-frame constants
@@ -747,7 +749,11 @@ struct KanekoWarp {
         bool rerun = false;
         for (uint32_t base = base0;;) {
             const uint32_t gbase = base - 1024u * (uint32_t)wi;   // first pattern of this group step
-            if (gbase >= kp.max_trials) { s.trials = gbase; s.flags |= PK_FLAG_TRUNCATED; return; }
+            if (gbase >= stop_at && !rerun) return PK_W_STOPPED;
+            if (gbase >= kp.max_trials) {
+                if (dry) return PK_W_DIRTY;   // the master decides about truncation
+                s.trials = gbase; s.flags |= PK_FLAG_TRUNCATED; return PK_W_FINISHED;
+            }
             if (!rerun) s.step_last = 0;
             const uint32_t bound0 = s.bound;   // the bound this pass masks its patterns with (identical in all G warps)
             uint32_t u[SW];
@@ -1038,6 +1044,10 @@ struct KanekoWarp {
 #pragma unroll
                 for (int g = 0; g < G; ++g) turns |= (fl[g] ? 1u : 0u) << g;
             }
+            if (dry) {
+                if (G == 1) turns = __ballot_sync(PK_FULL, cand != 0) ? 1u : 0u;
+                if (turns) return PK_W_DIRTY;
+            }
             if (turns) {
                 // only the warps that have candidates take a turn (one barrier each): late in a long search that is
                 // one warp in sixteen
@@ -1086,7 +1096,7 @@ struct KanekoWarp {
                     __syncthreads();   // everyone has re-read the state before a later step overwrites it
                 }
             }
-            if (s.early) return;
+            if (s.early) return PK_W_FINISHED;
             // An improvement may RAISE the bound (T = j can grow when a larger m shrinks calcT's border sum).  If the bound
             // this pass was masked with ended inside the step, the patterns [bound0, min(new bound, end of step)) have not
             // been looked at yet although the sequential loop runs them: re-run the step for exactly those.
@@ -1099,7 +1109,7 @@ struct KanekoWarp {
             if (s.bound <= gbase + 1024u * G) {
                 s.trials = s.bound;
                 if (s.step_last > s.trials) s.trials = s.step_last;
-                return;
+                return PK_W_FINISHED;
             }
             lo = 0;
             rerun = false;
@@ -1415,12 +1425,31 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
 }
 
 // ------------------------------------------------------------------ phase B
+__device__ __forceinline__ unsigned int pk_ld_vol(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
+__device__ __forceinline__ unsigned long long pk_ld_vol(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
+__device__ __forceinline__ void pk_st_vol(unsigned int *p, unsigned int v) { *reinterpret_cast<volatile unsigned int *>(p) = v; }
+
+// Work order inside one launch (every CTA walks the same stages; all queues are global atomics):
+//   1. parked HUGE frames and the cooperative share of the big ones: one CTA per frame (`master`), warp w takes block w
+//      of every 1024 * WB-pattern step, commits in pattern order through shared memory;
+//   2. the other parked frames: one warp per frame.  A one-warp search still running after kp.solo_patterns is handed
+//      to a whole CTA through the LATE list;
+//   3. end game: CTAs without work take late frames as masters, and otherwise HELP the masters that are still searching.
+// MEGA frames.  A master whose search has kp.mega_span patterns or more ahead of it (an uncapped search after an early
+// decision: up to 2^28 patterns; a large code before its first decodable pattern: up to 2^31) registers the frame in a
+// mega slot.  Idle CTAs then scan chunks of kp.mega_chunk patterns AHEAD of the master in `dry` mode against a snapshot
+// of (l0, best codeword) and set a bit per chunk that holds no possible improvement; the master skips those chunks and
+// searches every other chunk itself, so commits stay in pattern order and the master never waits for anybody.  A clean
+// verdict cannot go stale: l0 only decreases and a former best codeword never becomes an improvement again; the
+// bound, m0 and the counters are the master's business alone.  (Before this, one CTA ground through such a frame at
+// 16K patterns per 11 us while the other 147 SMs idled: the tail of every uncapped low-SNR launch.)
 template <int M, int T, bool LUT, bool GEN, bool CT = false>
 __global__ void __launch_bounds__(PkSmem<M, T, LUT, CT>::WB * 32, CT ? PkTraits<M, T>::MINB_CT : LUT ? 2 : PkTraits<M, T>::MINB)
-k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkLongRec *longs, long long_cap) {
+k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec *longs, long long_cap) {
     typedef PkSmem<M, T, LUT, CT> SM;
     typedef KanekoWarp<M, T, LUT, CT> KW;
     constexpr int NW = KW::NW;
+    constexpr int GW = SM::WB;
     extern __shared__ __align__(16) unsigned char smem[];
     const unsigned long long n_long = ctl->n_long, n_big = ctl->n_big;
     const unsigned long long n_huge = ctl->n_huge < (unsigned long long)PK_HUGE_CAP ? ctl->n_huge : (unsigned long long)PK_HUGE_CAP;
@@ -1450,60 +1479,325 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, const PkL
     __shared__ typename KW::Search s_shared;
     __shared__ unsigned long long s_idx;
     __shared__ uint32_t s_votes[2 * SM::WB];
+    __shared__ uint32_t s_cmd[4];
+    __shared__ double s_snap_l0;
+    __shared__ uint32_t s_snap[NW + 1];
+    PkLongRec *late = longs + long_cap + PK_HUGE_CAP;
+    const uint32_t CH = (kp.mega_chunk % (1024u * GW)) ? 0u : kp.mega_chunk;   // 0: no mega frames (chunks must be whole cooperative steps)
 
     PkWarpTotals tot;
     tot.clear();
-    // ---- big frames: the whole CTA searches one frame, 1024 patterns per warp per step.  Cooperation costs
-    // ~10 % throughput (hand-over barriers), so when there are far more big frames than CTAs only one round of
-    // them is searched cooperatively and the rest go warp-per-frame below; with few big frames (the tail
-    // regime of medium / high SNR launches) all of them are.
-    // With fewer parked frames than CTAs (high SNR) the launch time is the latency of the longest search:
-    // then the small frames are searched by a whole CTA as well.
-    // The huge frames (own list behind the main one) come first and are always cooperative.
-    const bool all_coop = (n_long + n_big + n_huge) <= (unsigned long long)gridDim.x;
-    const unsigned long long n_coop = all_coop ? n_big + n_long : (n_big > 8ull * gridDim.x) ? (unsigned long long)gridDim.x : n_big;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_idx = atomicAdd(&ctl->queue_big, 1ull);
-        __syncthreads();
-        if (s_idx >= n_huge + n_coop) break;
-        const unsigned long long idx = s_idx - (s_idx < n_huge ? 0ull : n_huge);
-        const PkLongRec *rec = (s_idx < n_huge) ? longs + (long_cap + (long)idx)
-                               : (idx < n_big) ? longs + (long_cap - 1 - (long)idx) : longs + (idx - n_big);
-        const long f = (long)rec->frame;
+    // frame tables of the frame this CTA has set up last (every warp keeps its own copy)
+    typename KW::Frame fr;
+    uint32_t CW[NW];
+    long cur_frame = -1;
+    auto load = [&](long f) {
         double yv[NW];
-        uint32_t CW[NW];
-        pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, false, yv, CW);
-        typename KW::Frame fr;
-        typename KW::Search s;
-        KW::setup(tabs, wm, yv, kp, fr);     // every warp keeps its own copy of the frame tables
+        pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, false, yv, CW);   // dumps were written in phase A
+        KW::setup(tabs, wm, yv, kp, fr);
+        cur_frame = f;
+    };
+
+    // Stage 1 / 3 share ONE call site of the cooperative search (the CTA-level loop below is a small state machine:
+    // several inlined copies of wide<GW> would triple the kernel's code and stack).
+    // master state (CTA-uniform)
+    bool m_active = false, m_late = false, m_may_open = false;
+    long m_f = 0;
+    PkMegaSlot *m_ms = nullptr;
+    uint32_t *m_bits = nullptr;
+    uint32_t m_limit = 0, m_own = 0, m_start = 0, m_g0 = 0;
+    typename KW::Search s;   // the master's sequential state, or a helper's snapshot
+    // parked frames of this launch
+    const bool all_coop = (n_long + n_big + n_huge) <= (unsigned long long)gridDim.x;
+    // Cooperation costs ~10 % throughput (hand-over barriers), so when there are far more big frames than CTAs only one
+    // round of them is searched cooperatively and the rest go warp-per-frame; with few big frames (the tail regime of
+    // medium / high SNR launches) all of them are, and with fewer parked frames than CTAs the small ones as well.
+    const unsigned long long n_coop = all_coop ? n_big + n_long : (n_big > 8ull * gridDim.x) ? (unsigned long long)gridDim.x : n_big;
+    const unsigned long long n_solo = all_coop ? 0ull : n_long + (n_big - n_coop);
+    int stage = 1;
+
+    auto begin_master = [&](const PkLongRec *rec, bool known_long, bool from_late) {
+        m_f = (long)rec->frame;
+        load(m_f);
         KW::unpark(s, rec);
-        KW::template wide<SM::WB>(tabs, wm, kp, fr, s, rec->base, &s_shared, s_votes, warp);
+        m_g0 = rec->base & ~1023u;   // the search's step grid (and chunk grid) starts here
+        m_start = rec->base;
+        m_ms = nullptr; m_bits = nullptr; m_limit = 0;
+        m_may_open = CH != 0;
+        m_own = known_long ? 0u : kp.mega_after;
+        m_late = from_late;
+        m_active = true;
+    };
+    auto end_master = [&]() {
+        if (m_ms && threadIdx.x == 0) pk_st_vol(&m_ms->finished, 1u);
         if (warp == 0) {
             KW::search_finish(s);
-            pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot);
+            pk_emit<M, NW, GEN>(io, m_f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot);
         }
-    }
-    // ---- small frames (and the big ones left over): one warp each
-    const unsigned long long n_solo = all_coop ? 0ull : n_long + (n_big - n_coop);
+        if (m_late) {
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(&ctl->masters, ~0ull);
+        }
+        m_active = false;
+    };
+
     for (;;) {
-        unsigned long long idx = 0;
-        if (lane == 0) idx = atomicAdd(&ctl->queue_b, 1ull);
-        idx = __shfl_sync(PK_FULL, idx, 0);
-        if (idx >= n_solo) break;
-        // big leftovers first (longest searches first), then the small list
-        const PkLongRec *rec = (idx < n_big - n_coop) ? longs + (long_cap - 1 - (long)(n_coop + idx)) : longs + (idx - (n_big - n_coop));
-        const long f = (long)rec->frame;
-        double yv[NW];
-        uint32_t CW[NW];
-        pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, false, yv, CW);   // dumps were written in phase A
-        typename KW::Frame fr;
-        typename KW::Search s;
-        KW::setup(tabs, wm, yv, kp, fr);
-        KW::unpark(s, rec);
-        KW::template wide<1>(tabs, wm, kp, fr, s, rec->base, nullptr, nullptr, 0);
-        KW::search_finish(s);
-        pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot);
+        uint32_t h_slot = 0, h_chunk = 0;
+        bool h_job = false;
+        // ---------------- A: something to do
+        if (!m_active && stage == 1) {
+            // huge frames (own list behind the main one) and the cooperative share of the big ones: one CTA per frame
+            __syncthreads();
+            if (threadIdx.x == 0) s_idx = atomicAdd(&ctl->queue_big, 1ull);
+            __syncthreads();
+            const unsigned long long si = s_idx;
+            if (si < n_huge + n_coop) {
+                const unsigned long long idx = si - (si < n_huge ? 0ull : n_huge);
+                const PkLongRec *rec = (si < n_huge) ? longs + (long_cap + (long)idx)
+                                       : (idx < n_big) ? longs + (long_cap - 1 - (long)idx) : longs + (idx - n_big);
+                begin_master(rec, si < n_huge, false);
+            } else {
+                stage = 2;
+            }
+        }
+        if (!m_active && stage == 2) {
+            // the other parked frames (big leftovers first), one warp each
+            for (;;) {
+                unsigned long long idx = 0;
+                if (lane == 0) idx = atomicAdd(&ctl->queue_b, 1ull);
+                idx = __shfl_sync(PK_FULL, idx, 0);
+                if (idx >= n_solo) break;
+                const PkLongRec *rec = (idx < n_big - n_coop) ? longs + (long_cap - 1 - (long)(n_coop + idx)) : longs + (idx - (n_big - n_coop));
+                const long f = (long)rec->frame;
+                double yv[NW];
+                pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, false, yv, CW);
+                KW::setup(tabs, wm, yv, kp, fr);
+                KW::unpark(s, rec);
+                uint32_t start = rec->base;
+                const unsigned long long st = (unsigned long long)(rec->base & ~1023u) + kp.solo_patterns;
+                uint32_t stop = (kp.solo_patterns && st < 0x80000000ull) ? (uint32_t)st : 0xFFFFFFFFu;
+                bool handed = false;
+                for (;;) {
+                    const int r = KW::template wide<1>(tabs, wm, kp, fr, s, start, nullptr, nullptr, 0, stop, false);
+                    if (r != KW::PK_W_STOPPED) break;
+                    // still running: hand the search to a whole CTA (and through it to the idle part of the grid)
+                    long slot = -1;
+                    if (lane == 0) {
+                        const unsigned long long q = atomicAdd(&ctl->n_late, 1ull);
+                        if (q < (unsigned long long)PK_LATE_CAP) {
+                            slot = (long)q;
+                            KW::park(s, (uint32_t)f, stop, late + slot);
+                            __threadfence();
+                            pk_st_vol(&late[slot].pad, kp.epoch);   // the record is complete
+                        }
+                    }
+                    slot = __shfl_sync(PK_FULL, slot, 0);
+                    if (slot >= 0) { handed = true; break; }
+                    start = stop;            // late list full: finish here
+                    stop = 0xFFFFFFFFu;
+                }
+                if (handed) continue;
+                KW::search_finish(s);
+                pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot);
+            }
+            cur_frame = -1;   // the warps of this CTA hold different frames now
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(&ctl->ctas_past_solo, 1ull);
+            stage = 3;
+        }
+        if (!m_active && stage == 3) {
+            // end game: late frames as a master, else help a master, else wait for the masters or leave
+            if (threadIdx.x == 0) {
+                uint32_t cmd = 0, a0 = 0, a1 = 0;   // 0 = look again, 1 = master of late frame a0, 2 = help slot a0 with chunk a1, 3 = leave
+                for (;;) {
+                    const unsigned long long nl = pk_ld_vol(&ctl->n_late), ql = pk_ld_vol(&ctl->queue_late);
+                    if (ql >= (nl < (unsigned long long)PK_LATE_CAP ? nl : (unsigned long long)PK_LATE_CAP)) break;
+                    atomicAdd(&ctl->masters, 1ull);
+                    if (atomicCAS(&ctl->queue_late, ql, ql + 1ull) == ql) { cmd = 1; a0 = (uint32_t)ql; break; }
+                    atomicAdd(&ctl->masters, ~0ull);
+                }
+                if (!cmd && CH) {
+                    const unsigned long long nmr = pk_ld_vol(&ctl->n_mega);
+                    const uint32_t nm = nmr < (unsigned long long)PK_MEGA_SLOTS ? (uint32_t)nmr : (uint32_t)PK_MEGA_SLOTS;
+                    for (uint32_t i = 0; i < nm && !cmd; ++i) {
+                        PkMegaSlot *ms = io.mega + i;
+                        if (!pk_ld_vol(&ms->ready) || pk_ld_vol(&ms->finished)) continue;
+                        const uint32_t lim = ms->limit, g0 = ms->g0;
+                        const uint32_t nx = pk_ld_vol(&ms->next);
+                        if (nx >= lim || (unsigned long long)g0 + (unsigned long long)nx * CH >= (unsigned long long)pk_ld_vol(&ms->bound)) continue;
+                        const uint32_t c = atomicAdd(&ms->next, 1u);
+                        if (c >= lim || (unsigned long long)g0 + (unsigned long long)c * CH >= (unsigned long long)pk_ld_vol(&ms->bound) || c <= pk_ld_vol(&ms->pos)) continue;
+                        cmd = 2; a0 = i; a1 = c;
+                    }
+                }
+                if (!cmd) {
+                    // leave when nobody is a master any more and nobody can become one: all CTAs are past the one-warp
+                    // loop (n_late is final), every late frame has been taken and is finished
+                    bool leave = pk_ld_vol(&ctl->ctas_past_solo) >= (unsigned long long)gridDim.x;
+                    __threadfence();
+                    if (leave) {
+                        const unsigned long long nl = pk_ld_vol(&ctl->n_late);
+                        leave = pk_ld_vol(&ctl->queue_late) >= (nl < (unsigned long long)PK_LATE_CAP ? nl : (unsigned long long)PK_LATE_CAP);
+                        __threadfence();
+                        leave = leave && pk_ld_vol(&ctl->masters) == 0ull;
+                    }
+                    if (leave) cmd = 3;
+                    else __nanosleep(400);
+                }
+                s_cmd[0] = cmd; s_cmd[1] = a0; s_cmd[2] = a1;
+            }
+            __syncthreads();
+            const uint32_t cmd = s_cmd[0], a0 = s_cmd[1], a1 = s_cmd[2];
+            __syncthreads();
+            if (cmd == 3) break;
+            if (cmd == 0) continue;
+            if (cmd == 1) {
+                PkLongRec *rec = late + a0;
+                if (threadIdx.x == 0)
+                    while (pk_ld_vol(&rec->pad) != kp.epoch) __nanosleep(100);   // the one-warp search is still writing it
+                __threadfence();
+                __syncthreads();
+                begin_master(rec, true, true);
+            } else {
+                h_job = true; h_slot = a0; h_chunk = a1;
+            }
+        }
+        // ---------------- B: the next stretch of patterns to run
+        uint32_t start, stop;
+        bool dry = false;
+        uint32_t nimpr0 = 0;
+        if (m_active) {
+            if (!m_ms) {
+                // plain cooperative search up to the point where it is opened to helpers (if ever)
+                stop = 0xFFFFFFFFu;
+                if (m_may_open) {
+                    const unsigned long long c = ((unsigned long long)(m_start - m_g0) + m_own + CH - 1) / CH;
+                    const unsigned long long st = (unsigned long long)m_g0 + c * CH;
+                    if (st < 0x80000000ull) stop = (uint32_t)st;
+                }
+            } else {
+                const uint32_t c = (m_start - m_g0) / CH;
+                if (threadIdx.x == 0) {
+                    // chunks marked clean by helpers, from c on, as far as the bound reaches
+                    pk_st_vol(&m_ms->pos, c);
+                    atomicMax(&m_ms->next, c + 1);
+                    const unsigned long long nch = ((unsigned long long)(s.bound - m_g0) + CH - 1) / CH;
+                    const uint32_t cend = nch < (unsigned long long)m_limit ? (uint32_t)nch : m_limit;
+                    uint32_t cc = c;
+                    while (cc < cend) {
+                        const uint32_t k = cc & 31u;
+                        const uint32_t rem = ~(pk_ld_vol(m_bits + (cc >> 5)) >> k);   // first zero bit ends the run (the k vacated top bits read as "not clean")
+                        uint32_t run = rem ? (uint32_t)(__ffs(rem) - 1) : 32u;
+                        const bool word_end = run >= 32u - k;
+                        if (run > cend - cc) run = cend - cc;
+                        cc += run;
+                        if (!word_end) break;
+                    }
+                    s_cmd[0] = cc - c;
+                }
+                __syncthreads();
+                const uint32_t skip = s_cmd[0];
+                __syncthreads();
+                if (skip) {
+                    // no pattern of these chunks improves on the state: the sequential loop just runs through them
+                    const unsigned long long st = (unsigned long long)m_start + (unsigned long long)skip * CH;
+                    if (st >= (unsigned long long)s.bound) { s.trials = s.bound; end_master(); continue; }
+                    m_start = (uint32_t)st;
+                    if (m_start >= kp.max_trials) { s.trials = m_start; s.flags |= PK_FLAG_TRUNCATED; end_master(); }
+                    continue;
+                }
+                const unsigned long long st = (unsigned long long)m_start + CH;
+                stop = st < 0x80000000ull ? (uint32_t)st : 0xFFFFFFFFu;
+            }
+            start = m_start;
+            nimpr0 = s.nimpr;
+        } else if (h_job) {
+            // a helper's share: chunk h_chunk of mega slot h_slot against a snapshot of the master's state, nothing committed
+            PkMegaSlot *ms = io.mega + h_slot;
+            const long f = (long)ms->frame;
+            if (cur_frame != f) load(f);
+            if (threadIdx.x == 0) {
+                for (;;) {
+                    const unsigned int q0 = pk_ld_vol(&ms->seq);
+                    if (q0 & 1u) continue;
+                    __threadfence();
+                    s_snap_l0 = *reinterpret_cast<volatile double *>(&ms->l0);
+                    s_snap[NW] = pk_ld_vol(&ms->have);
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) s_snap[w] = pk_ld_vol(&ms->bestF[w]);
+                    __threadfence();
+                    if (pk_ld_vol(&ms->seq) == q0) break;
+                }
+            }
+            __syncthreads();
+            s.l0 = s_snap_l0;
+            s.have = s_snap[NW] != 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s.bestF[w] = s_snap[w];
+            s.m0 = 0; s.first_ok = true; s.early = false;
+            s.bound = 0x7FFFFFFFu;
+            s.trials = 0; s.tsteps = 0; s.nimpr = 0; s.step_last = 0; s.flags = 0;
+            __syncthreads();
+            start = ms->g0 + h_chunk * CH;
+            stop = start + CH;
+            dry = true;
+        } else {
+            continue;
+        }
+        // ---------------- C: run it (the only call site of the cooperative search)
+        const int r = KW::template wide<GW>(tabs, wm, kp, fr, s, start, &s_shared, s_votes, warp, stop, dry);
+        // ---------------- D
+        if (dry) {
+            if (r == KW::PK_W_STOPPED && threadIdx.x == 0)
+                atomicOr(io.mega_bits + (size_t)h_slot * PK_MEGA_WORDS + (h_chunk >> 5), 1u << (h_chunk & 31u));
+            continue;
+        }
+        if (r == KW::PK_W_FINISHED) { end_master(); continue; }
+        m_start = stop;
+        if (!m_ms) {
+            // still running after its own share: open the search to the idle CTAs of the grid if it is long
+            m_may_open = false;
+            if (s.bound > m_start && s.bound - m_start >= kp.mega_span) {
+                if (threadIdx.x == 0) {
+                    const unsigned long long i = atomicAdd(&ctl->n_mega, 1ull);
+                    s_cmd[0] = i < (unsigned long long)PK_MEGA_SLOTS ? (uint32_t)i : 0xFFFFFFFFu;
+                }
+                __syncthreads();
+                const uint32_t slot = s_cmd[0];
+                __syncthreads();
+                if (slot != 0xFFFFFFFFu) {
+                    m_ms = io.mega + slot;
+                    m_bits = io.mega_bits + (size_t)slot * PK_MEGA_WORDS;
+                    const unsigned long long nch = ((unsigned long long)(s.bound - m_g0) + CH - 1) / CH;
+                    m_limit = nch < (unsigned long long)PK_MEGA_WORDS * 32 ? (uint32_t)nch : (uint32_t)PK_MEGA_WORDS * 32u;
+                    for (uint32_t w = threadIdx.x; w < (m_limit + 31) / 32; w += blockDim.x) m_bits[w] = 0;
+                    __threadfence();
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        const uint32_t c = (m_start - m_g0) / CH;
+                        m_ms->frame = (unsigned int)m_f; m_ms->g0 = m_g0; m_ms->limit = m_limit;
+                        m_ms->pos = c; m_ms->next = c + 1; m_ms->bound = s.bound;
+                        m_ms->l0 = s.l0; m_ms->have = s.have ? 1u : 0u;
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) m_ms->bestF[w] = s.bestF[w];
+                        m_ms->seq = 0; m_ms->finished = 0;
+                        __threadfence();
+                        pk_st_vol(&m_ms->ready, 1u);
+                    }
+                }
+            }
+        } else if (s.nimpr != nimpr0 && threadIdx.x == 0) {
+            // publish the new state for the helpers (sequence lock)
+            const unsigned int q = m_ms->seq;
+            pk_st_vol(&m_ms->seq, q + 1);
+            __threadfence();
+            m_ms->l0 = s.l0; m_ms->have = s.have ? 1u : 0u; m_ms->bound = s.bound;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) m_ms->bestF[w] = s.bestF[w];
+            __threadfence();
+            pk_st_vol(&m_ms->seq, q + 2);
+        }
     }
     if (lane == 0) tot.flush(io.totals);
 }
@@ -1668,7 +1962,7 @@ struct PkLaunch {
     template <bool LUT, bool GEN, bool CT>
     static cudaError_t run(const PkLaunchGeom *g, const PkDevTables &tb, const PkKanekoParams &kp, const PkIo &io, long B,
                            PkPhaseCtl *ctl, PkLongRec *longs, long long_cap, cudaStream_t st) {
-        cudaError_t e = cudaMemsetAsync(ctl, 0, sizeof(PkPhaseCtl), st);
+        cudaError_t e = cudaMemsetAsync(ctl, 0, sizeof(PkPhaseBlock), st);   // ctl is the head of a PkPhaseBlock (control words + mega slots)
         if (e != cudaSuccess) return e;
         const bool wide_ok = g[1].grid > 0 && long_cap > 0 && !(GEN && io.dump_only);
         k_phase_a<M, T, LUT, GEN, CT><<<g[0].grid, g[0].block, g[0].smem, st>>>(tb, kp, io, B, ctl, longs, wide_ok ? long_cap : 0);

@@ -7,6 +7,22 @@
 #include "../../include/pk_capi.h"
 #include "pk_code.h"
 
+#define PK_HUGE_CAP 4096   // records behind the main parked-frame list for the huge frames
+#define PK_LATE_CAP 4096   // ... and behind those, for one-warp searches handed over to a whole CTA
+#define PK_MEGA_SLOTS 32   // long searches open to helpers per launch
+#define PK_MEGA_WORDS 16384   // bitmap words per mega slot: 2^31 patterns / 4096 per chunk / 32
+struct PkMegaSlot;
+
+// warps per phase-B CTA
+#define PK_WARPS_B 4        // bit-sliced decoder (needs ~170 registers)
+#ifndef PK_WARPS_B_CT
+#define PK_WARPS_B_CT 4     // class-table mode (8: no faster in bulk, slower tails at mid SNR)
+#endif
+#ifndef PK_WARPS_B_LUT
+#define PK_WARPS_B_LUT 16   // coset-table mode: a whole CTA searches one long frame, 16K patterns per step
+                            // (the uncapped searches of these codes end in a few monster frames: latency matters)
+#endif
+
 // Per-decoder run-time parameters (constant for the life of a pk_kaneko handle).
 struct PkKanekoParams {
     double llr_den;       // pow(sd0, 2): alpha = 2*y / llr_den  (KanekoKernelProcessor.cpp:337)
@@ -18,6 +34,12 @@ struct PkKanekoParams {
     uint32_t huge_span;   // ... and with at least this many go to the separate "huge" list (always cooperative)
     int variant;          // 0: decode(answer, word, res) (:335-407); 1: decode(word, res), the file-mode flavour (:212-276)
     uint32_t extra_ops;   // per-frame constant added to both synthetic counters (2n+1 sort cost of the file-mode flavour, :221-224)
+    // long searches shared by the whole grid (see "mega frames" in pk_kernels.cuh)
+    uint32_t mega_chunk;    // patterns per helper chunk (multiple of 1024 * warps per phase-B CTA)
+    uint32_t mega_span;     // a cooperative search with at least this many patterns left is opened to helpers ...
+    uint32_t mega_after;    // ... once it has run this many patterns on its own CTA
+    uint32_t solo_patterns; // a one-warp search still running after this many patterns is handed to a whole CTA (late list)
+    uint32_t epoch;         // launch counter (marks the late-list records of THIS launch as written)
 };
 
 // Generation-mode parameters of one launch.
@@ -41,6 +63,8 @@ struct PkIo {
     int dump_only;
     // both
     uint32_t *zscratch;   // phase B of large codes: root-word scratch, grid_b * 4 warps * n * 32 words
+    PkMegaSlot *mega;     // [PK_MEGA_SLOTS] per launch slot
+    uint32_t *mega_bits;  // [PK_MEGA_SLOTS][PK_MEGA_WORDS] clean-chunk bitmaps
     pk_frame_rec *recs;
     unsigned long long *totals;
 };
@@ -49,7 +73,7 @@ struct PkIo {
 struct PkLongRec {
     double l0;
     uint32_t frame, base, bound, m0;
-    uint32_t tsteps, nimpr, sflags, pad;   // sflags: bit0 first_ok, bit1 have, bits 8.. = frame flags
+    uint32_t tsteps, nimpr, sflags, pad;   // sflags: bit0 first_ok, bit1 have, bits 8.. = frame flags; pad: late list: == launch epoch once written
     uint32_t bestF[8];
 };
 // Device-side control block of one phase A / phase B launch pair (zeroed by the launcher).
@@ -61,11 +85,41 @@ struct PkPhaseCtl {
     unsigned long long queue_big;   // next parked "big" frame (one CTA each)
     unsigned long long n_big;       // parked big frames: longs[cap-1 .. cap-n_big] (filled from the top)
     unsigned long long n_huge;      // parked huge frames: longs[cap .. cap+n_huge) (may count past PK_HUGE_CAP: the overflow went to the big list)
+    // phase B end game
+    unsigned long long n_late;          // one-warp searches handed over to a whole CTA: longs[cap + PK_HUGE_CAP ..) (may count past PK_LATE_CAP)
+    unsigned long long queue_late;      // next of them to take
+    unsigned long long n_mega;          // mega slots handed out (may count past PK_MEGA_SLOTS)
+    unsigned long long ctas_past_solo;  // CTAs that have left the one-warp loop: once all have, n_late is final
+    unsigned long long masters;         // CTAs that are (or are about to become) the master of a late frame
 };
+
+// A long search opened to the idle CTAs of the grid ("mega frame").  The master CTA keeps the sequential state and
+// commits in pattern order; helpers scan chunks AHEAD of it against a snapshot of (l0, best codeword) and mark the ones
+// that hold no possible improvement in a bitmap, which the master then skips.
+struct PkMegaSlot {
+    unsigned int ready;      // 1 once the master has filled the slot
+    unsigned int finished;   // 1 when the master is done with the frame
+    unsigned int seq;        // sequence lock over (l0, have, bestF): odd while the master writes
+    unsigned int pos;        // chunk the master is working on (helpers take later ones)
+    unsigned int next;       // next chunk to hand to a helper
+    unsigned int bound;      // pattern bound as of the last commit (chunks beyond it are not handed out)
+    unsigned int frame;      // frame index in the batch
+    unsigned int g0;         // first pattern of chunk 0 (the search's step grid starts there)
+    unsigned int limit;      // chunks covered by the (cleared) bitmap
+    unsigned int have;
+    double l0;
+    unsigned int bestF[8];
+};
+
+// what the launcher zeroes before every launch pair: the control words and, right behind them, the mega slots
+struct PkPhaseBlock {
+    PkPhaseCtl ctl;
+    PkMegaSlot mega[PK_MEGA_SLOTS];
+};
+
 
 enum { PK_MODE_ALG = 0, PK_MODE_LUT = 1, PK_MODE_CLASS = 2 };
 
-#define PK_HUGE_CAP 4096   // records behind the main parked-frame list for the huge frames
 
 struct PkLaunchGeom {
     int grid, block;

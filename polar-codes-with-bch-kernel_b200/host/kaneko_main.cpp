@@ -3,7 +3,7 @@
 //   kaneko_b200 <m> <t> <snr>                 one random word at <snr> dB
 //   kaneko_b200 <m> <t> <snr> <file>          word + samples from <file>
 //   kaneko_b200 <m> <t> <file> <p> <e>        FER sweep 0..5 dB -> <file>.csv
-// optional trailing flags: --J <cap>  --seed <s>
+// optional trailing flags: --J <cap>  --seed <s>  --gpus <n> (frames of every SNR point sharded over n GPUs of the box)
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -20,10 +20,12 @@
 int main(int argc, char *argv[]) {
     try {
         long J = -1;
+        int gpus = 1;
         std::vector<char *> pos;
         for (int i = 0; i < argc; ++i) {
             if (!std::strcmp(argv[i], "--J") && i + 1 < argc) J = std::atol(argv[++i]);
             else if (!std::strcmp(argv[i], "--seed") && i + 1 < argc) fun_seed = std::strtoull(argv[++i], nullptr, 10);
+            else if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = std::atoi(argv[++i]);
             else pos.push_back(argv[i]);
         }
         const int n_args = (int)pos.size();
@@ -51,6 +53,7 @@ int main(int argc, char *argv[]) {
 
         KanekoKernelProcessor decoder(power, n, t, k, antilogarithms.data(), logarithms.data(), 0.5, J);
         if (n_args == 6) {
+            if (gpus != 1) decoder.useGpus(gpus);
             fun(filename, decoder, g.data(), (unsigned long)gSize, p, e, 5.0);
             return 0;
         }

@@ -5,13 +5,26 @@
 
 KanekoKernelProcessor::KanekoKernelProcessor(long pw, long n, long t, long k, unsigned long *antilogarithms,
                                              unsigned long *logarithms, double signalToNoiseRatio, long J)
-    : decoder(pw, n, t, k, antilogarithms, logarithms), n_(n), t_(t), kan_(nullptr), alpha_(new double[n]()),
+    : decoder(pw, n, t, k, antilogarithms, logarithms), n_(n), t_(t), pw_(pw), J_(J), snr_(signalToNoiseRatio), kan_(nullptr), alpha_(new double[n]()),
       yH_(new unsigned char[n]()) {
     sd = sqrt(1 / (pow(10, signalToNoiseRatio / 10) * 2 * k / n));   // KanekoKernelProcessor.cpp:20
     if (pk_kaneko_create(decoder.handle(), signalToNoiseRatio, J, 0, &kan_) != PK_OK) throw pk_last_error();
 }
 
+void KanekoKernelProcessor::useGpus(int ngpus) {
+    if (ngpus < 1) throw "Invalid values of arguments\n";
+    if (ckan_) { pk_comm_kaneko_destroy(ckan_); ckan_ = nullptr; }
+    if (comm_) { pk_comm_destroy(comm_); comm_ = nullptr; }
+    ngpus_ = 1;
+    if (ngpus == 1) return;
+    if (pk_comm_create(ngpus, nullptr, &comm_) != PK_OK) throw pk_last_error();
+    if (pk_comm_kaneko_create(comm_, (int)pw_, (int)t_, snr_, J_, 0, &ckan_) != PK_OK) throw pk_last_error();
+    ngpus_ = ngpus;
+}
+
 KanekoKernelProcessor::~KanekoKernelProcessor() {
+    if (ckan_) pk_comm_kaneko_destroy(ckan_);
+    if (comm_) pk_comm_destroy(comm_);
     pk_kaneko_destroy(kan_);
     delete[] alpha_;
     delete[] yH_;
@@ -78,7 +91,9 @@ void KanekoKernelProcessor::decodeBatch(const double *words, long B, unsigned ch
 
 pk_point_result KanekoKernelProcessor::runPoint(double ebn0_db, int snr_index, uint64_t seed, long p, long e) {
     pk_point_result r;
-    if (pk_kaneko_run_point(kan_, ebn0_db, snr_index, seed, p, e, &r) != PK_OK) throw pk_last_error();
+    const int rc = ckan_ ? pk_comm_run_point(ckan_, ebn0_db, snr_index, seed, p, e, &r)
+                         : pk_kaneko_run_point(kan_, ebn0_db, snr_index, seed, p, e, &r);
+    if (rc != PK_OK) throw pk_last_error();
     account(r);
     return r;
 }

@@ -42,13 +42,20 @@ public:
     void decodeBatch(const double *words, long B, unsigned char *res, uint32_t *trials = nullptr);
     // generation mode: one SNR point with fun()'s stop rule, frames drawn on the device
     pk_point_result runPoint(double ebn0_db, int snr_index, uint64_t seed, long p, long e);
+    // shard the frames of runPoint over the first `ngpus` devices of the box (pk_comm_create / pk_comm_run_point:
+    // one NCCL all-reduce of the counters per SNR point); the results do not depend on ngpus
+    void useGpus(int ngpus);
+    int gpus() const { return ngpus_; }
     pk_kaneko *handle() const { return kan_; }
 
 private:
     Decoder decoder;
-    long n_, t_;
-    double sd;
+    long n_, t_, pw_, J_;
+    double sd, snr_;
     pk_kaneko *kan_;
+    int ngpus_{1};
+    pk_comm *comm_{nullptr};
+    pk_comm_kaneko *ckan_{nullptr};
     mutable double *alpha_;
     mutable unsigned char *yH_;
     unsigned long comparisonCount{0}, summCount{0}, decodingCount{0};

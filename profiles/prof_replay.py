@@ -1,5 +1,5 @@
 """Profiling driver: a few replay-mode launches of one code at one SNR point.
-usage: python profiles/prof_replay.py M T J SNR_DB FRAMES [LUT(0/1)] [REPS]"""
+usage: python profiles/prof_replay.py M T J SNR_DB FRAMES [LUT(0/1)] [REPS] [MAX_TRIALS]"""
 import os
 import sys
 import time
@@ -13,13 +13,14 @@ pk = pkb200.pk
 m, t, J, snr, B = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4]), int(sys.argv[5])
 lut = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 reps = int(sys.argv[7]) if len(sys.argv) > 7 else 3
+max_trials = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 torch.cuda.set_device(0)
 st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
 code = pk.Code(m, t, device=0)
 if not lut and code.uses_lut:
     code.set_lut(False)
-kan = pk.Kaneko(code, J=J)
+kan = pk.Kaneko(code, J=J, max_trials=max_trials)
 y = torch.empty((B, code.n), dtype=torch.float64, device="cuda")
 dec = torch.zeros((B, code.n), dtype=torch.uint8, device="cuda")
 tr = torch.zeros(B, dtype=torch.int32, device="cuda")

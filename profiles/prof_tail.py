@@ -1,5 +1,5 @@
 """Tail analysis of a replay launch: time of the whole batch, of the parked frames alone and of the single longest frame.
-usage: python profiles/prof_tail.py M T J SNR_DB FRAMES"""
+usage: python profiles/prof_tail.py M T J SNR_DB FRAMES [MAX_TRIALS]"""
 import os
 import sys
 
@@ -11,11 +11,12 @@ import pkb200
 
 pk = pkb200.pk
 m, t, J, snr, B = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4]), int(sys.argv[5])
+max_trials = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 torch.cuda.set_device(0)
 st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
 code = pk.Code(m, t, device=0)
-kan = pk.Kaneko(code, J=J)
+kan = pk.Kaneko(code, J=J, max_trials=max_trials)
 y = torch.empty((B, code.n), dtype=torch.float64, device="cuda")
 kan.generate_frames_dev(snr, int(round(snr * 2)), 1, 0, B, y.data_ptr(), stream=st.cuda_stream)
 torch.cuda.synchronize()

@@ -59,7 +59,7 @@ LONG_CASES = [
     (7, 10, 15, 3.0, 2000, 500, 1 << 18, 16_000_000),
     (7, 10, 15, 4.0, 1500, 500, 1 << 18, 16_000_000),
     (7, 10, 15, 5.0, 1500, 500, 1 << 18, 16_000_000),
-    (8, 15, 15, 3.5, 4000, 500, 1 << 16, 6_000_000),
+    (8, 15, 15, 3.5, 4000, 500, 1 << 16, 14_000_000),
     (8, 15, 15, 4.0, 2500, 500, 1 << 16, 6_000_000),
     (8, 15, 15, 4.5, 2000, 500, 1 << 16, 6_000_000),
 ]

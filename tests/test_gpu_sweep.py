@@ -78,3 +78,58 @@ def test_two_gpu_sweep_reproduces_one_gpu_csv(tmp_path):
                           "--master-port", "29533", script, "5", "3", str(tmp_path / "g2"), "40000", "300"], capture_output=True, text=True, timeout=600)
     assert two.returncode == 0, two.stderr
     assert open(tmp_path / "g1.csv").read() == open(tmp_path / "g2.csv").read()
+
+
+KEYS6 = ("frames", "frame_errors", "bit_errors", "trials", "cmp", "sum")
+
+
+def test_c_abi_communicator_of_one_rank_equals_run_point(pk):
+    """pk_comm_* with a single rank (no NCCL needed): pk_comm_run_point == pk_kaneko_run_point for both stop rules, and
+    pk_allreduce_point leaves a one-rank result alone."""
+    import torch
+
+    comm = pk.Comm(ndev=1)
+    assert (comm.world, comm.rank, comm.local_devices) == (1, 0, 1)
+    ck = pk.CommKaneko(comm, 4, 3)
+    kan = pk.Kaneko(pk.Code(4, 3, device=0))
+    for (snr, si, p, e) in [(0.0, 0, 50000, 100), (2.0, 4, 30000, 0), (5.0, 10, 20000, 1000)]:
+        a, b = ck.run_point(snr, si, 9, p, e), kan.run_point(snr, si, 9, p, e)
+        assert [a[k] for k in KEYS6] == [b[k] for k in KEYS6], (snr, p, e)
+        assert a["max_trials_seen"] == b["max_trials_seen"]
+    t = torch.arange(8, dtype=torch.int64, device="cuda") + 5
+    torch.cuda.synchronize()
+    comm.allreduce_point([t.data_ptr()])
+    comm.sync()
+    assert t.tolist() == list(range(5, 13))
+
+
+def test_c_abi_two_gpus_equal_one_gpu(pk, tmp_path):
+    """One process, two devices (ncclCommInitAll): the sharded point equals the one-device point for fixed-p and for the
+    stop rule in global frame order, and `kaneko_b200 --gpus 2` writes the CSV of `--gpus 1` byte for byte."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    c1, c2 = pk.Comm(ndev=1), pk.Comm(ndev=2)
+    assert c2.world == 2 and c2.local_devices == 2
+    for (m, t, J, snr, si, p, e) in [(4, 3, -1, 0.0, 0, 100000, 300), (5, 3, -1, 1.0, 2, 200001, 0), (6, 6, 9, 3.0, 6, 50000, 0), (5, 3, -1, 3.0, 6, 300000, 150)]:
+        k1, k2 = pk.CommKaneko(c1, m, t, J=J), pk.CommKaneko(c2, m, t, J=J)
+        a, b = k1.run_point(snr, si, 3, p, e), k2.run_point(snr, si, 3, p, e)
+        assert [a[k] for k in KEYS6] == [b[k] for k in KEYS6], (m, t, snr, p, e)
+        assert a["max_trials_seen"] == b["max_trials_seen"] and a["flags_or"] == b["flags_or"]
+    # device-resident results: sum / max / or over the two devices
+    ts = []
+    for d in range(2):
+        with torch.cuda.device(d):
+            ts.append(torch.tensor([1 + d, 2, 3, 4, 5, 6, 100 * (d + 1), 1 << d], dtype=torch.int64, device=f"cuda:{d}"))
+            torch.cuda.synchronize()
+    c2.allreduce_point([x.data_ptr() for x in ts])
+    c2.sync()
+    for x in ts:
+        assert x.tolist() == [3, 4, 6, 8, 10, 12, 200, 3]
+    exe = os.path.join(PKG, "kaneko_b200")
+    if os.path.exists(exe):
+        for g in (1, 2):
+            out = subprocess.run([exe, "5", "3", str(tmp_path / f"c{g}"), "60000", "250", "--gpus", str(g)], capture_output=True, text=True, timeout=600)
+            assert out.returncode == 0, out.stderr
+        assert open(tmp_path / "c1.csv").read() == open(tmp_path / "c2.csv").read()
