@@ -110,6 +110,16 @@ int pk_bch_decode_batch(pk_code *code, const uint8_t *words /*[B][n]*/, long B,
  * (main.cpp:176 passes 0.5).  J < 0: HEAD semantics T = j (line 393); J >= 0: capped
  * T = min(j,J) (line 392, the *_e*.csv runs).  max_trials <= 0: the reference bound. */
 int pk_kaneko_create(pk_code *code, double llr_snr_db, long J, long max_trials, pk_kaneko **out);
+/* Two things the reference does not have (it only builds n = 2^m - 1, src/main.cpp:60, and only its own stopping rules):
+ *   extended = 1: the EXTENDED code (n+1, k, 2t+2) -- position n carries the overall parity of the BCH codeword; frames are
+ *     n+1 long everywhere (y, decisions, generation mode), Eb/N0 uses the rate k/(n+1).  Test patterns flip the least
+ *     reliable BCH positions, the algebraic decoder works on the BCH part, the decided parity position follows from it, and
+ *     m, l, calcRightSide (with d = 2t+2) and calcT run over all n+1 positions.  eBCH(128,64,22) = (m,t) = (7,10), extended.
+ *     DESIGN.md states the definition; it is pinned against exhaustive ML on the small extended codes, not against the reference.
+ *   rules: 0 = decode(answer, word, res) (:335-407), 1 = decode(word, res) (:212-276), 2 = EXACT rules: loop bound 1 << T,
+ *     optimality test l < sum of the d - m least reliable agreeing positions, T = first j with l < sum_{i=j..j+t} alpha_(i):
+ *     both are sufficient conditions, so the decision is the ML codeword (what the kernel-LLR bridge needs). */
+int pk_kaneko_create_ext(pk_code *code, double llr_snr_db, long J, long max_trials, int extended, int rules, pk_kaneko **out);
 void pk_kaneko_destroy(pk_kaneko *dec);
 /* Which of the reference's decode flavours the handle runs: 0 (default) decode(answer, word, res), the one fun()
  * uses (KanekoKernelProcessor.cpp:335-407); 1 decode(word, res), the file-mode flavour of main.cpp:158 (:212-276:
@@ -235,7 +245,7 @@ void pk_polar_destroy(pk_polar *p);
 int pk_polar_info(const pk_polar *p, int *N, int *K, int *N0, int *layers, int *list_size);
 /* m_ppNumOfActiveBits of the kernel of `layer` (TrellisKernelProcessor.cpp:105,154): out[l][l+1] */
 int pk_polar_trellis_profile(const pk_polar *p, int layer, int *size, uint8_t *out);
-/* (2^m) x (2^m) extended-BCH polarisation kernel, makeMatrix of the root bchCoder.cpp:356-389; m in [3,5] */
+/* (2^m) x (2^m) extended-BCH polarisation kernel, makeMatrix of the root bchCoder.cpp:356-389; m in [3,6] */
 int pk_make_ebch_kernel(int m, uint8_t *out /*[2^m][2^m]*/);
 /* CBinaryEncoder::Encode (Codec.h:52; MixedKernelEncoder.cpp:142-176) */
 int pk_polar_encode_batch(pk_polar *p, const uint8_t *info /*[B][K]*/, long B, uint8_t *cw /*[B][N]*/);
@@ -249,6 +259,43 @@ int pk_polar_decode_batch(pk_polar *p, const float *llr /*[B][N]*/, long B, int 
                           float *metric);
 int pk_polar_decode_batch_dev(pk_polar *p, const float *d_llr, long B, int *d_count, uint8_t *d_inf, uint8_t *d_cw,
                               float *d_metric, void *stream);
+
+/* Generation mode of the polar path -- the body of the reference's simulator loop (out/external/Simulator.cpp:139-335,
+ * not buildable: GSL / Windows) on the device: Philox4x32-10 information bits (counter = (frame, snr_index, draw), key =
+ * seed) -> Encode -> BPSK (bit 0 -> +1, Modem.h:64) + AWGN -> LLR = 2y/sigma^2 as fp32 (Modem.h:78) -> Decode -> compare
+ * the best path's information vector with the transmitted one.  sigma^2 = 1 / (2 (K/N) 10^(EbN0/10)) (Simulator.cpp:104).
+ * d_totals (8 x u64, pk_point_result layout: frames, frame_errors, bit_errors = information-bit errors) is accumulated
+ * into; results do not depend on how the frame range is split over calls or GPUs. */
+int pk_polar_run_frames_dev(pk_polar *p, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
+                            uint64_t *d_totals, void *stream);
+int pk_polar_run_frames(pk_polar *p, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
+                        pk_point_result *totals);
+/* the frames themselves: info [B][K], cw [B][N] (either may be NULL), llr [B][N]; device / host buffers */
+int pk_polar_generate_frames_dev(pk_polar *p, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
+                                 uint8_t *d_info, uint8_t *d_cw, float *d_llr, void *stream);
+int pk_polar_generate_frames(pk_polar *p, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
+                             uint8_t *info, uint8_t *cw, float *llr);
+
+/* ======================================================================================================
+ * Kaneko decoding as a polarisation-kernel processor.  CKernProcLLR::GetLLRs
+ * (headers/external/KernProc.h:40-60) for the (2^m) x (2^m) extended-BCH kernel of the root bchCoder.cpp:356-389:
+ * LLR of kernel input `phase` = M[1] - M[0], M[v] = metric of the best codeword of the coset with u_phase = v -- the value
+ * the trellis processor computes as pStateMetric0[1] - pStateMetric0[0] (out/external/TrellisKernelProcessor.cpp:292),
+ * here by maximum-likelihood Kaneko decodings of extended BCH codes (exact rules of pk_kaneko_create_ext), which also
+ * serves the 64 x 64 kernel the trellis processor rejects (:71-72).  m in [3,6]; row tails of dimension <= enum_dim
+ * (<= 12, negative = 12) are enumerated instead of decoded; max_trials <= 0: 2^22 per search.
+ * ====================================================================================================== */
+typedef struct pk_kproc pk_kproc;
+int pk_kproc_create(int m, int device, long max_trials, int enum_dim, pk_kproc **out);
+void pk_kproc_destroy(pk_kproc *h);
+/* size = 2^m; per phase: mode (0 enumeration, 1 even-weight closed form, 2 Kaneko search), t of the BCH code decoded,
+ * number of kernel rows enumerated on top of it (2 * 2^rows searches per LLR).  Arrays of `size` ints, any may be NULL. */
+int pk_kproc_info(const pk_kproc *h, int *size, int *mode, int *t, int *nextra);
+/* GetLLRs(Stride, phase, pKnownInputSymbols [l][Stride], pChannelLLRs [l][Stride], pLLRs [Stride]); host buffers.
+ * *truncated (may be NULL): searches stopped by the trial budget (their minimum is over the codewords found so far). */
+int pk_kproc_get_llrs(pk_kproc *h, int stride, int phase, const uint8_t *known, const float *chan, float *out, long *truncated);
+/* all phases of B independent kernel blocks, layout of pk_polar_kernel_llrs: chan [B][l], u [B][l] -> out [B][l] */
+int pk_kproc_kernel_llrs(pk_kproc *h, const float *chan, const uint8_t *u, long B, float *out, long *truncated);
 
 /* Introspection for bench.py: kernels launched by this library since load / reset. */
 uint64_t pk_launch_count(void);

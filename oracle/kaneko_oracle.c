@@ -831,3 +831,127 @@ void ko_make_matrix(const ko_code *c, uint8_t *out) {
     }
     free(g); free(poly); free(quo); free(rem); free(row);
 }
+
+/* ------------------------------------------------------------------ extended codes / exact rules
+ * NOT IN THE REFERENCE (src/main.cpp:60 builds n = 2^m - 1 only; `parity unpinned`).  CPU statement of the definition in
+ * DESIGN.md that libpkb200's pk_kaneko_create_ext implements, for the GPU parity tests:
+ *   ext = 1 : code (n+1, k, 2t+2), position n = overall parity of the BCH codeword.  alpha, yH and the reliability order
+ *             run over all n+1 positions (std::sort replay as in kan_load); test pattern bit b flips the b-th least
+ *             reliable BCH position (the parity position is skipped); the algebraic decoder sees the BCH part; the decided
+ *             parity position is the parity of the decoded BCH word; m, l, calcRightSide (d = 2t+2) and calcT use all n+1
+ *             positions; T starts at n (so the initial loop bound is the BCH code's).
+ *   rules   : 0 = the 3-argument flavour's bookkeeping (kan_decode3), 2 = exact rules: loop bound 1 << T (64-bit),
+ *             m0 = m on every success, calcRightSide border d - m, calcT without its border sum.
+ * lbest (optional) receives l of the decision (DBL_MAX if none). */
+void ko_ext_gen_frames(ko_code *c, int ext, double ebn0_db, long B, uint8_t *info, uint8_t *cw, double *y) {
+    long k = c->k, n = c->n, ne = n + ext;
+    for (long f = 0; f < B; ++f) {
+        double sd = sqrt(1 / (pow(10, ebn0_db / 10) * 2 * k / ne));
+        for (long i = 0; i < k; ++i) info[f * k + i] = (uint8_t)rng_bit(c);
+        encode_one(c, info + f * k, cw + f * ne);
+        if (ext) {
+            uint8_t p = 0;
+            for (long i = 0; i < n; ++i) p ^= cw[f * ne + i];
+            cw[f * ne + n] = p;
+        }
+        normal_state st = {0, 0.0};
+        for (long i = 0; i < ne; ++i) y[f * ne + i] = (cw[f * ne + i] ? 1 : -1) + rng_normal(c, &st, sd);
+    }
+}
+
+void ko_ext_kaneko_decode(ko_code *c, int ext, int rules, double llr_snr_db, const double *y, long B, uint8_t *decided,
+                          uint32_t *trials, uint64_t *cmp, uint64_t *sum, double *lbest) {
+    const int n = c->n, ne = n + ext, t = c->t, d = 2 * t + 1 + ext;
+    double *alpha = malloc((size_t)(ne + 1) * sizeof(double)), *skey = malloc((size_t)(ne + 2) * sizeof(double));
+    int *sidx = malloc((size_t)(ne + 1) * sizeof(int)), *pidx = malloc((size_t)(ne + 1) * sizeof(int));
+    uint8_t *yH = malloc((size_t)ne + 1), *x = malloc((size_t)ne + 1), *word = malloc((size_t)ne + 1);
+    const double sd0 = sqrt(1 / (pow(10, llr_snr_db / 10) * 2 * (long)c->k / (long)ne));
+    for (long f = 0; f < B; ++f) {
+        const double *w = y + f * ne;
+        uint8_t *res = decided + f * ne;
+        uint64_t n_dec = 0, n_cmp = 0, n_sum = 0;
+        for (int i = 0; i < ne; ++i) {
+            const double a = 2 * w[i] / pow(sd0, 2);
+            yH[i] = (a <= 0.0) ? 0 : 1;
+            alpha[i] = fabs(a);
+            skey[i] = alpha[i];
+            sidx[i] = i;
+        }
+        ko_std_sort_pairs(skey, sidx, ne);
+        skey[ne] = 0.0;
+        int np = 0;   /* reliability order of the BCH positions alone: the pattern positions */
+        for (int r = 0; r < ne; ++r)
+            if (sidx[r] < n) pidx[np++] = sidx[r];
+        long mm = 0, mm0 = 0, j = 0, T = n;
+        uint64_t i = 0;
+        double l0 = DBL_MAX;
+        int first_ok = 1, have = 0;
+        dec_syndromes(c, yH);
+        for (;;) {
+            uint64_t bound;
+            if (rules == 2) bound = (T >= 63) ? UINT64_MAX : ((uint64_t)1 << T);
+            else bound = (uint64_t)(int64_t)pattern_bound(T);   /* (1 << T) - 1 on an int, wrapped */
+            if (rules != 2 && pattern_bound(T) < 0) bound = 0;
+            if (!(i < bound)) break;
+            memcpy(word, yH, (size_t)n);
+            for (int b = 0; b < 63 && b < np; ++b)
+                if ((i >> b) & 1) word[pidx[b]] ^= 1;
+            dec_alter_syndromes(c, word);
+            ++n_dec;
+            const int success = dec_decode(c, word, x);
+            if (!i && !success) first_ok = 0;
+            if (success) {
+                if (ext) {
+                    uint8_t p = 0;
+                    for (int q = 0; q < n; ++q) p ^= x[q];
+                    x[n] = p;
+                }
+                mm = 0;
+                double l = 0;
+                for (int q = 0; q < ne; ++q)
+                    if (yH[q] != x[q]) { ++mm; l += alpha[q]; }
+                if (!i || !first_ok || rules == 2) mm0 = mm;
+                if (l < l0) {
+                    memcpy(res, x, (size_t)ne);
+                    have = 1;
+                    l0 = l;
+                    {   /* calcRightSide */
+                        const long border = d - (mm + mm0) / 2;
+                        double rs = 0;
+                        long cnt = 0, q = 0;
+                        while (cnt < border && q < ne) {
+                            if (yH[sidx[q]] == x[sidx[q]]) { rs += skey[q]; ++cnt; }
+                            ++q;
+                        }
+                        if (l < rs) { if (trials) trials[f] = (uint32_t)n_dec; goto done; }
+                    }
+                    for (;;) {   /* while (j <= n-1-t && l >= calcT(j)) */
+                        if (!(j <= ne - 1 - t)) break;
+                        const long border = (rules == 2) ? 0 : t - (mm + mm0) / 2;
+                        double tj = 0;
+                        long cnt = 0, q = 0;
+                        while (cnt < border && q < ne) {
+                            if (yH[sidx[q]] == x[sidx[q]]) { tj += skey[q]; ++cnt; }
+                            ++q;
+                        }
+                        for (int q2 = 0; q2 <= t; ++q2) tj += skey[j + q2];
+                        if (!(l >= tj)) break;
+                        ++j; ++n_cmp; ++n_sum;
+                    }
+                    T = (rules != 2 && c->J >= 0 && j > c->J) ? c->J : j;
+                    j = 0;
+                    ++n_cmp;
+                }
+            }
+            ++i;
+            n_cmp += (uint64_t)ne + 6;
+            n_sum += (uint64_t)ne + 1;
+        }
+        if (trials) trials[f] = (uint32_t)n_dec;
+    done:
+        if (cmp) cmp[f] = n_cmp;
+        if (sum) sum[f] = n_sum;
+        if (lbest) lbest[f] = have ? l0 : DBL_MAX;
+    }
+    free(alpha); free(skey); free(sidx); free(pidx); free(yH); free(x); free(word);
+}

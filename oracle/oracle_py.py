@@ -106,6 +106,8 @@ class Oracle(_Base):
         lib.ko_fun.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_double, _f64p, _u64p]
         lib.ko_std_sort_pairs.argtypes = [_f64p, _i32p, C.c_int]
         lib.ko_make_matrix.argtypes = [C.c_void_p, _u8p]
+        lib.ko_ext_gen_frames.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_long, _u8p, _u8p, _f64p]
+        lib.ko_ext_kaneko_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, _f64p, C.c_long, _u8p, _u32p, _u64p, _u64p, _f64p]
         self.h = lib.ko_create(m, t)
         if not self.h:
             raise ValueError("Invalid values of arguments")
@@ -137,6 +139,27 @@ class Oracle(_Base):
         fn = self.lib.ko_kaneko_decode2 if two_arg else self.lib.ko_kaneko_decode
         fn(self.h, y, C.c_long(B), decided, trials, cmp_, sum_)
         return decided, trials, cmp_, sum_
+
+    # ---- extended codes / exact rules: OUR definition (the reference has neither), see kaneko_oracle.c
+    def ext_gen_frames(self, ebn0_db, B, ext=1):
+        ne = self.n + ext
+        info = np.zeros((B, self.k), np.uint8)
+        cw = np.zeros((B, ne), np.uint8)
+        y = np.zeros((B, ne), np.float64)
+        self.lib.ko_ext_gen_frames(self.h, ext, C.c_double(ebn0_db), C.c_long(B), info, cw, y)
+        return info, cw, y
+
+    def ext_kaneko_decode(self, y, ext=1, rules=0, llr_snr_db=0.5):
+        y = np.ascontiguousarray(y, np.float64)
+        B, ne = y.shape
+        assert ne == self.n + ext
+        decided = np.zeros((B, ne), np.uint8)
+        trials = np.zeros(B, np.uint32)
+        cmp_ = np.zeros(B, np.uint64)
+        sum_ = np.zeros(B, np.uint64)
+        lbest = np.zeros(B, np.float64)
+        self.lib.ko_ext_kaneko_decode(self.h, ext, rules, C.c_double(llr_snr_db), y, C.c_long(B), decided, trials, cmp_, sum_, lbest)
+        return decided, trials, cmp_, sum_, lbest
 
     def fun(self, p, e, max_snr=5.0):
         rows = np.zeros((64, 6), np.float64)

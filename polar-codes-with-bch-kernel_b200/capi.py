@@ -29,14 +29,16 @@ POINT_FIELDS = ("frames", "frame_errors", "bit_errors", "trials", "cmp", "sum", 
 #: every symbol include/pk_capi.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = (
     "pk_last_error pk_device_count pk_code_create pk_code_create_host pk_code_destroy pk_code_info pk_code_tables "
-    "pk_code_uses_lut pk_code_set_lut pk_code_class_table_check pk_code_coset_table pk_encode_batch pk_bch_decode_batch pk_kaneko_create "
+    "pk_code_uses_lut pk_code_set_lut pk_code_class_table_check pk_code_coset_table pk_encode_batch pk_bch_decode_batch pk_kaneko_create pk_kaneko_create_ext "
     "pk_kaneko_destroy pk_kaneko_set_variant pk_kaneko_set_frames_per_grab pk_kaneko_set_phase_a_limit pk_kaneko_launch_geometry pk_kaneko_decode_batch "
     "pk_kaneko_decode_batch_async pk_kaneko_wait pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames pk_generate_frames_dev "
     "pk_kaneko_run_point pk_make_kernel_matrix pk_launch_count pk_launch_count_reset "
     "pk_polar_create pk_polar_destroy pk_polar_info pk_polar_trellis_profile pk_make_ebch_kernel pk_polar_encode_batch "
     "pk_polar_kernel_llrs pk_polar_decode_batch pk_polar_decode_batch_dev "
     "pk_comm_create pk_comm_unique_id pk_comm_create_rank pk_comm_destroy pk_comm_size pk_comm_rank pk_comm_local_devices pk_comm_stream "
-    "pk_allreduce_point pk_comm_sync pk_comm_kaneko_create pk_comm_kaneko_destroy pk_comm_kaneko_local pk_comm_run_point"
+    "pk_allreduce_point pk_comm_sync pk_comm_kaneko_create pk_comm_kaneko_destroy pk_comm_kaneko_local pk_comm_run_point "
+    "pk_kproc_create pk_kproc_destroy pk_kproc_info pk_kproc_get_llrs pk_kproc_kernel_llrs "
+    "pk_polar_run_frames_dev pk_polar_run_frames pk_polar_generate_frames_dev pk_polar_generate_frames"
 ).split()
 
 
@@ -71,6 +73,7 @@ def _load():
     lib.pk_encode_batch.argtypes = [vp, vp, l, vp]
     lib.pk_bch_decode_batch.argtypes = [vp, vp, l, vp, vp]
     lib.pk_kaneko_create.argtypes = [vp, d, l, l, pp]
+    lib.pk_kaneko_create_ext.argtypes = [vp, d, l, l, i, i, pp]
     lib.pk_kaneko_destroy.argtypes = [vp]
     lib.pk_kaneko_destroy.restype = None
     lib.pk_kaneko_set_frames_per_grab.argtypes = [vp, i]
@@ -115,6 +118,16 @@ def _load():
     lib.pk_comm_kaneko_local.argtypes = [vp, i]
     lib.pk_comm_kaneko_local.restype = vp
     lib.pk_comm_run_point.argtypes = [vp, d, i, u64, l, l, vp]
+    lib.pk_polar_run_frames_dev.argtypes = [vp, d, i, u64, u64, l, vp, vp]
+    lib.pk_polar_run_frames.argtypes = [vp, d, i, u64, u64, l, vp]
+    lib.pk_polar_generate_frames_dev.argtypes = [vp, d, i, u64, u64, l, vp, vp, vp, vp]
+    lib.pk_polar_generate_frames.argtypes = [vp, d, i, u64, u64, l, vp, vp, vp]
+    lib.pk_kproc_create.argtypes = [i, i, l, i, pp]
+    lib.pk_kproc_destroy.argtypes = [vp]
+    lib.pk_kproc_destroy.restype = None
+    lib.pk_kproc_info.argtypes = [vp, ip, vp, vp, vp]
+    lib.pk_kproc_get_llrs.argtypes = [vp, i, i, vp, vp, vp, C.POINTER(l)]
+    lib.pk_kproc_kernel_llrs.argtypes = [vp, vp, vp, l, vp, C.POINTER(l)]
     lib.pk_launch_count.restype = u64
     lib.pk_launch_count_reset.restype = None
     return lib
@@ -223,12 +236,13 @@ class Code:
 class Kaneko:
     """pk_kaneko handle (KanekoKernelProcessor): J < 0 = HEAD semantics, J >= 0 = capped variant."""
 
-    def __init__(self, code, J=-1, llr_snr_db=0.5, max_trials=0):
+    def __init__(self, code, J=-1, llr_snr_db=0.5, max_trials=0, extended=False, rules=0):
         self.code = code
         h = C.c_void_p()
-        _check(lib.pk_kaneko_create(code.h, float(llr_snr_db), int(J), int(max_trials), C.byref(h)))
+        _check(lib.pk_kaneko_create_ext(code.h, float(llr_snr_db), int(J), int(max_trials), int(bool(extended)), int(rules), C.byref(h)))
         self.h = h
         self.J = J
+        self.n = code.n + int(bool(extended))   # frame length (extended code: overall parity at position n)
 
     def close(self):
         if getattr(self, "h", None) and lib is not None:
@@ -255,10 +269,10 @@ class Kaneko:
     # ---- replay mode, host buffers (H2D / D2H inside the call)
     def decode(self, y, decided=None, want_recs=True):
         y = np.ascontiguousarray(y, np.float64)
-        assert y.ndim == 2 and y.shape[1] == self.code.n
+        assert y.ndim == 2 and y.shape[1] == self.n
         B = y.shape[0]
         if decided is None:
-            decided = np.zeros((B, self.code.n), np.uint8)
+            decided = np.zeros((B, self.n), np.uint8)
         trials = np.zeros(B, np.uint32)
         recs = np.zeros(B, FRAME_REC) if want_recs else None
         tot = np.zeros(8, np.uint64)
@@ -295,8 +309,8 @@ class Kaneko:
 
     def generate_frames(self, ebn0_db, snr_index, seed, first_frame, nframes):
         info = np.zeros((nframes, self.code.k), np.uint8)
-        cw = np.zeros((nframes, self.code.n), np.uint8)
-        y = np.zeros((nframes, self.code.n), np.float64)
+        cw = np.zeros((nframes, self.n), np.uint8)
+        y = np.zeros((nframes, self.n), np.float64)
         _check(lib.pk_generate_frames(self.h, float(ebn0_db), int(snr_index), int(seed), int(first_frame), int(nframes), _np_ptr(info), _np_ptr(cw), _np_ptr(y)))
         return info, cw, y
 
@@ -379,6 +393,48 @@ class CommKaneko:
         return dict(zip(POINT_FIELDS, (int(v) for v in tot)))
 
 
+class KanekoKernelProc:
+    """pk_kproc: Kaneko decoding as the kernel processor (CKernProcLLR) of the (2^m) x (2^m) extended-BCH kernel."""
+
+    def __init__(self, m, device=0, max_trials=0, enum_dim=-1):
+        h = C.c_void_p()
+        _check(lib.pk_kproc_create(int(m), int(device), int(max_trials), int(enum_dim), C.byref(h)))
+        self.h = h
+        sz = C.c_int()
+        _check(lib.pk_kproc_info(h, C.byref(sz), None, None, None))
+        self.size = sz.value
+        self.mode = np.zeros(self.size, np.int32)
+        self.t = np.zeros(self.size, np.int32)
+        self.nextra = np.zeros(self.size, np.int32)
+        _check(lib.pk_kproc_info(h, C.byref(sz), _np_ptr(self.mode), _np_ptr(self.t), _np_ptr(self.nextra)))
+
+    def close(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib.pk_kproc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def get_llrs(self, phase, known, chan):
+        """known, chan: [l][stride] -> (out [stride], truncated searches)"""
+        known = np.ascontiguousarray(known, np.uint8)
+        chan = np.ascontiguousarray(chan, np.float32)
+        stride = chan.shape[1]
+        out = np.zeros(stride, np.float32)
+        tr = C.c_long()
+        _check(lib.pk_kproc_get_llrs(self.h, stride, int(phase), _np_ptr(known), _np_ptr(chan), _np_ptr(out), C.byref(tr)))
+        return out, tr.value
+
+    def kernel_llrs(self, chan, u):
+        """chan, u: [B][l] -> (out [B][l], truncated searches)"""
+        chan = np.ascontiguousarray(chan, np.float32)
+        u = np.ascontiguousarray(u, np.uint8)
+        out = np.zeros(chan.shape, np.float32)
+        tr = C.c_long()
+        _check(lib.pk_kproc_kernel_llrs(self.h, _np_ptr(chan), _np_ptr(u), chan.shape[0], _np_ptr(out), C.byref(tr)))
+        return out, tr.value
+
+
 def counters_from_recs(recs, n):
     """(decodingCount, comparisonCount, summCount) per frame from pk_frame_rec records."""
     tr = recs["trials"].astype(np.uint64)
@@ -453,3 +509,19 @@ class Polar:
 
     def decode_dev(self, d_llr, B, d_count, d_inf, d_cw=None, d_metric=None, stream=None):
         _check(lib.pk_polar_decode_batch_dev(self.h, d_llr, B, d_count, d_inf, d_cw, d_metric, stream))
+
+    # ---- generation mode (the simulator loop on the device)
+    def run_frames_dev(self, ebn0_db, snr_index, seed, first_frame, nframes, d_totals, stream=None):
+        _check(lib.pk_polar_run_frames_dev(self.h, float(ebn0_db), int(snr_index), int(seed), int(first_frame), int(nframes), d_totals, stream))
+
+    def run_frames(self, ebn0_db, snr_index, seed, first_frame, nframes):
+        tot = np.zeros(8, np.uint64)
+        _check(lib.pk_polar_run_frames(self.h, float(ebn0_db), int(snr_index), int(seed), int(first_frame), int(nframes), _np_ptr(tot)))
+        return dict(zip(POINT_FIELDS, (int(v) for v in tot)))
+
+    def generate_frames(self, ebn0_db, snr_index, seed, first_frame, nframes):
+        info = np.zeros((nframes, self.K), np.uint8)
+        cw = np.zeros((nframes, self.N), np.uint8)
+        llr = np.zeros((nframes, self.N), np.float32)
+        _check(lib.pk_polar_generate_frames(self.h, float(ebn0_db), int(snr_index), int(seed), int(first_frame), int(nframes), _np_ptr(info), _np_ptr(cw), _np_ptr(llr)))
+        return info, cw, llr

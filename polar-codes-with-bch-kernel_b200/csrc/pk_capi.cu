@@ -78,6 +78,9 @@ struct pk_kaneko {
     long grec_cap = 0;
 };
 
+// frame length: the BCH length, plus the overall-parity position of an extended code (pk_kaneko_create_ext)
+static inline int frame_len(const pk_kaneko *d) { return d->code->n + d->kp.ext; }
+
 extern "C" {
 
 const char *pk_last_error(void) { return g_err.c_str(); }
@@ -319,7 +322,12 @@ int pk_bch_decode_batch(pk_code *c, const uint8_t *words, long B, uint8_t *answe
 
 // ------------------------------------------------------------------ Kaneko handle
 int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_kaneko **out) {
+    return pk_kaneko_create_ext(c, llr_snr_db, J, max_trials, 0, 0, out);
+}
+
+int pk_kaneko_create_ext(pk_code *c, double llr_snr_db, long J, long max_trials, int extended, int rules, pk_kaneko **out) {
     if (!out) return fail(PK_ERR_ARG, "out is NULL");
+    if ((extended != 0 && extended != 1) || rules < 0 || rules > 2) return fail(PK_ERR_ARG, "pk_kaneko_create_ext: extended in {0,1}, rules in {0,1,2}");
     *out = nullptr;
     int rc = need_kernels(c);
     if (rc) return rc;
@@ -330,10 +338,11 @@ int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_
     d->code = c;
     {   // sd = sqrt(1 / (pow(10, snr/10) * 2 * k / n)); alpha = 2*y / pow(sd, 2)
         // (KanekoKernelProcessor.cpp:20,337) -- same expression, same operand types.
-        long k = c->k, n = c->n;
+        long k = c->k, n = c->n + extended;
         double sd = sqrt(1 / (pow(10, llr_snr_db / 10) * 2 * k / n));
         d->kp.llr_den = pow(sd, 2);
     }
+    d->kp.ext = extended;
     d->kp.J = (J < 0 || J >= c->n) ? -1 : (int)J;
     d->kp.max_trials = (max_trials <= 0 || max_trials > 0x7FFFFFFFL) ? 0x7FFFFFFFu : (uint32_t)max_trials;
     d->kp.frames_per_grab = 2;
@@ -351,8 +360,8 @@ int pk_kaneko_create(pk_code *c, double llr_snr_db, long J, long max_trials, pk_
         d->kp.solo_patterns = d->mode == PK_MODE_ALG ? 16384u : 65536u;
         d->kp.epoch = 0;
     }
-    d->kp.variant = 0;
-    d->kp.extra_ops = 0;
+    d->kp.variant = rules;
+    d->kp.extra_ops = rules == 1 ? (uint32_t)(2 * (c->n + extended) + 1) : 0u;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, c->device);
     if (e == cudaSuccess) e = c->ks->geom_kaneko(d->mode, c->nk, prop.multiProcessorCount, d->geom4);
@@ -396,8 +405,9 @@ int pk_kaneko_set_frames_per_grab(pk_kaneko *d, int g) {
 // 1: KanekoKernelProcessor::decode(word, res), the file-mode flavour of main.cpp:158
 int pk_kaneko_set_variant(pk_kaneko *d, int two_argument) {
     if (!d) return fail(PK_ERR_ARG, "NULL handle");
+    if (d->kp.variant == 2) return fail(PK_ERR_ARG, "handle runs the exact rules (pk_kaneko_create_ext)");
     d->kp.variant = two_argument ? 1 : 0;
-    d->kp.extra_ops = two_argument ? (uint32_t)(2 * d->code->n + 1) : 0u;
+    d->kp.extra_ops = two_argument ? (uint32_t)(2 * frame_len(d) + 1) : 0u;
     return PK_OK;
 }
 
@@ -443,11 +453,11 @@ static int launch_pairs(pk_kaneko *d, int slot, bool gen, PkIo io, long B, cudaS
         if (gen) {
             part.gp.first_frame = io.gp.first_frame + (uint64_t)off;
             if (io.d_info) part.d_info = io.d_info + off * c->k;
-            if (io.d_cw) part.d_cw = io.d_cw + off * c->n;
-            if (io.d_y) part.d_y = io.d_y + off * c->n;
+            if (io.d_cw) part.d_cw = io.d_cw + off * frame_len(d);
+            if (io.d_y) part.d_y = io.d_y + off * frame_len(d);
         } else {
-            part.y = io.y + off * c->n;
-            part.decided = io.decided + off * c->n;
+            part.y = io.y + off * frame_len(d);
+            part.decided = io.decided + off * frame_len(d);
             if (io.trials) part.trials = io.trials + off;
         }
         if (io.recs) part.recs = io.recs + off;
@@ -483,7 +493,7 @@ int pk_kaneko_decode_batch_dev(pk_kaneko *d, const double *d_y, long B, uint8_t 
 
 static int ensure_pipeline(pk_kaneko *d) {
     if (d->chunk) return PK_OK;
-    const int n = d->code->n;
+    const int n = frame_len(d);
     long chunk = (32L << 20) / (8L * n);
     chunk = std::max(1024L, chunk / 1024 * 1024);
     for (int s = 0; s < 2; ++s) {
@@ -500,7 +510,7 @@ static int ensure_pipeline(pk_kaneko *d) {
 static int enqueue_batch(pk_kaneko *d, const double *y, long B, uint8_t *decided, uint32_t *trials, pk_frame_rec *recs) {
     int rc = ensure_pipeline(d);
     if (rc) return rc;
-    const int n = d->code->n;
+    const int n = frame_len(d);
     if (!d->pending) {
         // first batch since the last wait: zero the device totals ahead of both streams
         if (!d->ev_zero) PK_CUDA(cudaEventCreateWithFlags(&d->ev_zero, cudaEventDisableTiming));
@@ -582,8 +592,8 @@ int pk_kaneko_decode_batch(pk_kaneko *d, const double *y, long B, uint8_t *decid
 }
 
 // ------------------------------------------------------------------ generation mode
-static double channel_sigma(const pk_code *c, double ebn0_db) {
-    long k = c->k, n = c->n;
+static double channel_sigma(const pk_kaneko *d, double ebn0_db) {
+    long k = d->code->k, n = frame_len(d);
     return sqrt(1 / (pow(10, ebn0_db / 10) * 2 * k / n));   // dataForPlot.cpp:45
 }
 
@@ -594,7 +604,7 @@ int pk_kaneko_run_frames_dev(pk_kaneko *d, double ebn0_db, int snr_index, uint64
     PK_CUDA(cudaSetDevice(d->code->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream[0];
     PkGenParams gp;
-    gp.sigma = channel_sigma(d->code, ebn0_db);
+    gp.sigma = channel_sigma(d, ebn0_db);
     gp.seed = seed;
     gp.first_frame = first_frame;
     gp.snr_index = (uint32_t)snr_index;
@@ -653,7 +663,7 @@ int pk_generate_frames_dev(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t
     PK_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream[0];
     PkGenParams gp;
-    gp.sigma = channel_sigma(c, ebn0_db);
+    gp.sigma = channel_sigma(d, ebn0_db);
     gp.seed = seed;
     gp.first_frame = first_frame;
     gp.snr_index = (uint32_t)snr_index;
@@ -671,11 +681,12 @@ int pk_generate_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t see
     double *d_y = nullptr;
     cudaError_t e = cudaSuccess;
     if (info) e = cudaMalloc(&d_info, (size_t)nframes * c->k);
-    if (e == cudaSuccess && cw) e = cudaMalloc(&d_cw, (size_t)nframes * c->n);
-    if (e == cudaSuccess && y) e = cudaMalloc(&d_y, (size_t)nframes * c->n * sizeof(double));
+    const size_t fl = (size_t)frame_len(d);
+    if (e == cudaSuccess && cw) e = cudaMalloc(&d_cw, (size_t)nframes * fl);
+    if (e == cudaSuccess && y) e = cudaMalloc(&d_y, (size_t)nframes * fl * sizeof(double));
     if (e == cudaSuccess) {
         PkGenParams gp;
-        gp.sigma = channel_sigma(c, ebn0_db);
+        gp.sigma = channel_sigma(d, ebn0_db);
         gp.seed = seed;
         gp.first_frame = first_frame;
         gp.snr_index = (uint32_t)snr_index;
@@ -683,8 +694,8 @@ int pk_generate_frames(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t see
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream[0]);
     if (e == cudaSuccess && info) e = cudaMemcpy(info, d_info, (size_t)nframes * c->k, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && cw) e = cudaMemcpy(cw, d_cw, (size_t)nframes * c->n, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && y) e = cudaMemcpy(y, d_y, (size_t)nframes * c->n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && cw) e = cudaMemcpy(cw, d_cw, (size_t)nframes * fl, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && y) e = cudaMemcpy(y, d_y, (size_t)nframes * fl * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d_info);
     cudaFree(d_cw);
     cudaFree(d_y);
@@ -701,7 +712,7 @@ int pk_kaneko_run_point(pk_kaneko *d, double ebn0_db, int snr_index, uint64_t se
     if (int rp = reject_pending(d)) return rp;
     std::memset(out, 0, sizeof(*out));
     if (e <= 0) return pk_kaneko_run_frames(d, ebn0_db, snr_index, seed, 0, p, nullptr, out);
-    const int n = d->code->n;
+    const int n = frame_len(d);
     long done = 0, chunk = 4096;
     std::vector<pk_frame_rec> recs;
     while (done < p && (long)out->frame_errors < e) {

@@ -202,6 +202,10 @@ struct KanekoWarp {
         uint32_t S0[SW];   // syndromes / coset index of yH (uniform)
         uint32_t aug[NA];  // lane b: column of the b-th least reliable position | its one-hot mask
         uint32_t flags;
+        // extended code (kp.ext): position N carries the overall parity of the BCH codeword
+        uint32_t py;       // parity of ALL hard decisions (uniform)
+        int rp;            // rank of position N in the reliability order (patterns skip it); huge when not extended
+        uint32_t topmask;  // mask of the BCH positions inside word NW-1 (all ones when not extended)
     };
     struct Search {      // the sequential state of the reference loop (uniform)
         double l0;
@@ -231,6 +235,7 @@ struct KanekoWarp {
     __device__ static void setup(const Tables &tb, const WarpMem &wm, const double (&yv)[NW], const PkKanekoParams &kp,
                                  Frame &f) {
         const int lane = threadIdx.x & 31;
+        const int NE = N + kp.ext;   // positions of the (possibly extended) code; NE <= 32 NW always
         f.flags = 0;
         unsigned long long keyb[NW];
         bool hard[NW];
@@ -238,7 +243,7 @@ struct KanekoWarp {
         for (int w = 0; w < NW; ++w) {
             const int p = lane + 32 * w;
             const double a = (2.0 * yv[w]) / kp.llr_den;      // alpha_i = 2 y_i / sd^2, IEEE divide
-            const bool valid = p < N;
+            const bool valid = p < NE;
             hard[w] = valid && !(a <= 0.0);                   // yH = (alpha <= 0) ? 0 : 1
             const double key = fabs(a);
             keyb[w] = (unsigned long long)__double_as_longlong(key);
@@ -260,7 +265,7 @@ struct KanekoWarp {
 #pragma unroll
             for (int w = 0; w < NW; ++w) keyd[w] = __longlong_as_double((long long)keyb[w]);
 #pragma unroll 8
-            for (int q = 0; q < N; ++q) {
+            for (int q = 0; q < NE; ++q) {
                 const double kq = wm.alpha[q];
 #pragma unroll
                 for (int w = 0; w < NW; ++w) rank[w] += (kq < keyd[w]) ? 1 : 0;
@@ -268,7 +273,7 @@ struct KanekoWarp {
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const int p = lane + 32 * w;
-                if (p < N) {
+                if (p < NE) {
                     wm.skey[rank[w]] = keyd[w];
                     wm.sidx[rank[w]] = (uint8_t)p;
                 }
@@ -278,7 +283,7 @@ struct KanekoWarp {
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const int p = lane + 32 * w;
-                if (p < N) clash |= (wm.sidx[rank[w]] != (uint8_t)p);
+                if (p < NE) clash |= (wm.sidx[rank[w]] != (uint8_t)p);
             }
             if (__any_sync(PK_FULL, clash)) {
                 // exact pass: integer compares of the bit patterns, ties broken by position
@@ -288,37 +293,37 @@ struct KanekoWarp {
                 for (int w = 0; w < NW; ++w) rank[w] = 0;
                 const unsigned long long *ak = reinterpret_cast<const unsigned long long *>(wm.alpha);
 #pragma unroll 4
-                for (int q = 0; q < N; ++q) {
+                for (int q = 0; q < NE; ++q) {
                     const unsigned long long kq = ak[q];
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {
                         const int p = lane + 32 * w;
                         const bool eq = (kq == keyb[w]);
                         rank[w] += (kq < keyb[w] || (eq && q < p)) ? 1 : 0;
-                        tie |= eq && (q != p) && (p < N);
+                        tie |= eq && (q != p) && (p < NE);
                     }
                 }
 #pragma unroll
                 for (int w = 0; w < NW; ++w) {
                     const int p = lane + 32 * w;
-                    if (p < N) {
+                    if (p < NE) {
                         wm.skey[rank[w]] = keyd[w];
                         wm.sidx[rank[w]] = (uint8_t)p;
                     }
                 }
                 if (__any_sync(PK_FULL, tie)) {
                     f.flags |= PK_FLAG_SORT_TIE;
-                    if (N > 16) {
+                    if (NE > 16) {
                         // equal keys: std::sort's order is an artefact of libstdc++'s introsort -- replay it on one lane
                         __syncwarp();
                         if (lane == 0) {
-                            for (int i = 0; i < N; ++i) { wm.skey[i] = wm.alpha[i]; wm.sidx[i] = (uint8_t)i; }
-                            pk_stdsort::sort(wm.skey, wm.sidx, N);
+                            for (int i = 0; i < NE; ++i) { wm.skey[i] = wm.alpha[i]; wm.sidx[i] = (uint8_t)i; }
+                            pk_stdsort::sort(wm.skey, wm.sidx, NE);
                         }
                     }
                 }
             }
-            if (lane == 0) wm.skey[N] = 0.0;  // the reference reads one past the end in calcT(n-t); value unused
+            if (lane == 0) wm.skey[NE] = 0.0;  // the reference reads one past the end in calcT(n-t); value unused
         }
         __syncwarp();
         // prefix sums of the sorted reliabilities: pref[m] <= l of ANY flip set of weight m (used only to
@@ -330,14 +335,14 @@ struct KanekoWarp {
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const int r = lane + 32 * w;
-                double v = (r < N) ? wm.skey[r] : 0.0;
+                double v = (r < NE) ? wm.skey[r] : 0.0;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
                     const double t = __shfl_up_sync(PK_FULL, v, off);
                     if (lane >= off) v += t;
                 }
                 v += carry;
-                if (r < N) wm.pref[r + 1] = v;
+                if (r < NE) wm.pref[r + 1] = v;
                 carry = __shfl_sync(PK_FULL, v, 31);
             }
         }
@@ -349,7 +354,7 @@ struct KanekoWarp {
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const int p = lane + 32 * w;
-                if (hard[w]) {
+                if (hard[w] && p < N) {   // (the parity position of an extended code is not part of the BCH word)
 #pragma unroll
                     for (int s = 0; s < SW; ++s) acc[s] ^= tb.col[p * SW + s];
                 }
@@ -357,12 +362,27 @@ struct KanekoWarp {
 #pragma unroll
             for (int s = 0; s < SW; ++s) f.S0[s] = __reduce_xor_sync(PK_FULL, acc[s]);
         }
+        // extended code: parity of all hard decisions, and where the parity position sits in the reliability order --
+        // test patterns flip BCH positions only, so pattern bit b is the b-th least reliable position NOT counting it
+        {
+            uint32_t par = 0;
+            f.rp = 0x7FFFFFFF;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                par ^= f.YH[w];
+                const int r = lane + 32 * w;
+                const uint32_t hit = __ballot_sync(PK_FULL, kp.ext && r < NE && wm.sidx[r] == (uint8_t)N);
+                if (hit) f.rp = 32 * w + __ffs(hit) - 1;
+            }
+            f.py = __popc(par) & 1u;
+            f.topmask = ~((uint32_t)kp.ext << (N & 31));
+        }
         // lane b keeps the augmented column of the b-th least reliable position (pattern bit b flips that
         // position, calcError :36-51).  Bits >= 31 never occur: the bound never exceeds 2^31 - 1.
 #pragma unroll
         for (int a = 0; a < NA; ++a) f.aug[a] = 0;
         if (lane < 31 && lane < N) {
-            const int p = wm.sidx[lane];
+            const int p = wm.sidx[lane + (lane >= f.rp ? 1 : 0)];
 #pragma unroll
             for (int s = 0; s < SW; ++s) f.aug[s] = tb.col[p * SW + s];
 #pragma unroll
@@ -407,16 +427,17 @@ struct KanekoWarp {
     __device__ static bool commit(Search &s, const WarpMem &wm, const PkKanekoParams &kp, double ls, int ms,
                                   const uint32_t (&Fs)[NW], uint32_t is) {
         const int lane = threadIdx.x & 31;
-        if (is == 0 || !s.first_ok) s.m0 = ms;   // :374
+        const int NE = N + kp.ext;
+        if (is == 0 || !s.first_ok || kp.variant == 2) s.m0 = ms;   // :374 (exact rules: m0 = m, the bound of the candidate alone)
         s.l0 = ls;
         s.have = true;
 #pragma unroll
         for (int w = 0; w < NW; ++w) s.bestF[w] = Fs[w];
         {   // calcRightSide (:54-67)
-            const int border = (2 * T + 1) - (ms + s.m0) / 2;
+            const int border = (2 * T + 1 + kp.ext) - (ms + s.m0) / 2;   // d = 2t+1 (+1: overall parity)
             double rs = 0.0;
             int cnt = 0, j = 0;
-            while (cnt < border && j < N) {
+            while (cnt < border && j < NE) {
                 const int p = wm.sidx[j];
                 if (!pk_getbit<NW>(Fs, p)) { rs += wm.skey[j]; ++cnt; }
                 ++j;
@@ -426,17 +447,17 @@ struct KanekoWarp {
         // while (l >= calcT(j) && j <= n-1-t) ++j   (:384-390, calcT :110-126); lanes try 32 j at a time
         int jn;
         {
-            const int border = T - (ms + s.m0) / 2;
+            const int border = (kp.variant == 2) ? 0 : T - (ms + s.m0) / 2;
             double bs = 0.0;
             int cnt = 0, k = 0;
-            while (cnt < border && k < N) {
+            while (cnt < border && k < NE) {
                 const int p = wm.sidx[k];
                 if (!pk_getbit<NW>(Fs, p)) { bs += wm.skey[k]; ++cnt; }
                 ++k;
             }
             // 3-argument flavour: j <= n-1-t is part of the loop condition (:384).  The 2-argument flavour (:257) has no
             // such test and would read past the reliability array (undefined behaviour) -- flagged, same stop.
-            const int jmax = N - 1 - T;
+            const int jmax = NE - 1 - T;
             jn = jmax + 1;
             for (int c0 = 0; c0 <= jmax; c0 += 32) {
                 const int jj = c0 + lane;
@@ -453,14 +474,27 @@ struct KanekoWarp {
         s.tsteps += (uint32_t)jn;
         ++s.nimpr;
         if (kp.variant) {
-            if (jn == N - T) s.flags |= PK_FLAG_REF_UNDEFINED;
-            s.bound = pk_pattern_bound2(jn);                   // T = j (:264)
+            if (kp.variant == 1 && jn == NE - T) s.flags |= PK_FLAG_REF_UNDEFINED;
+            s.bound = pk_pattern_bound2(jn);                   // T = j (:264); exact rules: every subset of the j least reliable
         } else {
             const int Tn = (kp.J >= 0 && jn > kp.J) ? kp.J : jn;   // :392-393
             s.bound = pk_pattern_bound(Tn);
         }
         return false;
     }
+
+    // extended code: the decided word's parity position is the parity of its BCH part, so its flip bit is
+    // parity(yH) ^ parity(F over the BCH positions)
+    __device__ static __forceinline__ void ext_bit(const Frame &f, const PkKanekoParams &kp, uint32_t (&F)[NW]) {
+        if (kp.ext) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) x ^= F[w];
+            F[NW - 1] |= ((f.py ^ (uint32_t)__popc(x)) & 1u) << (N & 31);
+        }
+    }
+    // reliability of the position pattern bit b flips (the b-th least reliable BCH position)
+    __device__ static __forceinline__ double pat_key(const WarpMem &wm, const Frame &f, int b) { return wm.skey[b + (b >= f.rp ? 1 : 0)]; }
 
     // coset-table entry -> located positions; returns the verdict
     __device__ static __forceinline__ bool lut_positions(uint32_t e, uint32_t (&A)[NW]) {
@@ -579,10 +613,10 @@ struct KanekoWarp {
             // m = d_H(yH, x) (calcM :89-97), l = sum_{yH != x} alpha in index order (calcL :69-77)
             int m = 0;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                F[w] = Vb[SW + w] ^ Vl[SW + w] ^ A[w];
-                m += __popc(F[w]);
-            }
+            for (int w = 0; w < NW; ++w) F[w] = Vb[SW + w] ^ Vl[SW + w] ^ A[w];
+            ext_bit(f, kp, F);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) m += __popc(F[w]);
             double l = DBL_MAX;
             if (succ && may_improve(wm, m, s.l0)) l = calc_l(wm, F);
             if (base == 0) s.first_ok = __shfl_sync(PK_FULL, succ ? 1 : 0, 0) != 0;   // :371
@@ -670,7 +704,7 @@ struct KanekoWarp {
             double ws = 0.0;
 #pragma unroll
             for (int b = 0; b < 5; ++b)
-                if (b < N && ((lane >> b) & 1)) ws += wm.skey[b];
+                if (b < N && ((lane >> b) & 1)) ws += pat_key(wm, f, b);
             wm.wl[lane] = ws;
         } else {
             // cm[j*M + b] = plane (over the 32 in-word patterns) of bit b of syndrome S_{j+1}
@@ -682,7 +716,7 @@ struct KanekoWarp {
                 for (int q = 0; q < 5; ++q) {
                     if (q < N) {
                         const uint32_t pat = (q == 0) ? 0xAAAAAAAAu : (q == 1) ? 0xCCCCCCCCu : (q == 2) ? 0xF0F0F0F0u : (q == 3) ? 0xFF00FF00u : 0xFFFF0000u;
-                        const uint32_t col = tb.col[(int)wm.sidx[q] * SW + word];
+                        const uint32_t col = tb.col[(int)wm.sidx[q + (q >= f.rp ? 1 : 0)] * SW + word];
                         plane ^= ((col >> sh) & 1u) ? pat : 0u;
                     }
                 }
@@ -719,7 +753,7 @@ struct KanekoWarp {
         if constexpr (LUT || CT) {
 #pragma unroll
             for (int b = 0; b < 5; ++b)
-                if (5 + b < N && ((lane >> b) & 1)) lsum += wm.skey[5 + b];
+                if (5 + b < N && ((lane >> b) & 1)) lsum += pat_key(wm, f, 5 + b);
         }
         // pattern bits 10.. = base
         {
@@ -769,7 +803,7 @@ struct KanekoWarp {
                 while (hb) {
                     const int b = __ffs(hb) - 1;
                     hb &= hb - 1;
-                    bsum += wm.skey[10 + b];
+                    bsum += pat_key(wm, f, 10 + b);
                 }
             }
             // Per-lane filter of decodable trials (bits of `ok`) against the search state `st`, with an APPROXIMATE l
@@ -789,7 +823,7 @@ struct KanekoWarp {
                         {   // within distance t of a known codeword: decodes to it again (see class-table mode below)
                             int dist = st.have ? 0 : 99;
 #pragma unroll
-                            for (int w2 = 0; w2 < NW; ++w2) dist += __popc(pat[w2] ^ st.bestF[w2]);
+                            for (int w2 = 0; w2 < NW; ++w2) dist += __popc((pat[w2] ^ st.bestF[w2]) & (w2 == NW - 1 ? f.topmask : PK_FULL));
                             bool known = dist <= T;
 #pragma unroll
                             for (int k = 0; k < KR; ++k) {
@@ -843,7 +877,7 @@ struct KanekoWarp {
                             // improvement -- most decodable patterns of a low-SNR frame are of this kind.
                             int dist = st.have ? 0 : 99;
 #pragma unroll
-                            for (int w2 = 0; w2 < NW; ++w2) dist += __popc(pat[w2] ^ st.bestF[w2]);
+                            for (int w2 = 0; w2 < NW; ++w2) dist += __popc((pat[w2] ^ st.bestF[w2]) & (w2 == NW - 1 ? f.topmask : PK_FULL));
                             bool known = dist <= T;
 #pragma unroll
                             for (int k = 0; k < KR; ++k) {
@@ -898,7 +932,7 @@ struct KanekoWarp {
 #pragma unroll
                         for (int w2 = 0; w2 < NW; ++w2) {
                             const uint32_t pat = Ul[SW + w2] ^ Ub[SW + w2] ^ wm.pb[q * NW + w2];
-                            dist += __popc(pat ^ st.bestF[w2]);
+                            dist += __popc((pat ^ st.bestF[w2]) & (w2 == NW - 1 ? f.topmask : PK_FULL));
                             d0 += __popc(pat ^ rej[0][w2]);
                             d1 += __popc(pat ^ rej[1][w2]);
                         }
@@ -965,7 +999,7 @@ struct KanekoWarp {
                     int dist = st.have ? 0 : 99, d0 = 0, d1 = 0;
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {
-                        dist += __popc(P[w] ^ st.bestF[w]);
+                        dist += __popc((P[w] ^ st.bestF[w]) & (w == NW - 1 ? f.topmask : PK_FULL));
                         d0 += __popc(P[w] ^ rej[0][w]);
                         d1 += __popc(P[w] ^ rej[1][w]);
                     }
@@ -987,16 +1021,19 @@ struct KanekoWarp {
                     }
                 }
                 m = 0;
+                bool better = false;
 #pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    F[w] = P[w] ^ A[w];
-                    m += __popc(F[w]);
-                }
+                for (int w = 0; w < NW; ++w) F[w] = P[w] ^ A[w];
+                uint32_t Fb[NW];   // flip set over the BCH positions (what the known-codeword tests compare)
+#pragma unroll
+                for (int w = 0; w < NW; ++w) Fb[w] = F[w];
+                ext_bit(f, kp, F);
+#pragma unroll
+                for (int w = 0; w < NW; ++w) m += __popc(F[w]);
                 bool same = st.have;   // same codeword as the current best: l == l0 exactly, no improvement
 #pragma unroll
                 for (int w = 0; w < NW; ++w) same = same && (F[w] == st.bestF[w]);
                 if (same) return false;
-                bool better = false;
                 if (may_improve(wm, m, st.l0)) {
                     l = calc_l(wm, F);
                     better = l < st.l0;
@@ -1004,7 +1041,7 @@ struct KanekoWarp {
                 if constexpr (!LUT && !CT) {
                     if (!better) {   // remember the rejected codeword (uniform across the warp)
 #pragma unroll
-                        for (int w = 0; w < NW; ++w) { rej[1][w] = rej[0][w]; rej[0][w] = F[w]; }
+                        for (int w = 0; w < NW; ++w) { rej[1][w] = rej[0][w]; rej[0][w] = Fb[w]; }
                     }
                 }
                 return better;
@@ -1221,14 +1258,15 @@ struct PkWarpTotals {
 // blocks 0.. hold the info bits (128 per block), blocks 0x100+q the Box-Muller pair of positions 2q, 2q+1.
 template <int M, int NW, bool GEN>
 __device__ __forceinline__ void pk_load_frame(const PkIo &io, const PkDevTables &tb, long f, double *stage, uint32_t *w_u,
-                                              bool dump, double (&yv)[NW], uint32_t (&CW)[NW]) {
+                                              bool dump, double (&yv)[NW], uint32_t (&CW)[NW], int ext) {
     constexpr int N = (1 << M) - 1;
+    const int NE = N + ext;   // frame length: the extended code appends the overall parity at position N
     const int lane = threadIdx.x & 31;
     if constexpr (!GEN) {
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             const int p = lane + 32 * w;
-            yv[w] = (p < N) ? __ldg(io.y + f * N + p) : 0.0;
+            yv[w] = (p < NE) ? __ldg(io.y + f * NE + p) : 0.0;
             CW[w] = 0;
         }
     } else {
@@ -1265,8 +1303,14 @@ __device__ __forceinline__ void pk_load_frame(const PkIo &io, const PkDevTables 
         }
 #pragma unroll
         for (int w = 0; w < NW; ++w) CW[w] = __reduce_xor_sync(PK_FULL, cwp[w]);
+        if (ext) {   // overall parity of the BCH codeword
+            uint32_t x = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) x ^= CW[w];
+            CW[NW - 1] |= ((uint32_t)__popc(x) & 1u) << (N & 31);
+        }
         // BPSK + AWGN (addNoise, bchCoder.cpp:243-250): y = (c ? +1 : -1) + N(0, sigma^2), f64 Box-Muller
-        for (int q = lane; 2 * q < N; q += 32) {
+        for (int q = lane; 2 * q < NE; q += 32) {
             PkPhilox r = pk_philox(c0, c1, 0x100u + (uint32_t)q, io.gp.snr_index, k0, k1);
             const unsigned long long a = ((unsigned long long)r.c[0] << 32) | r.c[1];
             const unsigned long long b = ((unsigned long long)r.c[2] << 32) | r.c[3];
@@ -1277,13 +1321,13 @@ __device__ __forceinline__ void pk_load_frame(const PkIo &io, const PkDevTables 
             sincospi(2.0 * u2, &sn, &cs);
             const int p0 = 2 * q, p1 = 2 * q + 1;
             stage[p0] = (pk_getbit<NW>(CW, p0) ? 1.0 : -1.0) + io.gp.sigma * (rad * cs);
-            if (p1 < N) stage[p1] = (pk_getbit<NW>(CW, p1) ? 1.0 : -1.0) + io.gp.sigma * (rad * sn);
+            if (p1 < NE) stage[p1] = (pk_getbit<NW>(CW, p1) ? 1.0 : -1.0) + io.gp.sigma * (rad * sn);
         }
         __syncwarp();
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             const int p = lane + 32 * w;
-            yv[w] = (p < N) ? stage[p] : 0.0;
+            yv[w] = (p < NE) ? stage[p] : 0.0;
         }
         __syncwarp();
         if (dump) {
@@ -1293,9 +1337,9 @@ __device__ __forceinline__ void pk_load_frame(const PkIo &io, const PkDevTables 
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const int p = lane + 32 * w;
-                if (p < N) {
-                    if (io.d_cw) io.d_cw[f * N + p] = (uint8_t)((CW[w] >> lane) & 1u);
-                    if (io.d_y) io.d_y[f * N + p] = yv[w];
+                if (p < NE) {
+                    if (io.d_cw) io.d_cw[f * NE + p] = (uint8_t)((CW[w] >> lane) & 1u);
+                    if (io.d_y) io.d_y[f * NE + p] = yv[w];
                 }
             }
         }
@@ -1308,8 +1352,8 @@ __device__ __forceinline__ void pk_load_frame(const PkIo &io, const PkDevTables 
 template <int M, int NW, bool GEN>
 __device__ __forceinline__ void pk_emit(const PkIo &io, long f, const uint32_t (&YH)[NW], const uint32_t (&bestF)[NW],
                                         const uint32_t (&CW)[NW], uint32_t trials, uint32_t ecmp, uint32_t esum,
-                                        uint32_t flags, PkWarpTotals &tot) {
-    constexpr int N = (1 << M) - 1;
+                                        uint32_t flags, PkWarpTotals &tot, int ext) {
+    const int N = (1 << M) - 1 + ext;   // length of the (possibly extended) code
     const int lane = threadIdx.x & 31;
     uint32_t be = 0;
     if constexpr (!GEN) {
@@ -1385,7 +1429,7 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
         for (long f = (long)f0; f < f1; ++f) {
             double yv[NW];
             uint32_t CW[NW];
-            pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, true, yv, CW);
+            pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, true, yv, CW, kp.ext);
             if (GEN && io.dump_only) continue;
             typename KW::Frame fr;
             typename KW::Search s;
@@ -1418,7 +1462,7 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
                 KW::narrow(tabs, wm, kp, fr, s, next, 0xFFFFFFFFu, &next);
             }
             KW::search_finish(s);
-            pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot);
+            pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot, kp.ext);
         }
     }
     if (lane == 0) tot.flush(io.totals);
@@ -1444,7 +1488,7 @@ __device__ __forceinline__ void pk_st_vol(unsigned int *p, unsigned int v) { *re
 // bound, m0 and the counters are the master's business alone.  (Before this, one CTA ground through such a frame at
 // 16K patterns per 11 us while the other 147 SMs idled: the tail of every uncapped low-SNR launch.)
 template <int M, int T, bool LUT, bool GEN, bool CT = false>
-__global__ void __launch_bounds__(PkSmem<M, T, LUT, CT>::WB * 32, CT ? PkTraits<M, T>::MINB_CT : LUT ? 2 : PkTraits<M, T>::MINB)
+__global__ void __launch_bounds__(PkSmem<M, T, LUT, CT>::WB * 32, CT ? PkTraits<M, T>::MINB_CT : LUT ? 1 : PkTraits<M, T>::MINB)   // (coset-table mode: 16 warps, one CTA per SM next to its 64 KB table -- 128 registers, no spills)
 k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec *longs, long long_cap) {
     typedef PkSmem<M, T, LUT, CT> SM;
     typedef KanekoWarp<M, T, LUT, CT> KW;
@@ -1493,7 +1537,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
     long cur_frame = -1;
     auto load = [&](long f) {
         double yv[NW];
-        pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, false, yv, CW);   // dumps were written in phase A
+        pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, false, yv, CW, kp.ext);   // dumps were written in phase A
         KW::setup(tabs, wm, yv, kp, fr);
         cur_frame = f;
     };
@@ -1505,7 +1549,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
     long m_f = 0;
     PkMegaSlot *m_ms = nullptr;
     uint32_t *m_bits = nullptr;
-    uint32_t m_limit = 0, m_own = 0, m_start = 0, m_g0 = 0;
+    uint32_t m_limit = 0, m_cbase = 0, m_gen = 0, m_own = 0, m_start = 0, m_g0 = 0;
     typename KW::Search s;   // the master's sequential state, or a helper's snapshot
     // parked frames of this launch
     const bool all_coop = (n_long + n_big + n_huge) <= (unsigned long long)gridDim.x;
@@ -1522,17 +1566,44 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
         KW::unpark(s, rec);
         m_g0 = rec->base & ~1023u;   // the search's step grid (and chunk grid) starts here
         m_start = rec->base;
-        m_ms = nullptr; m_bits = nullptr; m_limit = 0;
+        m_ms = nullptr; m_bits = nullptr; m_limit = 0; m_cbase = 0; m_gen = 0;
         m_may_open = CH != 0;
         m_own = known_long ? 0u : kp.mega_after;
         m_late = from_late;
         m_active = true;
     };
+    // (re)open a window of PK_MEGA_WINDOW chunks at the master's position: fields + tagged bitmap words, then the state word
+    auto open_window = [&]() {
+        if (threadIdx.x == 0) pk_st_vol(&m_ms->state, 0u);
+        __threadfence();
+        __syncthreads();
+        m_gen = (m_gen + 1u) ? (m_gen + 1u) : 1u;
+        m_cbase = (m_start - m_g0) / CH;
+        m_limit = m_cbase + PK_MEGA_WINDOW;
+        for (uint32_t w = threadIdx.x; w < PK_MEGA_WORDS; w += blockDim.x) m_bits[w] = m_gen << 16;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            m_ms->gen = m_gen;
+            m_ms->frame = (unsigned int)m_f; m_ms->g0 = m_g0; m_ms->cbase = m_cbase; m_ms->limit = m_limit;
+            m_ms->pos = m_cbase; m_ms->next = m_cbase + 1; m_ms->bound = s.bound;
+            m_ms->l0 = s.l0; m_ms->have = s.have ? 1u : 0u;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) m_ms->bestF[w] = s.bestF[w];
+            m_ms->seq = 0;
+            __threadfence();
+            pk_st_vol(&m_ms->state, m_gen);
+        }
+    };
     auto end_master = [&]() {
-        if (m_ms && threadIdx.x == 0) pk_st_vol(&m_ms->finished, 1u);
+        if (m_ms && threadIdx.x == 0) {
+            pk_st_vol(&m_ms->state, 0u);
+            __threadfence();
+            atomicExch(&m_ms->owner, 0u);   // the slot is free again (its generation counter lives on in m_ms->gen)
+        }
         if (warp == 0) {
             KW::search_finish(s);
-            pk_emit<M, NW, GEN>(io, m_f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot);
+            pk_emit<M, NW, GEN>(io, m_f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot, kp.ext);
         }
         if (m_late) {
             __syncthreads();
@@ -1542,7 +1613,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
     };
 
     for (;;) {
-        uint32_t h_slot = 0, h_chunk = 0;
+        uint32_t h_slot = 0, h_chunk = 0, h_gen = 0;
         bool h_job = false;
         // ---------------- A: something to do
         if (!m_active && stage == 1) {
@@ -1570,7 +1641,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
                 const PkLongRec *rec = (idx < n_big - n_coop) ? longs + (long_cap - 1 - (long)(n_coop + idx)) : longs + (idx - (n_big - n_coop));
                 const long f = (long)rec->frame;
                 double yv[NW];
-                pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, false, yv, CW);
+                pk_load_frame<M, NW, GEN>(io, tb, f, wm.skey, w_u, false, yv, CW, kp.ext);
                 KW::setup(tabs, wm, yv, kp, fr);
                 KW::unpark(s, rec);
                 uint32_t start = rec->base;
@@ -1598,7 +1669,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
                 }
                 if (handed) continue;
                 KW::search_finish(s);
-                pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot);
+                pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot, kp.ext);
             }
             cur_frame = -1;   // the warps of this CTA hold different frames now
             __threadfence();
@@ -1609,7 +1680,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
         if (!m_active && stage == 3) {
             // end game: late frames as a master, else help a master, else wait for the masters or leave
             if (threadIdx.x == 0) {
-                uint32_t cmd = 0, a0 = 0, a1 = 0;   // 0 = look again, 1 = master of late frame a0, 2 = help slot a0 with chunk a1, 3 = leave
+                uint32_t cmd = 0, a0 = 0, a1 = 0, a2 = 0;   // 0 = look again, 1 = master of late frame a0, 2 = help slot a0 (generation a2) with chunk a1, 3 = leave
                 for (;;) {
                     const unsigned long long nl = pk_ld_vol(&ctl->n_late), ql = pk_ld_vol(&ctl->queue_late);
                     if (ql >= (nl < (unsigned long long)PK_LATE_CAP ? nl : (unsigned long long)PK_LATE_CAP)) break;
@@ -1618,17 +1689,19 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
                     atomicAdd(&ctl->masters, ~0ull);
                 }
                 if (!cmd && CH) {
-                    const unsigned long long nmr = pk_ld_vol(&ctl->n_mega);
-                    const uint32_t nm = nmr < (unsigned long long)PK_MEGA_SLOTS ? (uint32_t)nmr : (uint32_t)PK_MEGA_SLOTS;
-                    for (uint32_t i = 0; i < nm && !cmd; ++i) {
+                    for (uint32_t i = 0; i < (uint32_t)PK_MEGA_SLOTS && !cmd; ++i) {
                         PkMegaSlot *ms = io.mega + i;
-                        if (!pk_ld_vol(&ms->ready) || pk_ld_vol(&ms->finished)) continue;
-                        const uint32_t lim = ms->limit, g0 = ms->g0;
+                        const uint32_t st = pk_ld_vol(&ms->state);
+                        if (!st) continue;
+                        __threadfence();
+                        const uint32_t lim = pk_ld_vol(&ms->limit), g0 = pk_ld_vol(&ms->g0);
                         const uint32_t nx = pk_ld_vol(&ms->next);
                         if (nx >= lim || (unsigned long long)g0 + (unsigned long long)nx * CH >= (unsigned long long)pk_ld_vol(&ms->bound)) continue;
                         const uint32_t c = atomicAdd(&ms->next, 1u);
+                        __threadfence();
+                        if (pk_ld_vol(&ms->state) != st) continue;   // the window moved on meanwhile
                         if (c >= lim || (unsigned long long)g0 + (unsigned long long)c * CH >= (unsigned long long)pk_ld_vol(&ms->bound) || c <= pk_ld_vol(&ms->pos)) continue;
-                        cmd = 2; a0 = i; a1 = c;
+                        cmd = 2; a0 = i; a1 = c; a2 = st;
                     }
                 }
                 if (!cmd) {
@@ -1645,10 +1718,10 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
                     if (leave) cmd = 3;
                     else __nanosleep(400);
                 }
-                s_cmd[0] = cmd; s_cmd[1] = a0; s_cmd[2] = a1;
+                s_cmd[0] = cmd; s_cmd[1] = a0; s_cmd[2] = a1; s_cmd[3] = a2;
             }
             __syncthreads();
-            const uint32_t cmd = s_cmd[0], a0 = s_cmd[1], a1 = s_cmd[2];
+            const uint32_t cmd = s_cmd[0], a0 = s_cmd[1], a1 = s_cmd[2], a2 = s_cmd[3];
             __syncthreads();
             if (cmd == 3) break;
             if (cmd == 0) continue;
@@ -1660,11 +1733,11 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
                 __syncthreads();
                 begin_master(rec, true, true);
             } else {
-                h_job = true; h_slot = a0; h_chunk = a1;
+                h_job = true; h_slot = a0; h_chunk = a1; h_gen = a2;
             }
         }
         // ---------------- B: the next stretch of patterns to run
-        uint32_t start, stop;
+        uint32_t start, stop, h_cbase = 0;
         bool dry = false;
         uint32_t nimpr0 = 0;
         if (m_active) {
@@ -1678,18 +1751,19 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
                 }
             } else {
                 const uint32_t c = (m_start - m_g0) / CH;
+                if (c >= m_limit) { open_window(); continue; }   // end of the window: the next one starts here
                 if (threadIdx.x == 0) {
-                    // chunks marked clean by helpers, from c on, as far as the bound reaches
+                    // chunks marked clean by helpers, from c on, as far as the window and the bound reach
                     pk_st_vol(&m_ms->pos, c);
                     atomicMax(&m_ms->next, c + 1);
                     const unsigned long long nch = ((unsigned long long)(s.bound - m_g0) + CH - 1) / CH;
                     const uint32_t cend = nch < (unsigned long long)m_limit ? (uint32_t)nch : m_limit;
                     uint32_t cc = c;
                     while (cc < cend) {
-                        const uint32_t k = cc & 31u;
-                        const uint32_t rem = ~(pk_ld_vol(m_bits + (cc >> 5)) >> k);   // first zero bit ends the run (the k vacated top bits read as "not clean")
-                        uint32_t run = rem ? (uint32_t)(__ffs(rem) - 1) : 32u;
-                        const bool word_end = run >= 32u - k;
+                        const uint32_t rel = cc - m_cbase, k = rel & 15u;
+                        const uint32_t rem = (~(pk_ld_vol(m_bits + (rel >> 4)) >> k)) & 0xFFFFu;   // first zero flag ends the run (the k vacated top flags read as "not clean")
+                        uint32_t run = rem ? (uint32_t)(__ffs(rem) - 1) : 16u;
+                        const bool word_end = run >= 16u - k;
                         if (run > cend - cc) run = cend - cc;
                         cc += run;
                         if (!word_end) break;
@@ -1715,22 +1789,32 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
         } else if (h_job) {
             // a helper's share: chunk h_chunk of mega slot h_slot against a snapshot of the master's state, nothing committed
             PkMegaSlot *ms = io.mega + h_slot;
-            const long f = (long)ms->frame;
-            if (cur_frame != f) load(f);
             if (threadIdx.x == 0) {
+                // frame, grid origin and the snapshot, all of generation h_gen (else the job is void)
+                uint32_t ok = 1;
                 for (;;) {
                     const unsigned int q0 = pk_ld_vol(&ms->seq);
+                    if (pk_ld_vol(&ms->state) != h_gen) { ok = 0; break; }
                     if (q0 & 1u) continue;
                     __threadfence();
                     s_snap_l0 = *reinterpret_cast<volatile double *>(&ms->l0);
                     s_snap[NW] = pk_ld_vol(&ms->have);
 #pragma unroll
                     for (int w = 0; w < NW; ++w) s_snap[w] = pk_ld_vol(&ms->bestF[w]);
+                    s_cmd[1] = pk_ld_vol(&ms->frame);
+                    s_cmd[2] = pk_ld_vol(&ms->g0);
+                    s_cmd[3] = pk_ld_vol(&ms->cbase);
                     __threadfence();
-                    if (pk_ld_vol(&ms->seq) == q0) break;
+                    if (pk_ld_vol(&ms->seq) == q0) { ok = pk_ld_vol(&ms->state) == h_gen; break; }
                 }
+                s_cmd[0] = ok;
             }
             __syncthreads();
+            const uint32_t h_ok = s_cmd[0], h_frame = s_cmd[1], h_g0 = s_cmd[2];
+            h_cbase = s_cmd[3];
+            __syncthreads();
+            if (!h_ok) continue;
+            if (cur_frame != (long)h_frame) load((long)h_frame);
             s.l0 = s_snap_l0;
             s.have = s_snap[NW] != 0;
 #pragma unroll
@@ -1739,7 +1823,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
             s.bound = 0x7FFFFFFFu;
             s.trials = 0; s.tsteps = 0; s.nimpr = 0; s.step_last = 0; s.flags = 0;
             __syncthreads();
-            start = ms->g0 + h_chunk * CH;
+            start = h_g0 + h_chunk * CH;
             stop = start + CH;
             dry = true;
         } else {
@@ -1749,43 +1833,48 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
         const int r = KW::template wide<GW>(tabs, wm, kp, fr, s, start, &s_shared, s_votes, warp, stop, dry);
         // ---------------- D
         if (dry) {
-            if (r == KW::PK_W_STOPPED && threadIdx.x == 0)
-                atomicOr(io.mega_bits + (size_t)h_slot * PK_MEGA_WORDS + (h_chunk >> 5), 1u << (h_chunk & 31u));
+            if (r == KW::PK_W_STOPPED && threadIdx.x == 0) {
+                // mark the chunk clean -- only in a word that still carries the generation the scan was made for
+                const uint32_t rel = h_chunk - h_cbase;
+                unsigned int *word = io.mega_bits + (size_t)h_slot * PK_MEGA_WORDS + (rel >> 4);
+                unsigned int old = pk_ld_vol(word);
+                while ((old >> 16) == (h_gen & 0xFFFFu)) {
+                    const unsigned int seen = atomicCAS(word, old, old | (1u << (rel & 15u)));
+                    if (seen == old) break;
+                    old = seen;
+                }
+            }
             continue;
         }
         if (r == KW::PK_W_FINISHED) { end_master(); continue; }
         m_start = stop;
         if (!m_ms) {
             // still running after its own share: open the search to the idle CTAs of the grid if it is long
-            m_may_open = false;
             if (s.bound > m_start && s.bound - m_start >= kp.mega_span) {
                 if (threadIdx.x == 0) {
-                    const unsigned long long i = atomicAdd(&ctl->n_mega, 1ull);
-                    s_cmd[0] = i < (unsigned long long)PK_MEGA_SLOTS ? (uint32_t)i : 0xFFFFFFFFu;
+                    uint32_t got = 0xFFFFFFFFu;
+                    const uint32_t h0 = (blockIdx.x * 7u) % (uint32_t)PK_MEGA_SLOTS;   // spread the probes
+                    for (uint32_t q = 0; q < (uint32_t)PK_MEGA_SLOTS; ++q) {
+                        const uint32_t i = (h0 + q) % (uint32_t)PK_MEGA_SLOTS;
+                        if (pk_ld_vol(&io.mega[i].owner) == 0u && atomicCAS(&io.mega[i].owner, 0u, 1u) == 0u) { got = i; break; }
+                    }
+                    s_cmd[0] = got;
+                    if (got != 0xFFFFFFFFu) s_cmd[1] = pk_ld_vol(&io.mega[got].gen);
                 }
                 __syncthreads();
-                const uint32_t slot = s_cmd[0];
+                const uint32_t slot = s_cmd[0], gen0 = s_cmd[1];
                 __syncthreads();
                 if (slot != 0xFFFFFFFFu) {
                     m_ms = io.mega + slot;
                     m_bits = io.mega_bits + (size_t)slot * PK_MEGA_WORDS;
-                    const unsigned long long nch = ((unsigned long long)(s.bound - m_g0) + CH - 1) / CH;
-                    m_limit = nch < (unsigned long long)PK_MEGA_WORDS * 32 ? (uint32_t)nch : (uint32_t)PK_MEGA_WORDS * 32u;
-                    for (uint32_t w = threadIdx.x; w < (m_limit + 31) / 32; w += blockDim.x) m_bits[w] = 0;
-                    __threadfence();
-                    __syncthreads();
-                    if (threadIdx.x == 0) {
-                        const uint32_t c = (m_start - m_g0) / CH;
-                        m_ms->frame = (unsigned int)m_f; m_ms->g0 = m_g0; m_ms->limit = m_limit;
-                        m_ms->pos = c; m_ms->next = c + 1; m_ms->bound = s.bound;
-                        m_ms->l0 = s.l0; m_ms->have = s.have ? 1u : 0u;
-#pragma unroll
-                        for (int w = 0; w < NW; ++w) m_ms->bestF[w] = s.bestF[w];
-                        m_ms->seq = 0; m_ms->finished = 0;
-                        __threadfence();
-                        pk_st_vol(&m_ms->ready, 1u);
-                    }
+                    m_gen = gen0;        // generations of a slot go on where its last owner stopped
+                    m_may_open = false;
+                    open_window();
+                } else {
+                    m_own = 8u * CH;     // every slot is taken: go on alone, ask again later
                 }
+            } else {
+                m_may_open = false;
             }
         } else if (s.nimpr != nimpr0 && threadIdx.x == 0) {
             // publish the new state for the helpers (sequence lock)

@@ -9,8 +9,7 @@
 
 #define PK_HUGE_CAP 4096   // records behind the main parked-frame list for the huge frames
 #define PK_LATE_CAP 4096   // ... and behind those, for one-warp searches handed over to a whole CTA
-#define PK_MEGA_SLOTS 32   // long searches open to helpers per launch
-#define PK_MEGA_WORDS 16384   // bitmap words per mega slot: 2^31 patterns / 4096 per chunk / 32
+#define PK_MEGA_SLOTS 256  // long searches open to helpers at any one time
 struct PkMegaSlot;
 
 // warps per phase-B CTA
@@ -32,7 +31,9 @@ struct PkKanekoParams {
     uint32_t limit_a;     // trials (multiple of 32) a frame may spend in the narrow phase A before it is parked
     uint32_t big_span;    // parked frames with at least this many patterns left are searched by a whole CTA
     uint32_t huge_span;   // ... and with at least this many go to the separate "huge" list (always cooperative)
-    int variant;          // 0: decode(answer, word, res) (:335-407); 1: decode(word, res), the file-mode flavour (:212-276)
+    int variant;          // 0: decode(answer, word, res) (:335-407); 1: decode(word, res), the file-mode flavour (:212-276);
+                          // 2: exact rules (ours, for the kernel-LLR bridge): bound 1 << T, calcRightSide over d - m positions, calcT without the border sum
+    int ext;              // 1: extended code -- position n carries the overall parity of the BCH codeword (ours: src/main.cpp:60 only builds n = 2^m - 1)
     uint32_t extra_ops;   // per-frame constant added to both synthetic counters (2n+1 sort cost of the file-mode flavour, :221-224)
     // long searches shared by the whole grid (see "mega frames" in pk_kernels.cuh)
     uint32_t mega_chunk;    // patterns per helper chunk (multiple of 1024 * warps per phase-B CTA)
@@ -88,28 +89,36 @@ struct PkPhaseCtl {
     // phase B end game
     unsigned long long n_late;          // one-warp searches handed over to a whole CTA: longs[cap + PK_HUGE_CAP ..) (may count past PK_LATE_CAP)
     unsigned long long queue_late;      // next of them to take
-    unsigned long long n_mega;          // mega slots handed out (may count past PK_MEGA_SLOTS)
+    unsigned long long n_mega;          // mega slots in use
     unsigned long long ctas_past_solo;  // CTAs that have left the one-warp loop: once all have, n_late is final
     unsigned long long masters;         // CTAs that are (or are about to become) the master of a late frame
 };
 
 // A long search opened to the idle CTAs of the grid ("mega frame").  The master CTA keeps the sequential state and
 // commits in pattern order; helpers scan chunks AHEAD of it against a snapshot of (l0, best codeword) and mark the ones
-// that hold no possible improvement in a bitmap, which the master then skips.
+// that hold no possible improvement in a bitmap, which the master then skips.  A slot covers a WINDOW of
+// PK_MEGA_WINDOW chunks from the master's position; the master re-registers (same slot, next generation) when it
+// reaches the end of the window and gives the slot back when the frame is finished.
 struct PkMegaSlot {
-    unsigned int ready;      // 1 once the master has filled the slot
-    unsigned int finished;   // 1 when the master is done with the frame
+    unsigned int owner;      // 0 = free, 1 = taken by a master (atomicCAS)
+    unsigned int state;      // 0 = fields invalid, else the generation (never 0) the fields below belong to
+    unsigned int gen;        // last generation handed out (owner only)
     unsigned int seq;        // sequence lock over (l0, have, bestF): odd while the master writes
     unsigned int pos;        // chunk the master is working on (helpers take later ones)
     unsigned int next;       // next chunk to hand to a helper
     unsigned int bound;      // pattern bound as of the last commit (chunks beyond it are not handed out)
     unsigned int frame;      // frame index in the batch
     unsigned int g0;         // first pattern of chunk 0 (the search's step grid starts there)
-    unsigned int limit;      // chunks covered by the (cleared) bitmap
+    unsigned int cbase;      // first chunk of the window
+    unsigned int limit;      // one past the last chunk of the window
     unsigned int have;
     double l0;
     unsigned int bestF[8];
 };
+// bitmap word of a window: clean flags of 16 chunks in the low half, generation tag in the high half -- a helper that was
+// scanning for an earlier generation of the slot cannot mark anything (its compare-and-swap fails on the tag)
+#define PK_MEGA_WINDOW 2048                      // chunks per window
+#define PK_MEGA_WORDS (PK_MEGA_WINDOW / 16)      // bitmap words per slot
 
 // what the launcher zeroes before every launch pair: the control words and, right behind them, the mega slots
 struct PkPhaseBlock {

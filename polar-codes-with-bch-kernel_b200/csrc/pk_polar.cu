@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/pk_capi.h"
+#include "pk_philox.cuh"
 #include "pk_polar.h"
 
 extern unsigned long long g_pk_launches;
@@ -187,43 +188,50 @@ __host__ __device__ inline PathLayout path_layout(const PkPolarDev &d) {
 }
 
 // ------------------------------------------------------------------ encoder (a15)
+// One warp: a[] holds the K information symbols at their positions (zero elsewhere) on entry and the unshortened
+// codeword on exit (the returned pointer is a or b).  Frozen symbols are evaluated in order
+// (MixedKernelEncoder.cpp:148-159), then the layers m-1 .. 0 multiply every block by its kernel (:161-173).
+__device__ __forceinline__ uint8_t *polar_encode_warp(const PkPolarDev &d, uint8_t *a, uint8_t *b) {
+    const int lane = threadIdx.x & 31;
+    if (!d.all_static && lane == 0) {
+        for (int i = 0; i < d.N0; ++i) {
+            if (!d.frozen[i]) continue;
+            uint8_t v = 0;
+            for (int w = 0; w < d.nw; ++w) {
+                uint32_t m = d.cmask[i * d.nw + w];
+                while (m) { const int t = __ffs(m) - 1; m &= m - 1; v ^= a[32 * w + t]; }
+            }
+            a[i] = v;
+        }
+    }
+    __syncwarp();
+    int stride = 1;
+    for (int L = d.layers - 1; L >= 0; --L) {
+        const int l = d.ksize[L], bs = l * stride;
+        for (int e = lane; e < d.N0; e += 32) {
+            const int blk = e / bs, r0 = e - blk * bs, c = r0 / stride, i = r0 - c * stride;
+            uint8_t v = 0;
+            for (int r = 0; r < l; ++r) v ^= d.kern[L].mat[r * l + c] & a[blk * bs + r * stride + i];
+            b[e] = v;
+        }
+        __syncwarp();
+        uint8_t *t = a; a = b; b = t;
+        stride = bs;
+    }
+    return a;
+}
+
 __global__ void __launch_bounds__(128)
 k_polar_encode(PkPolarDev d, const uint8_t *__restrict__ info, long B, uint8_t *__restrict__ cw) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    uint8_t *a = smem + (size_t)warp * 2 * d.N0, *b = a + d.N0;
+    uint8_t *a0 = smem + (size_t)warp * 2 * d.N0, *b0 = a0 + d.N0;
     for (long f = (long)blockIdx.x * nwarps + warp; f < B; f += (long)gridDim.x * nwarps) {
-        // information symbols in place, frozen symbols evaluated in order (MixedKernelEncoder.cpp:148-159)
-        for (int i = lane; i < d.N0; i += 32) a[i] = 0;
+        for (int i = lane; i < d.N0; i += 32) a0[i] = 0;
         __syncwarp();
-        for (int q = lane; q < d.K; q += 32) a[d.info_pos[q]] = info[f * d.K + q] ? 1 : 0;
+        for (int q = lane; q < d.K; q += 32) a0[d.info_pos[q]] = info[f * d.K + q] ? 1 : 0;
         __syncwarp();
-        if (!d.all_static && lane == 0) {
-            for (int i = 0; i < d.N0; ++i) {
-                if (!d.frozen[i]) continue;
-                uint8_t v = 0;
-                for (int w = 0; w < d.nw; ++w) {
-                    uint32_t m = d.cmask[i * d.nw + w];
-                    while (m) { const int t = __ffs(m) - 1; m &= m - 1; v ^= a[32 * w + t]; }
-                }
-                a[i] = v;
-            }
-        }
-        __syncwarp();
-        // layers m-1 .. 0: blocks of size l*stride, y = x F_l on every stride element (:161-173)
-        int stride = 1;
-        for (int L = d.layers - 1; L >= 0; --L) {
-            const int l = d.ksize[L], bs = l * stride;
-            for (int e = lane; e < d.N0; e += 32) {
-                const int blk = e / bs, r0 = e - blk * bs, c = r0 / stride, i = r0 - c * stride;
-                uint8_t v = 0;
-                for (int r = 0; r < l; ++r) v ^= d.kern[L].mat[r * l + c] & a[blk * bs + r * stride + i];
-                b[e] = v;
-            }
-            __syncwarp();
-            uint8_t *t = a; a = b; b = t;
-            stride = bs;
-        }
+        const uint8_t *a = polar_encode_warp(d, a0, b0);
         // Shorten (:115-139): drop shortened / punctured symbols
         if (!d.symtype) {
             for (int i = lane; i < d.N0; i += 32) cw[f * d.N + i] = a[i];
@@ -233,6 +241,91 @@ k_polar_encode(PkPolarDev d, const uint8_t *__restrict__ info, long B, uint8_t *
                 if (d.symtype[i] == 0) cw[f * d.N + o++] = a[i];
         }
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ generation mode (the simulator loop on the device)
+// CSimulator::Iterate (out/external/Simulator.cpp:139-335, not buildable: GSL / Windows) restated for the device:
+// random information symbols -> Encode -> BPSK (bit 0 -> +1, Modem.h:64) + AWGN -> LLR = 2 y / sigma^2 (> 0 <=> bit 0,
+// :78) as fp32.  Frame f of SNR point s draws from Philox4x32-10 with key = seed, counter (f_lo, f_hi, block, s): blocks
+// 0.. hold the information bits (128 per block), blocks 0x1000+q the Box-Muller pair of transmitted symbols 2q, 2q+1.
+__global__ void __launch_bounds__(128)
+k_polar_generate(PkPolarDev d, double sigma, uint64_t seed, uint64_t first_frame, uint32_t snr_index, long B,
+                 uint8_t *__restrict__ info_out, uint8_t *__restrict__ cw_out, float *__restrict__ llr_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint8_t *a0 = smem + (size_t)warp * 3 * d.N0, *b0 = a0 + d.N0, *tx = b0 + d.N0;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (long f = (long)blockIdx.x * nwarps + warp; f < B; f += (long)gridDim.x * nwarps) {
+        const unsigned long long gf = first_frame + (unsigned long long)f;
+        const uint32_t c0 = (uint32_t)gf, c1 = (uint32_t)(gf >> 32);
+        for (int i = lane; i < d.N0; i += 32) a0[i] = 0;
+        __syncwarp();
+        for (int q0 = 0; q0 < d.K; q0 += 32) {
+            const int q = q0 + lane;
+            const PkPhilox r = pk_philox(c0, c1, (uint32_t)(q0 >> 7), snr_index, k0, k1);   // same word in all lanes of a group of 32
+            const uint32_t word = r.c[(q0 >> 5) & 3];
+            if (q < d.K) {
+                const uint8_t bit = (uint8_t)((word >> lane) & 1u);
+                a0[d.info_pos[q]] = bit;
+                if (info_out) info_out[f * d.K + q] = bit;
+            }
+        }
+        __syncwarp();
+        const uint8_t *a = polar_encode_warp(d, a0, b0);
+        // Shorten: the transmitted symbols
+        if (!d.symtype) {
+            for (int i = lane; i < d.N0; i += 32) tx[i] = a[i];
+        } else if (lane == 0) {
+            int o = 0;
+            for (int i = 0; i < d.N0; ++i)
+                if (d.symtype[i] == 0) tx[o++] = a[i];
+        }
+        __syncwarp();
+        for (int q = lane; 2 * q < d.N; q += 32) {
+            const PkPhilox r = pk_philox(c0, c1, 0x1000u + (uint32_t)q, snr_index, k0, k1);
+            const unsigned long long ra = ((unsigned long long)r.c[0] << 32) | r.c[1];
+            const unsigned long long rb = ((unsigned long long)r.c[2] << 32) | r.c[3];
+            const double u1 = ((double)(ra >> 11) + 1.0) * (1.0 / 9007199254740992.0);   // (0,1]
+            const double u2 = (double)(rb >> 11) * (1.0 / 9007199254740992.0);           // [0,1)
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+            const int p0 = 2 * q, p1 = 2 * q + 1;
+            const double y0 = (tx[p0] ? -1.0 : 1.0) + sigma * (rad * cs);
+            llr_out[f * d.N + p0] = (float)(2.0 * y0 / (sigma * sigma));
+            if (cw_out) cw_out[f * d.N + p0] = tx[p0];
+            if (p1 < d.N) {
+                const double y1 = (tx[p1] ? -1.0 : 1.0) + sigma * (rad * sn);
+                llr_out[f * d.N + p1] = (float)(2.0 * y1 / (sigma * sigma));
+                if (cw_out) cw_out[f * d.N + p1] = tx[p1];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// decided information vector of the best path against the transmitted one: frame / bit error counters
+// (pk_point_result layout: [0] frames, [1] frame errors, [2] information-bit errors, [7] flags)
+__global__ void __launch_bounds__(256)
+k_polar_compare(int K, int L, const uint8_t *__restrict__ info, const uint8_t *__restrict__ inf_out, const int *__restrict__ count,
+                long B, unsigned long long *__restrict__ totals) {
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    unsigned long long fr = 0, fe = 0, be = 0;
+    for (long f = warp; f < B; f += nwarps) {
+        int e = 0;
+        for (int q = lane; q < K; q += 32) e += (info[f * K + q] != inf_out[(f * L) * K + q]) ? 1 : 0;
+        e = __reduce_add_sync(PKP_FULL, e);
+        if (count[f] < 1) e = K;   // no path survived (cannot happen with list size >= 1; counted as a total loss)
+        fr += 1;
+        fe += e ? 1 : 0;
+        be += (unsigned long long)e;
+    }
+    if (lane == 0 && fr) {
+        atomicAdd(totals + 0, fr);
+        if (fe) atomicAdd(totals + 1, fe);
+        if (be) atomicAdd(totals + 2, be);
     }
 }
 
@@ -535,6 +628,12 @@ struct pk_polar {
     cudaStream_t stream = nullptr;
     size_t smem_decode = 0;
     int fpc = 1;   // frames per CTA
+    // generation-mode workspaces (one chunk of frames)
+    long gen_cap = 0;
+    uint8_t *g_info = nullptr, *g_inf = nullptr;
+    float *g_llr = nullptr;
+    int *g_cnt = nullptr;
+    unsigned long long *g_tot = nullptr, *h_tot = nullptr;
 };
 
 namespace {
@@ -636,6 +735,7 @@ int pk_polar_create(const char *spec_text, int L, int device, pk_polar **out) {
         }
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_polar_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_decode);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_polar_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2 * d.N0);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_polar_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * d.N0);
     }
     if (e != cudaSuccess) {
         std::string msg = std::string("pk_polar_create: ") + cudaGetErrorString(e);
@@ -653,6 +753,8 @@ void pk_polar_destroy(pk_polar *h) {
         cudaSetDevice(h->device);
         if (h->stream) cudaStreamDestroy(h->stream);
         for (void *p : h->allocs) cudaFree(p);
+        cudaFree(h->g_info); cudaFree(h->g_inf); cudaFree(h->g_llr); cudaFree(h->g_cnt); cudaFree(h->g_tot);
+        if (h->h_tot) cudaFreeHost(h->h_tot);
     }
     delete h;
 }
@@ -679,7 +781,7 @@ int pk_polar_trellis_profile(const pk_polar *h, int layer, int *size, uint8_t *o
 
 // (2^m) x (2^m) extended-BCH polarisation kernel (root bchCoder.cpp:356-389), row-major bytes
 int pk_make_ebch_kernel(int m, uint8_t *out) {
-    if (m < 3 || m > 5 || !out) return pk_set_error(PK_ERR_ARG, "m must be in [3,5]");
+    if (m < 3 || m > 6 || !out) return pk_set_error(PK_ERR_ARG, "m must be in [3,6]");
     std::vector<uint8_t> k;
     pk_polar_ebch_kernel(m, k);
     std::memcpy(out, k.data(), k.size());
@@ -789,6 +891,111 @@ int pk_polar_decode_batch(pk_polar *h, const float *llr, long B, int *count, uin
     if (metric) PKP_CUDA(cudaMemcpyAsync(metric, d4, (size_t)B * L * 4, cudaMemcpyDeviceToHost, h->stream));
     PKP_CUDA(cudaStreamSynchronize(h->stream));
     cudaFree(d0); cudaFree(d1); cudaFree(d2); cudaFree(d3); cudaFree(d4);
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------ generation mode
+static int polar_gen_ws(pk_polar *h) {
+    if (h->gen_cap) return PK_OK;
+    const long cap = std::max(1024L, (1L << 21) / h->L / std::max(1, h->code.K / 128));
+    cudaError_t e = cudaMalloc(&h->g_info, (size_t)cap * h->code.K);
+    if (e == cudaSuccess) e = cudaMalloc(&h->g_inf, (size_t)cap * h->L * h->code.K);
+    if (e == cudaSuccess) e = cudaMalloc(&h->g_llr, (size_t)cap * h->code.N * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->g_cnt, (size_t)cap * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->g_tot, 8 * 8);
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_tot, 8 * 8);
+    if (e != cudaSuccess) return pk_set_error(PK_ERR_CUDA, std::string("pk_polar generation workspaces: ") + cudaGetErrorString(e));
+    h->gen_cap = cap;
+    return PK_OK;
+}
+static double polar_sigma(const pk_polar *h, double ebn0_db) {
+    return sqrt(1.0 / (2.0 * ((double)h->code.K / (double)h->code.N) * pow(10.0, ebn0_db / 10.0)));   // Simulator.cpp:104 (SetEbN0)
+}
+
+// The frames generation mode draws, written out (device buffers, any of d_info [B][K] / d_cw [B][N] may be NULL; d_llr [B][N])
+int pk_polar_generate_frames_dev(pk_polar *h, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
+                                 uint8_t *d_info, uint8_t *d_cw, float *d_llr, void *stream) {
+    if (!h || nframes < 0 || (nframes && !d_llr)) return pk_set_error(PK_ERR_ARG, "bad arguments");
+    if (h->device < 0) return pk_set_error(PK_ERR_CUDA, "host-only handle: libpkb200 has no CPU compute path");
+    if (!nframes) return PK_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return pk_set_error(PK_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const int grid = (int)std::min<long>((nframes + 3) / 4, 148L * 8);
+    k_polar_generate<<<grid, 128, 4 * 3 * h->dev.N0, st>>>(h->dev, polar_sigma(h, ebn0_db), seed, first_frame, (uint32_t)snr_index, nframes, d_info, d_cw, d_llr);
+    ++g_pk_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pk_set_error(PK_ERR_CUDA, cudaGetErrorString(e));
+    return PK_OK;
+}
+
+// Monte-Carlo body for frames [first_frame, first_frame + nframes) of SNR point snr_index, fully on the device:
+// generate -> SC / SC-list decode -> compare the best path's information vector with the transmitted one.  d_totals
+// (8 x u64, pk_point_result layout: frames, frame_errors, bit_errors = information-bit errors) is ACCUMULATED into.
+// Asynchronous on `stream` (NULL = the handle's).  Results do not depend on how the frame range is split.
+int pk_polar_run_frames_dev(pk_polar *h, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
+                            uint64_t *d_totals, void *stream) {
+    if (!h || nframes < 0 || !d_totals) return pk_set_error(PK_ERR_ARG, "bad arguments");
+    if (h->device < 0) return pk_set_error(PK_ERR_CUDA, "host-only handle: libpkb200 has no CPU compute path");
+    if (!nframes) return PK_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return pk_set_error(PK_ERR_CUDA, "cudaSetDevice failed");
+    int rc = polar_gen_ws(h);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    for (long off = 0; off < nframes; off += h->gen_cap) {
+        const long nb = std::min(h->gen_cap, nframes - off);
+        rc = pk_polar_generate_frames_dev(h, ebn0_db, snr_index, seed, first_frame + (uint64_t)off, nb, h->g_info, nullptr, h->g_llr, st);
+        if (rc) return rc;
+        rc = pk_polar_decode_batch_dev(h, h->g_llr, nb, h->g_cnt, h->g_inf, nullptr, nullptr, st);
+        if (rc) return rc;
+        const int grid = (int)std::min<long>((nb + 7) / 8, 148L * 8);
+        k_polar_compare<<<grid, 256, 0, st>>>(h->code.K, h->L, h->g_info, h->g_inf, h->g_cnt, nb, (unsigned long long *)d_totals);
+        ++g_pk_launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return pk_set_error(PK_ERR_CUDA, cudaGetErrorString(e));
+    }
+    return PK_OK;
+}
+
+// Same, synchronous, host result (adds into *totals).
+int pk_polar_run_frames(pk_polar *h, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
+                        pk_point_result *totals) {
+    if (!h || nframes < 0 || !totals) return pk_set_error(PK_ERR_ARG, "bad arguments");
+    if (h->device < 0) return pk_set_error(PK_ERR_CUDA, "host-only handle: libpkb200 has no CPU compute path");
+    if (!nframes) return PK_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return pk_set_error(PK_ERR_CUDA, "cudaSetDevice failed");
+    int rc = polar_gen_ws(h);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(h->g_tot, 0, 64, h->stream);
+    if (e != cudaSuccess) return pk_set_error(PK_ERR_CUDA, cudaGetErrorString(e));
+    rc = pk_polar_run_frames_dev(h, ebn0_db, snr_index, seed, first_frame, nframes, (uint64_t *)h->g_tot, h->stream);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(h->h_tot, h->g_tot, 64, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return pk_set_error(PK_ERR_CUDA, cudaGetErrorString(e));
+    uint64_t *t = reinterpret_cast<uint64_t *>(totals);
+    for (int i = 0; i < 6; ++i) t[i] += h->h_tot[i];
+    return PK_OK;
+}
+
+// host copies of the generated frames (tests): info [B][K], cw [B][N] (any may be NULL), llr [B][N]
+int pk_polar_generate_frames(pk_polar *h, double ebn0_db, int snr_index, uint64_t seed, uint64_t first_frame, long nframes,
+                             uint8_t *info, uint8_t *cw, float *llr) {
+    if (!h || nframes < 0 || (nframes && !llr)) return pk_set_error(PK_ERR_ARG, "bad arguments");
+    if (h->device < 0) return pk_set_error(PK_ERR_CUDA, "host-only handle: libpkb200 has no CPU compute path");
+    if (!nframes) return PK_OK;
+    const int N = h->code.N, K = h->code.K;
+    void *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *d3 = nullptr, *d4 = nullptr;
+    PKP_CUDA(cudaSetDevice(h->device));
+    PKP_CUDA(cudaMalloc(&d0, (size_t)nframes * K));
+    PKP_CUDA(cudaMalloc(&d1, (size_t)nframes * N));
+    PKP_CUDA(cudaMalloc(&d2, (size_t)nframes * N * 4));
+    int rc = pk_polar_generate_frames_dev(h, ebn0_db, snr_index, seed, first_frame, nframes, (uint8_t *)d0, (uint8_t *)d1, (float *)d2, h->stream);
+    if (rc) { cudaFree(d0); cudaFree(d1); cudaFree(d2); return rc; }
+    if (info) PKP_CUDA(cudaMemcpyAsync(info, d0, (size_t)nframes * K, cudaMemcpyDeviceToHost, h->stream));
+    if (cw) PKP_CUDA(cudaMemcpyAsync(cw, d1, (size_t)nframes * N, cudaMemcpyDeviceToHost, h->stream));
+    PKP_CUDA(cudaMemcpyAsync(llr, d2, (size_t)nframes * N * 4, cudaMemcpyDeviceToHost, h->stream));
+    PKP_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d0); cudaFree(d1); cudaFree(d2);
     return PK_OK;
 }
 

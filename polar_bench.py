@@ -1,0 +1,234 @@
+"""bench.py --workload polar : BASELINE configs[2-3] -- the (256,128) polar code with two 16 x 16 extended-BCH kernels
+(frozen set of this repository: the reference ships none), SC (L = 1) and SC-list decoding (L = 8, 32).
+
+One "step" = this rank's share of `frames` frames at every point of the Eb/N0 grid for L = 1, 8 and 32 in generation
+mode (Philox info bits -> mixed-kernel encode -> BPSK + AWGN -> fp32 LLRs -> SC / SC-list decode -> compare, all on the
+device: pk_polar_run_frames_dev), one all-reduce of the counters per (L, point) inside the timed region.
+
+  value : decoded frames/s (all three list sizes together), device-timed, max over ranks
+  e2e   : pk_polar_decode_batch_dev fed from pinned HOST LLR buffers, decisions back in host memory (H2D + D2H inside)
+  cpu_baseline : the reference's own vendored library (oracle/_ref/libpolar_ref.so, CMixedKernelListDecoder) on one core
+  roofline : add-compare-selects of the kernel-trellis Viterbi recursions per second against the issue-slot roof, with the
+             warp instructions per ACS of the committed ncu capture
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+LS = (1, 8, 32)
+POLAR_SNRS = [1.0, 1.5, 2.0, 2.5, 3.0]
+POLAR_METRIC = "decoded frames/s (polar (256,128), two 16x16 eBCH kernels, SC + SCL-8 + SCL-32, Eb/N0 1..3 dB)"
+# branch evaluations (add-compare-selects) of one SC pass over the code: 2 layers x 16 kernel blocks x 11 712
+ACS_PER_PATH = 2 * 16 * 11712
+
+
+def frames_for(L, short):
+    base = {1: 1 << 18, 8: 1 << 16, 32: 1 << 14}[L]
+    return base // 8 if short else base
+
+
+def polar_measure(env, a, short=False):
+    torch, pk = env.torch, env.pk
+    spec = pk.load_spec()
+    steps = 1 if short else max(1, a.steps)
+    warm = 1 if short else a.warmup
+    snrs = [2.0] if short else POLAR_SNRS
+    pols = {L: pk.Polar(spec, L=L, device=env.local) for L in LS}
+    tot = torch.zeros((len(LS), len(snrs), 8), dtype=torch.int64, device=env.dev)
+
+    def share(P):
+        per = (P + env.world - 1) // env.world
+        first = env.rank * per
+        return first, max(0, min(per, P - first))
+
+    def step(evs=None):
+        tot.zero_()
+        for li, L in enumerate(LS):
+            first, cnt = share(frames_for(L, short))
+            for si, s in enumerate(snrs):
+                if evs is not None:
+                    e0, e1 = env.event(), env.event()
+                    e0.record(env.stream)
+                if cnt:
+                    pols[L].run_frames_dev(s, int(round(2 * s)), a.seed, first, cnt, tot[li, si].data_ptr(), env.sp)
+                env.comm.allreduce_point([tot[li, si].data_ptr()])
+                if evs is not None:
+                    e1.record(env.stream)
+                    evs.append((li, si, e0, e1))
+
+    for _ in range(warm):
+        step()
+    env.barrier()
+    pk.launch_count_reset()
+    evs = []
+    ev0, ev1 = env.event(), env.event()
+    ev0.record(env.stream)
+    for _ in range(steps):
+        step(evs)
+    ev1.record(env.stream)
+    env.barrier()
+    launches = pk.launch_count()
+    ms = env.max_over_ranks(ev0.elapsed_time(ev1))
+    t = tot.cpu().numpy().astype(np.int64)
+    frames_step = sum(frames_for(L, short) for L in LS) * len(snrs)
+    per = {}
+    for li, si, e0, e1 in evs:
+        per.setdefault((li, si), []).append(e0.elapsed_time(e1))
+    out = {"code": "(256,128), two layers of the 16x16 extended-BCH kernel, frozen set of this repository (specs/polar_256_128_ebch16.spec.in)",
+           "value": frames_step * steps / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches": int(launches), "frames_per_step": frames_step, "lists": {}}
+    for li, L in enumerate(LS):
+        P = frames_for(L, short)
+        pts = []
+        for si, s in enumerate(snrs):
+            pm = float(np.mean(per[(li, si)]))
+            assert int(t[li, si, 0]) == P
+            pts.append({"ebn0_db": s, "frames": P, "frames_per_s": P / pm * 1e3, "fer": float(t[li, si, 1]) / P, "ber": float(t[li, si, 2]) / P / pols[L].K})
+        out["lists"][f"L{L}"] = pts
+    return out
+
+
+def run_polar(a, Env, ClockSampler):
+    env = Env(a)
+    torch, pk = env.torch, env.pk
+    sampler = ClockSampler(env.local)
+    if env.rank == 0:
+        sampler.start()
+    res = polar_measure(env, a)
+    # ---- e2e: host LLRs -> decisions in host memory, per list size, 2 dB
+    spec = pk.load_spec()
+    rng = np.random.default_rng(5 + env.rank)
+    e2e = {}
+    h2d = d2h = 0
+    e2e_frames = 0
+    t_e2e = 0.0
+    hold = []
+    for L in LS:
+        p = pk.Polar(spec, L=L, device=env.local)
+        B = frames_for(L, False) // 4
+        info = rng.integers(0, 2, (B, p.K), dtype=np.uint8)
+        sg = np.sqrt(1 / (2 * (p.K / p.N) * 10 ** 0.2))
+        cw = p.encode(info)
+        llr = torch.from_numpy((2 * ((1 - 2.0 * cw) + sg * rng.standard_normal(cw.shape)) / sg ** 2).astype(np.float32)).pin_memory()
+        h_cnt = torch.zeros(B, dtype=torch.int32).pin_memory()
+        h_inf = torch.zeros((B, L, p.K), dtype=torch.uint8).pin_memory()
+        d_llr = torch.empty((B, p.N), dtype=torch.float32, device=env.dev)
+        d_cnt = torch.zeros(B, dtype=torch.int32, device=env.dev)
+        d_inf = torch.zeros((B, L, p.K), dtype=torch.uint8, device=env.dev)
+
+        def once():
+            d_llr.copy_(llr, non_blocking=True)
+            p.decode_dev(d_llr.data_ptr(), B, d_cnt.data_ptr(), d_inf.data_ptr(), None, None, env.sp)
+            h_cnt.copy_(d_cnt, non_blocking=True)
+            h_inf.copy_(d_inf, non_blocking=True)
+            torch.cuda.synchronize()
+
+        once()
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, a.steps)):
+            once()
+        dt = env.max_over_ranks(time.perf_counter() - t0)
+        e2e[f"L{L}_frames_per_s"] = env.world * B * max(1, a.steps) / dt
+        t_e2e += dt
+        e2e_frames += env.world * B * max(1, a.steps)
+        h2d += B * p.N * 4
+        d2h += B * 4 + B * L * p.K
+        assert (h_inf[:, 0, :].numpy() == info).all(1).mean() > 0.5
+        hold.append((L, llr.numpy(), h_inf.numpy().copy(), h_cnt.numpy().copy()))
+    clocks = sampler.stop() if env.rank == 0 else None
+    if env.rank == 0:
+        # ---- CPU baseline: the reference library itself, one core, bounded sample, decisions checked equal
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_py
+
+        cpu = None
+        if oracle_py.polar_ref_available():
+            t_cpu, n_cpu = 0.0, 0
+            per_l = {}
+            for (L, llr, inf, cnt) in hold:
+                ref = oracle_py.PolarReference(spec, L)
+                nb = {1: 1200, 8: 300, 32: 100}[L]
+                t0 = time.perf_counter()
+                r_cnt, r_inf, _, _ = ref.decode(llr[:nb])
+                dt = time.perf_counter() - t0
+                assert np.array_equal(r_cnt, cnt[:nb]) and np.array_equal(r_inf, inf[:nb]), "GPU lists differ from the reference library"
+                per_l[f"L{L}_frames_per_s"] = nb / dt
+                t_cpu += dt
+                n_cpu += nb
+            cpu = {"value": n_cpu / t_cpu, "unit": "frames/s", "cores": 1, "kind": "reference",
+                   "sample": f"first 1200 / 300 / 100 frames of the e2e inputs for L = 1 / 8 / 32 ({t_cpu:.1f} s, CMixedKernelListDecoder of the reference's vendored library, scalar -O2 build); lists checked equal to the GPU's", **per_l}
+        NCU = json.load(open(os.path.join(ROOT, "profiles", "ncu_constants.json")))
+        sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+        l1 = [p for p in res["lists"]["L1"] if p["ebn0_db"] == 2.0][0]
+        acs_per_s = l1["frames_per_s"] * ACS_PER_PATH
+        ipa = NCU.get("polar_warp_inst_per_acs")
+        roofline = {"bound": "issue_slots", "unit": "Gwarp-inst/s", "achieved": acs_per_s * ipa / 1e9 if ipa else None, "peak": 148 * 4 * sm_hz / 1e9,
+                    "frac": acs_per_s * ipa / (148 * 4 * sm_hz) if ipa else None, "traffic": NCU.get("polar_dram_bytes_per_launch"),
+                    "kernel": "k_polar_decode (L = 1, 2 dB)", "acs_per_s": acs_per_s, "acs_per_frame": ACS_PER_PATH, "warp_inst_per_acs_ncu": ipa,
+                    "peak_source": "148 SMs x 4 schedulers x one warp instruction per clock at the sampled SM clock", "ncu_source": NCU.get("polar_source")}
+        line = {"metric": POLAR_METRIC, "value": res["value"], "unit": "frames/s", "n_gpus": env.world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32 LLRs / path metrics, u8 bits",
+                "data": "synthetic (Philox4x32-10 info bits + AWGN drawn on the device)",
+                "config": {"workload": "BASELINE configs[2-3]: polar (256,128) with two 16x16 eBCH kernels, SC and SC-list L = 8, 32, generation mode, frames sharded over the GPUs",
+                           "frames_per_point": {f"L{L}": frames_for(L, False) for L in LS}, "ebn0_db": POLAR_SNRS},
+                "e2e": {"value": e2e_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "pinned host LLRs -> pk_polar_decode_batch_dev -> list sizes + information vectors in pinned host memory", **e2e},
+                "gpu_launches": res["gpu_launches"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "detail": res["lists"]}
+        print(json.dumps(line))
+    env.close()
+    return 0
+
+
+def _ref_worker(args):
+    widx, steps = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, ROOT)
+    import oracle_py
+
+    spec = open(os.path.join(ROOT, "polar-codes-with-bch-kernel_b200", "specs", "polar_256_128_ebch16.spec.in")).read().replace(
+        "@KERNEL@", os.path.join(ROOT, "polar-codes-with-bch-kernel_b200", "specs", "ebch16.kernel"))
+    rng = np.random.default_rng(100 + widx)
+    out = []
+    nbs = {1: 64, 8: 16, 32: 4}
+    refs = {L: oracle_py.PolarReference(spec, L) for L in LS}
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        for L in LS:
+            ref = refs[L]
+            for s in POLAR_SNRS:
+                info = rng.integers(0, 2, (nbs[L], ref.K), dtype=np.uint8)
+                cw = ref.encode(info)
+                sg = np.sqrt(1 / (2 * (ref.K / ref.N) * 10 ** (s / 10)))
+                llr = (2 * ((1 - 2.0 * cw) + sg * rng.standard_normal(cw.shape)) / sg ** 2).astype(np.float32)
+                ref.decode(llr)
+        out.append(time.perf_counter() - t0)
+    return out
+
+
+def run_reference_polar(a):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+
+    if not oracle_py.polar_ref_available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpolar_ref.so not built (needs /root/reference at build time)"}))
+        return 0
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0))
+    total = a.warmup + a.steps
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_ref_worker, [(w, total) for w in range(cores)])
+    step_t = [max(res[w][s] for w in range(cores)) for s in range(total)][a.warmup:]
+    frames = cores * (64 + 16 + 4) * len(POLAR_SNRS)
+    value = frames * a.steps / sum(step_t)
+    sample = f"64 / 16 / 4 frames (L = 1 / 8 / 32) x {len(POLAR_SNRS)} SNR points per process per step, {cores} processes"
+    print(json.dumps({"impl": "reference", "metric": POLAR_METRIC, "value": value, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                      "ms_per_step": 1e3 * sum(step_t) / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32",
+                      "data": "synthetic (numpy AWGN)", "config": {"workload": "BASELINE configs[2-3]: polar (256,128), two 16x16 eBCH kernels, SC + SCL-8 + SCL-32 (a bounded sample)", "processes": cores},
+                      "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+                      "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return 0

@@ -118,3 +118,25 @@ def test_extra_specs_against_committed_golden_vectors(pk, tag, name):
         assert np.array_equal(met.view(np.uint32), z[k + "_metric"].view(np.uint32))
         assert np.array_equal(np.packbits(inf, axis=2), z[k + "_inf"])
         assert np.array_equal(np.packbits(cw, axis=2), z[k + "_cwl"])
+
+
+@pytest.mark.parametrize("name,L", [("polar_256_128_ebch16.spec.in", 1), ("polar_256_128_ebch16.spec.in", 8), ("polar_240_114_ebch16_sp.spec.in", 8),
+                                    ("polar_256_128_ebch16_dyn.spec.in", 32)])
+def test_generation_mode_equals_decode_of_the_dumped_frames(pk, name, L):
+    """pk_polar_run_frames (generate + decode + compare on the device) against decode() of the frames it draws; the drawn
+    codewords are the encoder's, the noise has the right statistics, and the totals do not depend on the split."""
+    p = pk.Polar(pk.load_spec(name), L=L, device=0)
+    B, snr, si = 3000, 2.0, 4
+    info, cw, llr = p.generate_frames(snr, si, 7, 100, B)
+    assert np.array_equal(p.encode(info), cw)
+    assert 0.45 < info.mean() < 0.55
+    sigma = np.sqrt(1 / (2 * (p.K / p.N) * 10 ** (snr / 10)))
+    z = (llr.astype(np.float64) * sigma ** 2 / 2 - (1 - 2.0 * cw)) / sigma
+    assert abs(z.mean()) < 5 / np.sqrt(z.size) and abs(z.var() - 1) < 8 * np.sqrt(2 / z.size)
+    cnt, inf, _, _ = p.decode(llr)
+    be = (inf[:, 0, :] != info).sum(1)
+    tot = p.run_frames(snr, si, 7, 100, B)
+    assert tot["frames"] == B and tot["frame_errors"] == int((be > 0).sum()) and tot["bit_errors"] == int(be.sum())
+    t1, t2 = p.run_frames(snr, si, 7, 100, 1234), p.run_frames(snr, si, 7, 100 + 1234, B - 1234)
+    for k in ("frames", "frame_errors", "bit_errors"):
+        assert t1[k] + t2[k] == tot[k]
