@@ -37,6 +37,8 @@ typedef enum {
 #define PK_FLAG_SORT_TIE 0x04     /* informational: equal |alpha| keys met; their order was resolved by replaying libstdc++'s std::sort */
 #define PK_FLAG_FRAME_ERROR 0x08  /* generation mode: decided != transmitted (dataForPlot.cpp:66) */
 #define PK_FLAG_TRUNCATED 0x10    /* stopped by the max_trials safety cap (never set with the default cap) */
+#define PK_FLAG_NON_ML 0x40       /* generation mode: the transmitted word is more likely than the decision -- what the
+                                      reference's DEBUG build writes to out/errWords.txt (dataForPlot.cpp:55-64) */
 #define PK_FLAG_REF_UNDEFINED 0x20 /* 2-argument flavour only: the reference's unbounded `while (l >= calcT(j))` (:257) ran
                                       past the reliability array here, i.e. its own result is undefined */
 

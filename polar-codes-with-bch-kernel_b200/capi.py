@@ -18,6 +18,7 @@ PK_FLAG_SORT_TIE = 0x04
 PK_FLAG_FRAME_ERROR = 0x08
 PK_FLAG_TRUNCATED = 0x10
 PK_FLAG_REF_UNDEFINED = 0x20
+PK_FLAG_NON_ML = 0x40
 
 #: numpy view of pk_frame_rec (16 bytes)
 FRAME_REC = np.dtype(

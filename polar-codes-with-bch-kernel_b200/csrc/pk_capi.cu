@@ -56,7 +56,7 @@ struct pk_kaneko {
     // one control block + parked-frame list per concurrent launch slot:
     // slots 0/1 = the handle's two pipeline streams, slot 2 = caller-supplied streams
     PkPhaseBlock *d_ctl = nullptr;            // [3]: control words + mega slots, zeroed before every launch pair
-    PkLongRec *d_longs[3] = {nullptr, nullptr, nullptr};   // parked frames: [long_cap] main, [PK_HUGE_CAP] huge, [PK_LATE_CAP] late
+    PkLongRec *d_longs[3] = {nullptr, nullptr, nullptr};   // parked frames: [long_cap] main, [PK_HUGE_CAP] huge, [long_cap] late
     uint32_t *d_mega_bits[3] = {nullptr, nullptr, nullptr};   // clean-chunk bitmaps of the mega slots
     uint32_t epoch = 0;                       // launch counter (PkKanekoParams::epoch)
     uint32_t *d_zscr[3] = {nullptr, nullptr, nullptr};   // root-word scratch of the large-code phase B
@@ -432,7 +432,7 @@ static int launch_pairs(pk_kaneko *d, int slot, bool gen, PkIo io, long B, cudaS
     const pk_code *c = d->code;
     const bool wide = d->geom4[gen ? 3 : 1].grid > 0;
     if (wide && !d->d_longs[slot]) {
-        const size_t bytes = (size_t)(d->long_cap + PK_HUGE_CAP + PK_LATE_CAP) * sizeof(PkLongRec);
+        const size_t bytes = (size_t)(2 * d->long_cap + PK_HUGE_CAP) * sizeof(PkLongRec);   // parked, huge, late
         PK_CUDA(cudaMalloc(&d->d_longs[slot], bytes));
         PK_CUDA(cudaMemsetAsync(d->d_longs[slot], 0, bytes, st));   // late-list records carry the launch epoch (never 0)
         PK_CUDA(cudaMalloc(&d->d_mega_bits[slot], (size_t)PK_MEGA_SLOTS * PK_MEGA_WORDS * sizeof(uint32_t)));

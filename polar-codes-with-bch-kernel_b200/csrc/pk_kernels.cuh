@@ -32,6 +32,7 @@
 #include "pk_alg.cuh"
 #include "pk_bs.cuh"
 #include "pk_kernels.h"
+#include "pk_philox.cuh"
 #include "pk_stdsort.cuh"
 
 #define PK_FULL 0xFFFFFFFFu
@@ -53,26 +54,6 @@ __device__ __forceinline__ uint32_t pk_pattern_bound(int T) { return (1u << (T &
 // SHL (count masked to 6 bits), no "- 1", and T starts at LONG_MAX (= no bound).  Pattern indices here are 31-bit,
 // anything larger is "unbounded" (a search that long ends with PK_FLAG_TRUNCATED at max_trials).
 __device__ __forceinline__ uint32_t pk_pattern_bound2(int T) { return ((T & 63) >= 31) ? 0x7FFFFFFFu : (1u << (T & 63)); }
-
-// ------------------------------------------------------------------ Philox4x32-10
-struct PkPhilox {
-    uint32_t c[4];
-};
-__device__ __forceinline__ PkPhilox pk_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    PkPhilox o;
-    o.c[0] = c0; o.c[1] = c1; o.c[2] = c2; o.c[3] = c3;
-    return o;
-}
 
 // ------------------------------------------------------------------ compile-time switches per (M,T)
 template <int M, int T>
@@ -953,10 +934,52 @@ struct KanekoWarp {
                 }
                 cand = refine(ok & vmask, s);
             } else if constexpr (CT) {
-                // one bitmap probe per pattern: does ANY error pattern of weight <= t have this syndrome class?
+                // Patterns whose flip set lies within distance t of a codeword this lane already knows (the best one, the
+                // last two it rejected) decode to that codeword again -- refine() drops them anyway, so they are not even
+                // probed: their flip set is (lane / base part) ^ (in-word part q), the in-word part lives on the five
+                // least reliable positions, hence dist = D0 + popc(q ^ c5) with D0 the distance outside those positions
+                // and c5 the codeword's bits on them.  15 % of the probes at 0 dB, half of them at 3 dB (L2 requests are
+                // what bounds this kernel).
+                uint32_t skip = 0;
+                {
+                    uint32_t low[NW];   // the five in-word positions
+#pragma unroll
+                    for (int w2 = 0; w2 < NW; ++w2) low[w2] = wm.pb[31 * NW + w2];
+                    auto near = [&](const uint32_t (&Cw)[NW], bool valid) -> uint32_t {
+                        int d0 = 0;
+                        uint32_t c5 = 0;
+#pragma unroll
+                        for (int w2 = 0; w2 < NW; ++w2) {
+                            const uint32_t x = (Ul[SW + w2] ^ Ub[SW + w2] ^ Cw[w2]) & (w2 == NW - 1 ? f.topmask : PK_FULL);
+                            d0 += __popc(x & ~low[w2]);
+                        }
+#pragma unroll
+                        for (int b = 0; b < 5; ++b) {
+                            uint32_t hit = 0;
+#pragma unroll
+                            for (int w2 = 0; w2 < NW; ++w2) hit |= Cw[w2] & wm.pb[(1 << b) * NW + w2];
+                            c5 |= (hit ? 1u : 0u) << b;
+                        }
+                        const int r = T - d0;
+                        if (!valid || r < 0) return 0u;
+                        // { q : popc(q) <= r } moved by q -> q ^ c5
+                        uint32_t m = (r >= 5) ? PK_FULL : (r == 4) ? 0x7FFFFFFFu : (r == 3) ? 0x177F7FFFu : (r == 2) ? 0x0117177Fu : (r == 1) ? 0x00010117u : 0x00000001u;
+                        m = (c5 & 1u) ? (((m & 0x55555555u) << 1) | ((m >> 1) & 0x55555555u)) : m;
+                        m = (c5 & 2u) ? (((m & 0x33333333u) << 2) | ((m >> 2) & 0x33333333u)) : m;
+                        m = (c5 & 4u) ? (((m & 0x0F0F0F0Fu) << 4) | ((m >> 4) & 0x0F0F0F0Fu)) : m;
+                        m = (c5 & 8u) ? (((m & 0x00FF00FFu) << 8) | ((m >> 8) & 0x00FF00FFu)) : m;
+                        m = (c5 & 16u) ? ((m << 16) | (m >> 16)) : m;
+                        return m;
+                    };
+                    skip = near(s.bestF, s.have);
+#pragma unroll
+                    for (int k = 0; k < KR; ++k) skip |= near(rej[k], true);   // (an empty slot is all ones: farther than t from every pattern)
+                }
+                // one bitmap probe per remaining pattern: does ANY error pattern of weight <= t have this syndrome class?
                 uint32_t ok = 0;
 #pragma unroll 8
                 for (int q = 0; q < 32; ++q) {
+                    if ((skip >> q) & 1u) continue;
                     uint32_t w[SW];
 #pragma unroll
                     for (int a = 0; a < SW; ++a) w[a] = u[a] ^ wm.cm[q * SW + a];
@@ -1352,7 +1375,7 @@ __device__ __forceinline__ void pk_load_frame(const PkIo &io, const PkDevTables 
 template <int M, int NW, bool GEN>
 __device__ __forceinline__ void pk_emit(const PkIo &io, long f, const uint32_t (&YH)[NW], const uint32_t (&bestF)[NW],
                                         const uint32_t (&CW)[NW], uint32_t trials, uint32_t ecmp, uint32_t esum,
-                                        uint32_t flags, PkWarpTotals &tot, int ext) {
+                                        uint32_t flags, PkWarpTotals &tot, int ext, const double *alpha) {
     const int N = (1 << M) - 1 + ext;   // length of the (possibly extended) code
     const int lane = threadIdx.x & 31;
     uint32_t be = 0;
@@ -1374,6 +1397,18 @@ __device__ __forceinline__ void pk_emit(const PkIo &io, long f, const uint32_t (
             for (int w = 0; w < NW; ++w) be += __popc(CW[w]);   // undecided buffer counted as all-zero
         }
         flags |= be ? PK_FLAG_FRAME_ERROR : 0;
+        if (be && !(flags & PK_FLAG_NO_DECISION)) {
+            // the reference's DEBUG build logs the frames whose transmitted word is MORE likely than the decision
+            // (calcL(res) < calcL(decoded), dataForPlot.cpp:55-64: a decoder that is not maximum-likelihood there)
+            double l_tx = 0.0, l_dec = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                uint32_t a = YH[w] ^ CW[w], b = bestF[w];
+                while (a) { const int i = __ffs(a) - 1; a &= a - 1; l_tx += alpha[32 * w + i]; }
+                while (b) { const int i = __ffs(b) - 1; b &= b - 1; l_dec += alpha[32 * w + i]; }
+            }
+            if (l_tx < l_dec) flags |= PK_FLAG_NON_ML;
+        }
     }
     if (lane == 0) {
         if (io.recs) {
@@ -1462,7 +1497,7 @@ k_phase_a(PkDevTables tb, PkKanekoParams kp, PkIo io, long B, PkPhaseCtl *ctl, P
                 KW::narrow(tabs, wm, kp, fr, s, next, 0xFFFFFFFFu, &next);
             }
             KW::search_finish(s);
-            pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot, kp.ext);
+            pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot, kp.ext, wm.alpha);
         }
     }
     if (lane == 0) tot.flush(io.totals);
@@ -1527,6 +1562,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
     __shared__ double s_snap_l0;
     __shared__ uint32_t s_snap[NW + 1];
     PkLongRec *late = longs + long_cap + PK_HUGE_CAP;
+    const long late_cap = long_cap;   // every parked frame of the launch may be handed over
     const uint32_t CH = (kp.mega_chunk % (1024u * GW)) ? 0u : kp.mega_chunk;   // 0: no mega frames (chunks must be whole cooperative steps)
 
     PkWarpTotals tot;
@@ -1593,17 +1629,21 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
             m_ms->seq = 0;
             __threadfence();
             pk_st_vol(&m_ms->state, m_gen);
+            const uint32_t slot = (uint32_t)(m_ms - io.mega);
+            atomicOr(&ctl->mega_mask[slot >> 6], 1ull << (slot & 63u));
         }
     };
     auto end_master = [&]() {
         if (m_ms && threadIdx.x == 0) {
+            const uint32_t slot = (uint32_t)(m_ms - io.mega);
+            atomicAnd(&ctl->mega_mask[slot >> 6], ~(1ull << (slot & 63u)));
             pk_st_vol(&m_ms->state, 0u);
             __threadfence();
             atomicExch(&m_ms->owner, 0u);   // the slot is free again (its generation counter lives on in m_ms->gen)
         }
         if (warp == 0) {
             KW::search_finish(s);
-            pk_emit<M, NW, GEN>(io, m_f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot, kp.ext);
+            pk_emit<M, NW, GEN>(io, m_f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot, kp.ext, wm.alpha);
         }
         if (m_late) {
             __syncthreads();
@@ -1655,7 +1695,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
                     long slot = -1;
                     if (lane == 0) {
                         const unsigned long long q = atomicAdd(&ctl->n_late, 1ull);
-                        if (q < (unsigned long long)PK_LATE_CAP) {
+                        if (q < (unsigned long long)late_cap) {
                             slot = (long)q;
                             KW::park(s, (uint32_t)f, stop, late + slot);
                             __threadfence();
@@ -1669,7 +1709,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
                 }
                 if (handed) continue;
                 KW::search_finish(s);
-                pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot, kp.ext);
+                pk_emit<M, NW, GEN>(io, f, fr.YH, s.bestF, CW, s.trials, s.tsteps + s.nimpr + kp.extra_ops, s.tsteps + kp.extra_ops, s.flags, tot, kp.ext, wm.alpha);
             }
             cur_frame = -1;   // the warps of this CTA hold different frames now
             __threadfence();
@@ -1683,13 +1723,21 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
                 uint32_t cmd = 0, a0 = 0, a1 = 0, a2 = 0;   // 0 = look again, 1 = master of late frame a0, 2 = help slot a0 (generation a2) with chunk a1, 3 = leave
                 for (;;) {
                     const unsigned long long nl = pk_ld_vol(&ctl->n_late), ql = pk_ld_vol(&ctl->queue_late);
-                    if (ql >= (nl < (unsigned long long)PK_LATE_CAP ? nl : (unsigned long long)PK_LATE_CAP)) break;
+                    if (ql >= (nl < (unsigned long long)late_cap ? nl : (unsigned long long)late_cap)) break;
                     atomicAdd(&ctl->masters, 1ull);
                     if (atomicCAS(&ctl->queue_late, ql, ql + 1ull) == ql) { cmd = 1; a0 = (uint32_t)ql; break; }
                     atomicAdd(&ctl->masters, ~0ull);
                 }
                 if (!cmd && CH) {
+                    // slots with an open window (a bit mask: scanning all the slot records costs a helper ~100 us)
+                    unsigned long long act[PK_MEGA_SLOTS / 64];
+#pragma unroll
+                    for (int w = 0; w < PK_MEGA_SLOTS / 64; ++w) act[w] = pk_ld_vol(&ctl->mega_mask[w]);
                     for (uint32_t i = 0; i < (uint32_t)PK_MEGA_SLOTS && !cmd; ++i) {
+                        if (!((act[i >> 6] >> (i & 63u)) & 1ull)) {
+                            if (!(act[i >> 6] >> (i & 63u))) i |= 63u;   // nothing left in this word
+                            continue;
+                        }
                         PkMegaSlot *ms = io.mega + i;
                         const uint32_t st = pk_ld_vol(&ms->state);
                         if (!st) continue;
@@ -1711,7 +1759,7 @@ k_phase_b(PkDevTables tb, PkKanekoParams kp, PkIo io, PkPhaseCtl *ctl, PkLongRec
                     __threadfence();
                     if (leave) {
                         const unsigned long long nl = pk_ld_vol(&ctl->n_late);
-                        leave = pk_ld_vol(&ctl->queue_late) >= (nl < (unsigned long long)PK_LATE_CAP ? nl : (unsigned long long)PK_LATE_CAP);
+                        leave = pk_ld_vol(&ctl->queue_late) >= (nl < (unsigned long long)late_cap ? nl : (unsigned long long)late_cap);
                         __threadfence();
                         leave = leave && pk_ld_vol(&ctl->masters) == 0ull;
                     }
@@ -1984,16 +2032,19 @@ struct PkLaunch {
     // for its whole (persistent) life.  The class-table search needs >= 64 KB of L1 to keep its bitmap gathers in flight
     // (1.7 ms vs 3.1 ms per launch with 32 KB), so every kernel asks for the 164 KB configuration and sizes its grid for
     // it; only kernels whose single CTA does not fit take the maximum.
+    // big_smem: the bit-sliced wide search of the large codes keeps its Berlekamp-Massey state in shared memory (20-32 KB per
+    // warp) and gathers nothing from global memory: it takes the whole 227 KB so that a second CTA fits next to the first
+    // (BCH(127,64,21): 4 -> 8 warps per SM; with one warp per scheduler the ALU pipe idles on every dependent LOP3).
     template <class K>
-    static cudaError_t fit(K kernel, int threads, size_t dyn, int sm_count, PkLaunchGeom *g) {
+    static cudaError_t fit(K kernel, int threads, size_t dyn, int sm_count, PkLaunchGeom *g, bool big_smem = false) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return e;
         cudaFuncAttributes fa;
         e = cudaFuncGetAttributes(&fa, kernel);
         if (e != cudaSuccess) return e;
-        const size_t budget = (size_t)164 << 10, per_cta = dyn + fa.sharedSizeBytes + 1024;
+        const size_t budget = (size_t)(big_smem ? 227 : 164) << 10, per_cta = dyn + fa.sharedSizeBytes + 1024;
         const bool fits = per_cta <= budget;
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, fits ? 70 : 100);
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (fits && !big_smem) ? 70 : 100);
         if (e != cudaSuccess) return e;
         int per = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, threads, dyn);
@@ -2009,7 +2060,8 @@ struct PkLaunch {
     static cudaError_t geom_one(int nk, int sm_count, PkLaunchGeom *ga, PkLaunchGeom *gb) {
         cudaError_t e = fit(k_phase_a<M, T, LUT, GEN, CT>, PK_WARPS_A * 32, PkSmem<M, T, LUT, CT>::total_a(nk), sm_count, ga);
         if (e != cudaSuccess) return e;
-        return fit(k_phase_b<M, T, LUT, GEN, CT>, PkSmem<M, T, LUT, CT>::WB * 32, PkSmem<M, T, LUT, CT>::total_b(nk), sm_count, gb);
+        return fit(k_phase_b<M, T, LUT, GEN, CT>, PkSmem<M, T, LUT, CT>::WB * 32, PkSmem<M, T, LUT, CT>::total_b(nk), sm_count, gb,
+                   PkSmem<M, T, LUT, CT>::BSM);
     }
     // out[0..1] = replay phase A / B, out[2..3] = generation phase A / B
     static cudaError_t geom_kaneko(int mode, int nk, int sm_count, PkLaunchGeom *out) {

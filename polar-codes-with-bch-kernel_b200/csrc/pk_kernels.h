@@ -8,7 +8,6 @@
 #include "pk_code.h"
 
 #define PK_HUGE_CAP 4096   // records behind the main parked-frame list for the huge frames
-#define PK_LATE_CAP 4096   // ... and behind those, for one-warp searches handed over to a whole CTA
 #define PK_MEGA_SLOTS 256  // long searches open to helpers at any one time
 struct PkMegaSlot;
 
@@ -87,9 +86,9 @@ struct PkPhaseCtl {
     unsigned long long n_big;       // parked big frames: longs[cap-1 .. cap-n_big] (filled from the top)
     unsigned long long n_huge;      // parked huge frames: longs[cap .. cap+n_huge) (may count past PK_HUGE_CAP: the overflow went to the big list)
     // phase B end game
-    unsigned long long n_late;          // one-warp searches handed over to a whole CTA: longs[cap + PK_HUGE_CAP ..) (may count past PK_LATE_CAP)
+    unsigned long long n_late;          // one-warp searches handed over to a whole CTA: longs[cap + PK_HUGE_CAP ..) (cap of them at most)
     unsigned long long queue_late;      // next of them to take
-    unsigned long long n_mega;          // mega slots in use
+    unsigned long long mega_mask[PK_MEGA_SLOTS / 64];   // slots with an open window
     unsigned long long ctas_past_solo;  // CTAs that have left the one-warp loop: once all have, n_late is final
     unsigned long long masters;         // CTAs that are (or are about to become) the master of a late frame
 };

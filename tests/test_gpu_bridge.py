@@ -23,7 +23,8 @@ def test_bridge_equals_trellis_processor_16(pk, enum_dim):
     kp = pk.KanekoKernelProc(4, enum_dim=enum_dim)
     assert kp.size == 16 and kp.mode[0] == 1
     if enum_dim == 0:
-        assert (kp.mode[1:15] == 2).all() and set(kp.t[1:15]) <= {1, 2, 3}
+        # rows 1..10 leave an extended BCH code with t = 1, 2, 3 in the tail; the last rows (repetition-code tail) are enumerated
+        assert (kp.mode[1:11] == 2).all() and set(kp.t[1:11]) == {1, 2, 3} and (kp.mode[11:] == 0).all()
     p = pk.Polar(pk.load_spec(), L=1, device=0)
     rng = np.random.default_rng(3)
     B = 400

@@ -1,64 +1,78 @@
-"""GPU, generation mode: FER (and the average number of algebraic trials) of the Philox-driven
-Monte-Carlo against the reference's published curves (out/*.csv, values quoted in BASELINE.md).
+"""GPU, generation mode: FER of the Philox-driven Monte-Carlo against EVERY published curve of the reference
+(out/*.csv: 36 files with data, 11 Eb/N0 points each; numbers committed as tests/golden/ref_curves.json by
+tests/golden/make_ref_curves.py) -- the `FER within the 95 % CI of the reference's curves` half of the north star.
 
-The reference points carry only e = 100 or 1000 error events (dataForPlot.cpp:43), so the check is:
-our FER (>= 10x more frames) lies inside the 99.9 % two-sided binomial interval of the reference
-point, widened by our own (much smaller) sampling error.  Full-size property checks (10^6 frames per
-point: split invariance, counters) are in test_gpu_fullsize.py."""
-import math
+A reference point is k_ref frame errors in n_ref frames (stop rule `count < p && countErr < e`, dataForPlot.cpp:43:
+e = 100 or 1000, p = 10^6), i.e. a wide binomial interval; ours uses up to 3000 errors / 2*10^7 frames.  Per point the
+two exact (Clopper-Pearson) intervals must intersect: at 95 % this fails by chance for about one point in twenty even for
+identical decoders, so the per-curve test demands the 99.99 % intervals for every point and at most 3 of 11 misses at
+95 %, and the summary test bounds the overall 95 % miss rate (396 points) at 9 % (expected 5 % + 3.6 sigma).
+The average number of algebraic trials per frame (column 3/4 of the files) is heavy-tailed; it is compared loosely."""
+import json
+import os
 
 import numpy as np
 import pytest
+from scipy.stats import beta
 
 pytestmark = pytest.mark.gpu
 
-# out/15_5_7_new.csv (e = 1000), out/31_16_7.csv (e = 100), out/63_30_13_e15.csv (e = 100, J = 15)
-REF = {
-    (4, 3, -1, 1000): dict(
-        fer=[0.170242, 0.130107, 0.0997009, 0.0637389, 0.0433426, 0.0299204, 0.017404, 0.00997079, 0.00511946, 0.00249565, 0.00101912],
-        trials=[9.75672, 8.1478, 6.29182, 5.07426, 4.00121, 3.11555, 2.44913, 1.99461, 1.68766, 1.51712, 1.4479]),
-    (5, 3, -1, 100): dict(
-        fer=[0.2849, 0.262467, 0.154083, 0.0976562, 0.0660939, 0.034002, 0.0154154, 0.00677186, 0.00211341, 0.000681426, 0.000210735],
-        trials=[1231.44, 936.034, 614.404, 255.855, 182.939, 97.185, 43.1989, 15.6042, 5.93472, 2.6529, 1.84171]),
-    (6, 6, 15, 100): dict(
-        fer=[0.37594, 0.248139, 0.132802, 0.0693481, 0.0269179, 0.0103402, 0.00231358, 0.000495233, 7.4e-05, 1.1e-05, 0.0],
-        trials=[24465.3, 20655.5, 16494.2, 11572.5, 7504.13, 4161.11, 1644.66, 596.437, 164.899, 36.463, 7.16645]),
-}
+CURVES = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_curves.json")))
+P_REF = 1_000_000
+RESULTS = []   # (curve, ebn0, miss95, miss9999) of every point checked in this session
 
 
-def _ref_interval(fer, e, z=3.3):
-    """Interval for the TRUE error rate given the reference stopped at e errors (n = e / fer frames)."""
+def cp(k, n, conf):
+    """Clopper-Pearson interval of a binomial proportion."""
+    a = 1 - conf
+    lo = 0.0 if k == 0 else float(beta.ppf(a / 2, k, n - k + 1))
+    hi = 1.0 if k == n else float(beta.ppf(1 - a / 2, k + 1, n - k))
+    return lo, hi
+
+
+def ref_point(fer, e):
     if fer <= 0:
-        return 0.0, 1.0
-    n = max(e / fer, e)
-    # Wilson interval
-    c = fer + z * z / (2 * n)
-    h = z * math.sqrt(fer * (1 - fer) / n + z * z / (4 * n * n))
-    d = 1 + z * z / n
-    return max(0.0, (c - h) / d), min(1.0, (c + h) / d)
+        return 0, P_REF
+    if e / fer <= P_REF * 1.0005:
+        return e, max(e, int(round(e / fer)))
+    return int(round(fer * P_REF)), P_REF
 
 
-@pytest.mark.parametrize("m,t,J,e,frames,points", [
-    (4, 3, -1, 1000, 400_000, range(11)),
-    (5, 3, -1, 100, 100_000, range(11)),
-    (6, 6, 15, 100, 30_000, [0, 2, 4, 6, 8]),
-])
-def test_fer_inside_reference_interval(pk, m, t, J, e, frames, points):
-    code = pk.Code(m, t, device=0)
-    kan = pk.Kaneko(code, J=J)
-    ref = REF[(m, t, J, e)]
-    bad = []
-    for si in points:
-        snr = 0.5 * si
-        tot, _ = kan.run_frames(snr, si, 20260101, 0, frames)
-        assert tot["frames"] == frames
-        fer = tot["frame_errors"] / frames
-        lo, hi = _ref_interval(ref["fer"][si], e)
-        ours = 3.3 * math.sqrt(max(fer * (1 - fer), 1.0 / frames) / frames)
-        ok = (lo - ours) <= fer <= (hi + ours)
-        # the average trial count is heavy-tailed; require the right order of magnitude only
-        tr = tot["trials"] / frames
-        ok_tr = 0.5 * ref["trials"][si] <= tr <= 2.0 * ref["trials"][si]
-        if not (ok and ok_tr):
-            bad.append((snr, fer, (lo, hi), tr, ref["trials"][si]))
-    assert not bad, f"outside the reference interval: {bad}"
+@pytest.mark.parametrize("name", sorted(CURVES))
+def test_fer_curve_within_reference_interval(pk, name):
+    c = CURVES[name]
+    code = pk.Code(c["m"], c["t"], device=0)
+    assert (code.n, code.k, code.d) == (c["n"], c["k"], c["d"])
+    kan = pk.Kaneko(code, J=c["J"], max_trials=1 << 28)
+    miss95, report = 0, []
+    for si, snr in enumerate(c["ebn0_db"]):
+        assert abs(snr - 0.5 * si) < 1e-9
+        k_ref, n_ref = ref_point(c["fer"][si], c["e"])
+        r = kan.run_point(snr, si, 20261018, 20_000_000, 3000)
+        assert not (r["flags_or"] & pk.PK_FLAG_TRUNCATED), "a search hit the 2^28 safety bound"
+        k, n = r["frame_errors"], r["frames"]
+        out = {}
+        for conf in (0.95, 0.9999):
+            lo_r, hi_r = cp(k_ref, n_ref, conf)
+            lo_o, hi_o = cp(k, n, conf)
+            out[conf] = not (hi_o < lo_r or hi_r < lo_o)
+        tr_ratio = (r["trials"] / n) / c["trials"][si]
+        tol = (0.6, 1.6) if c["J"] >= 0 else (0.2, 5.0)
+        ok_tr = tol[0] <= tr_ratio <= tol[1]
+        RESULTS.append((name, snr, not out[0.95], not out[0.9999]))
+        miss95 += not out[0.95]
+        report.append(f"{snr:.1f} dB: ref {k_ref}/{n_ref} = {c['fer'][si]:.3e}, ours {k}/{n} = {k / n:.3e}, trials x{tr_ratio:.2f}"
+                      + ("" if out[0.95] else "  [outside 95 %]") + ("" if out[0.9999] else "  [OUTSIDE 99.99 %]") + ("" if ok_tr else "  [TRIALS]"))
+        assert out[0.9999] and ok_tr, "\n".join(report)
+    assert miss95 <= 3, "\n".join(report)
+    print("\n" + name + "\n  " + "\n  ".join(report))
+
+
+def test_zz_overall_miss_rate_at_95_percent():
+    """runs after the per-curve tests (alphabetical order inside the module)"""
+    if len(RESULTS) < 100:
+        pytest.skip("needs the per-curve tests of this module in the same session")
+    rate = sum(r[2] for r in RESULTS) / len(RESULTS)
+    assert rate <= 0.09, f"{rate:.3f} of {len(RESULTS)} points outside the 95 % intervals"
+    assert not any(r[3] for r in RESULTS)
+    print(f"\n{len(RESULTS)} reference points checked, {100 * rate:.1f} % outside the 95 % intervals (5 % expected by chance)")
