@@ -239,6 +239,10 @@ class Env:
         return self.torch.cuda.Event(enable_timing=True)
 
     def close(self):
+        # torch's current stream is the communicator's: hand it back before that stream is destroyed (tensors freed
+        # afterwards would query a dead stream)
+        self.torch.cuda.synchronize()
+        self.torch.cuda.set_stream(self.torch.cuda.default_stream(self.dev))
         self.comm.close()
         if self.world > 1:
             self.dist.destroy_process_group()

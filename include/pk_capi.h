@@ -299,6 +299,21 @@ int pk_kproc_get_llrs(pk_kproc *h, int stride, int phase, const uint8_t *known, 
 /* all phases of B independent kernel blocks, layout of pk_polar_kernel_llrs: chan [B][l], u [B][l] -> out [B][l] */
 int pk_kproc_kernel_llrs(pk_kproc *h, const float *chan, const uint8_t *u, long B, float *out, long *truncated);
 
+/* ---- kernel construction tooling of the reference's newer bchCoder.cpp
+ * Work of the trellis kernel processor (TrellisKernelProcessor.cpp:234-295) on a binary size x size kernel: branch
+ * evaluations of one GetLLRs pass over all phases (11 712 for the 16 x 16 extended-BCH kernel) and the largest number of
+ * state bits.  Stands in for the Sum/Cmp counters of the `SectionedTrellisKernelProcessor` the reference's own scoring
+ * calls but does not ship (root bchCoder.cpp:13,497-511). */
+int pk_kernel_trellis_cost(int size, const uint8_t *matrix, uint64_t *branches, int *max_state_bits);
+/* swapColumns (root bchCoder.cpp:478-496): columns 0..2 stay, column i >= 3 <- column j+1 with fieldElements[j] == i */
+int pk_kernel_swap_columns(int power, const uint64_t *field_elements /*[2^power]*/, const uint8_t *matrix, uint8_t *out);
+/* candidate `trial` of the random search: B = L U (randomInvertibleMatrix :766-784) drawn from Philox(seed, trial),
+ * column j <- column B j (:604-622); basis_out [power] = newBasis */
+int pk_kernel_permute_columns(int power, const uint8_t *matrix, uint64_t seed, uint64_t trial, uint8_t *out, uint32_t *basis_out);
+/* randomSwapColumns (:541-699) on the GPU, one thread per candidate: ntrials <= 2^26 (the reference: 2*10^7) */
+int pk_kernel_random_search(int power, const uint8_t *matrix, long ntrials, uint64_t seed, int device, int max_state_bits,
+                            uint8_t *best_matrix, uint32_t *best_basis, uint64_t *best_cost, uint64_t *best_trial, uint64_t *input_cost);
+
 /* Introspection for bench.py: kernels launched by this library since load / reset. */
 uint64_t pk_launch_count(void);
 void pk_launch_count_reset(void);

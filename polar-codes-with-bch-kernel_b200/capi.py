@@ -39,7 +39,8 @@ SYMBOLS = (
     "pk_comm_create pk_comm_unique_id pk_comm_create_rank pk_comm_destroy pk_comm_size pk_comm_rank pk_comm_local_devices pk_comm_stream "
     "pk_allreduce_point pk_comm_sync pk_comm_kaneko_create pk_comm_kaneko_destroy pk_comm_kaneko_local pk_comm_run_point "
     "pk_kproc_create pk_kproc_destroy pk_kproc_info pk_kproc_get_llrs pk_kproc_kernel_llrs "
-    "pk_polar_run_frames_dev pk_polar_run_frames pk_polar_generate_frames_dev pk_polar_generate_frames"
+    "pk_polar_run_frames_dev pk_polar_run_frames pk_polar_generate_frames_dev pk_polar_generate_frames "
+    "pk_kernel_trellis_cost pk_kernel_swap_columns pk_kernel_permute_columns pk_kernel_random_search"
 ).split()
 
 
@@ -123,6 +124,10 @@ def _load():
     lib.pk_polar_run_frames.argtypes = [vp, d, i, u64, u64, l, vp]
     lib.pk_polar_generate_frames_dev.argtypes = [vp, d, i, u64, u64, l, vp, vp, vp, vp]
     lib.pk_polar_generate_frames.argtypes = [vp, d, i, u64, u64, l, vp, vp, vp]
+    lib.pk_kernel_trellis_cost.argtypes = [i, vp, vp, ip]
+    lib.pk_kernel_swap_columns.argtypes = [i, vp, vp, vp]
+    lib.pk_kernel_permute_columns.argtypes = [i, vp, u64, u64, vp, vp]
+    lib.pk_kernel_random_search.argtypes = [i, vp, l, u64, i, i, vp, vp, vp, vp, vp]
     lib.pk_kproc_create.argtypes = [i, i, l, i, pp]
     lib.pk_kproc_destroy.argtypes = [vp]
     lib.pk_kproc_destroy.restype = None
@@ -392,6 +397,42 @@ class CommKaneko:
         tot = np.zeros(8, np.uint64)
         _check(lib.pk_comm_run_point(self.h, float(ebn0_db), int(snr_index), int(seed), int(p), int(e), _np_ptr(tot)))
         return dict(zip(POINT_FIELDS, (int(v) for v in tot)))
+
+
+def kernel_trellis_cost(matrix):
+    """(branch evaluations of one pass over all phases, max state bits) of the trellis kernel processor for `matrix`."""
+    matrix = np.ascontiguousarray(matrix, np.uint8)
+    cost = np.zeros(1, np.uint64)
+    mb = C.c_int()
+    _check(lib.pk_kernel_trellis_cost(matrix.shape[0], _np_ptr(matrix), _np_ptr(cost), C.byref(mb)))
+    return int(cost[0]), mb.value
+
+
+def kernel_swap_columns(power, field_elements, matrix):
+    matrix = np.ascontiguousarray(matrix, np.uint8)
+    fe = np.ascontiguousarray(field_elements, np.uint64)
+    out = np.zeros_like(matrix)
+    _check(lib.pk_kernel_swap_columns(int(power), _np_ptr(fe), _np_ptr(matrix), _np_ptr(out)))
+    return out
+
+
+def kernel_permute_columns(power, matrix, seed, trial):
+    matrix = np.ascontiguousarray(matrix, np.uint8)
+    out = np.zeros_like(matrix)
+    basis = np.zeros(power, np.uint32)
+    _check(lib.pk_kernel_permute_columns(int(power), _np_ptr(matrix), int(seed), int(trial), _np_ptr(out), _np_ptr(basis)))
+    return out, basis
+
+
+def kernel_random_search(power, matrix, ntrials, seed=1, device=0, max_state_bits=0):
+    """randomSwapColumns on the GPU -> dict(matrix, basis, cost, trial, input_cost)"""
+    matrix = np.ascontiguousarray(matrix, np.uint8)
+    out = np.zeros_like(matrix)
+    basis = np.zeros(power, np.uint32)
+    v = np.zeros(3, np.uint64)
+    _check(lib.pk_kernel_random_search(int(power), _np_ptr(matrix), int(ntrials), int(seed), int(device), int(max_state_bits), _np_ptr(out), _np_ptr(basis),
+                                       v[0:1].ctypes.data_as(C.c_void_p), v[1:2].ctypes.data_as(C.c_void_p), v[2:3].ctypes.data_as(C.c_void_p)))
+    return dict(matrix=out, basis=basis, cost=int(v[0]), trial=int(v[1]), input_cost=int(v[2]))
 
 
 class KanekoKernelProc:

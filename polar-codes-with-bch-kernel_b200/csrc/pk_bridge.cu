@@ -209,9 +209,11 @@ int pk_kproc_create(int m, int device, long max_trials, int enum_dim, pk_kproc *
         for (int c = 0; c < l; ++c)
             if (K[(size_t)r * l + c]) h->rows[r] |= 1ull << c;
     // extended BCH codes ext(C_t) in column order: column p+1 = coefficient of x^p, column 0 = overall parity
+    // (several designed t give the same code; the largest one with sm_100a kernels decodes it best)
     struct Cand { int t, k; std::vector<uint64_t> gen; };
     std::vector<Cand> cands;
     for (int t = 1; t < (1 << (m - 1)); ++t) {
+        if (!pk_find_kernels(m, t)) continue;
         pk_code *c = nullptr;
         if (pk_code_create_host(m, t, &c) != PK_OK) continue;
         int nn = 0, kk = 0, gs = 0;
@@ -219,7 +221,6 @@ int pk_kproc_create(int m, int device, long max_trials, int enum_dim, pk_kproc *
         std::vector<uint8_t> g(gs);
         pk_code_info(c, nullptr, nullptr, nullptr, nullptr, g.data());
         pk_code_destroy(c);
-        if (!cands.empty() && cands.back().k == kk) continue;   // same code as the previous designed distance
         Cand cd;
         cd.t = t; cd.k = kk;
         for (int s = 0; s < kk; ++s) {
@@ -230,7 +231,8 @@ int pk_kproc_create(int m, int device, long max_trials, int enum_dim, pk_kproc *
             if (wt & 1) w |= 1ull;
             cd.gen.push_back(w);
         }
-        cands.push_back(cd);
+        if (!cands.empty() && cands.back().k == kk) cands.back() = cd;   // same code, larger designed t
+        else cands.push_back(cd);
     }
     h->plan.assign(l, PhasePlan());
     std::string err;
@@ -254,7 +256,6 @@ int pk_kproc_create(int m, int device, long max_trials, int enum_dim, pk_kproc *
                 bool inside = true;
                 for (uint64_t w : cd.gen) inside = inside && gf2_in_span(tail, w);
                 if (!inside) continue;
-                if (!pk_find_kernels(m, cd.t)) continue;   // no sm_100a instantiation for this (m, t): try the next smaller code
                 pl.mode = KP_BCH;
                 pl.t = cd.t;
                 for (uint64_t w : cd.gen) gf2_rank_insert(have, w);

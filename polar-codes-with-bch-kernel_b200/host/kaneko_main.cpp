@@ -4,6 +4,7 @@
 //   kaneko_b200 <m> <t> <snr> <file>          word + samples from <file>
 //   kaneko_b200 <m> <t> <file> <p> <e>        FER sweep 0..5 dB -> <file>.csv
 // optional trailing flags: --J <cap>  --seed <s>  --gpus <n> (frames of every SNR point sharded over n GPUs of the box)
+//                          --errwords <file> (the reference's DEBUG dump of non-ML frames, dataForPlot.cpp:55-64; one GPU)
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -26,6 +27,7 @@ int main(int argc, char *argv[]) {
             if (!std::strcmp(argv[i], "--J") && i + 1 < argc) J = std::atol(argv[++i]);
             else if (!std::strcmp(argv[i], "--seed") && i + 1 < argc) fun_seed = std::strtoull(argv[++i], nullptr, 10);
             else if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = std::atoi(argv[++i]);
+            else if (!std::strcmp(argv[i], "--errwords") && i + 1 < argc) fun_errwords = argv[++i];
             else pos.push_back(argv[i]);
         }
         const int n_args = (int)pos.size();

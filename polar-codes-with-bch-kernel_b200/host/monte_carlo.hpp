@@ -13,3 +13,5 @@
 void fun(const std::string &file, KanekoKernelProcessor &decoder, const unsigned char *g, unsigned long gSize, long p,
          long e, double maxSTNR = 5.0);
 extern uint64_t fun_seed;
+// non-empty: write the frames the decoder did not decode maximum-likelihood there (the reference's DEBUG build, out/errWords.txt)
+extern std::string fun_errwords;

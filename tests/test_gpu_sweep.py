@@ -133,3 +133,57 @@ def test_c_abi_two_gpus_equal_one_gpu(pk, tmp_path):
             out = subprocess.run([exe, "5", "3", str(tmp_path / f"c{g}"), "60000", "250", "--gpus", str(g)], capture_output=True, text=True, timeout=600)
             assert out.returncode == 0, out.stderr
         assert open(tmp_path / "c1.csv").read() == open(tmp_path / "c2.csv").read()
+
+
+def test_non_ml_flag_and_errwords_dump(pk, tmp_path):
+    """The reference's DEBUG build writes the frames whose transmitted word is more likely than the decision
+    (calcL(res) < calcL(decoded), dataForPlot.cpp:55-64) to out/errWords.txt.  BCH(15,11,3) has plenty of them (the
+    reference's rules are not ML there): the kernels' PK_FLAG_NON_ML equals the definition recomputed from
+    the dumped frames, and `kaneko_b200 --errwords` writes exactly those frames in the reference's format."""
+    code = pk.Code(4, 1, device=0)
+    kan = pk.Kaneko(code)
+    B, snr, si, seed = 20000, 1.0, 2, 1
+    tot, recs = kan.run_frames(snr, si, seed, 0, B, want_recs=True)
+    info, cw, y = kan.generate_frames(snr, si, seed, 0, B)
+    dec, *_ = kan.decode(y)
+    alpha = np.abs(y)
+    yh = (y > 0).astype(np.uint8)
+    l_tx = (alpha * (yh != cw)).sum(1)
+    l_dec = (alpha * (yh != dec)).sum(1)
+    want = (l_tx < l_dec) & (dec != cw).any(1)
+    got = (recs["flags"] & pk.PK_FLAG_NON_ML) != 0
+    # sums in another order may differ in the last ulp: compare away from exact ties
+    clear = np.abs(l_tx - l_dec) > 1e-9 * (l_tx + l_dec + 1e-300)
+    assert np.array_equal(got[clear], want[clear]) and got.sum() > 100
+    assert bool(tot["flags_or"] & pk.PK_FLAG_NON_ML)
+    exe = os.path.join(PKG, "kaneko_b200")
+    if not os.path.exists(exe):
+        pytest.skip("kaneko_b200 not built")
+    ew = tmp_path / "errWords.txt"
+    out = subprocess.run([exe, "4", "1", str(tmp_path / "dbg"), "3000", "1000000", "--errwords", str(ew)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = ew.read_text().splitlines()
+    blocks = [lines[i:i + 4] for i in range(0, len(lines), 4)]
+    assert len(blocks) > 50 and all(len(b) == 4 and b[3] == "" for b in blocks)
+    n0 = sum(1 for b in blocks if b[0] == "0")
+    _, r0 = kan.run_frames(0.0, 0, 1, 0, 3000, want_recs=True)
+    assert n0 == int(((r0["flags"] & pk.PK_FLAG_NON_ML) != 0).sum())
+    assert len(blocks[0][1].split()) == 15 and len(blocks[0][2].split()) == 15
+
+
+def test_random_column_permutation_search(pk):
+    """randomSwapColumns (root bchCoder.cpp:541-699) on the GPU: the winner's cost is what the host evaluates for the
+    same trial, it does not exceed the natural order's, and every candidate is a column permutation of the kernel."""
+    E = pk.ebch_kernel(4)
+    r = pk.kernel_random_search(4, E, 300000, seed=5)
+    assert r["input_cost"] == 11712 and r["cost"] <= r["input_cost"]
+    again, basis = pk.kernel_permute_columns(4, E, 5, r["trial"])
+    assert np.array_equal(again, r["matrix"]) and np.array_equal(basis, r["basis"])
+    assert pk.kernel_trellis_cost(r["matrix"])[0] == r["cost"]
+    assert sorted(map(tuple, r["matrix"].T.tolist())) == sorted(map(tuple, E.T.tolist()))
+    # brute force over the first trials on the host agrees with the device's minimum over the same range
+    few = pk.kernel_random_search(4, E, 500, seed=5)
+    host = min((pk.kernel_trellis_cost(pk.kernel_permute_columns(4, E, 5, t)[0])[0], t) for t in range(500))
+    assert (few["cost"], few["trial"]) == host
+    r5 = pk.kernel_random_search(5, pk.ebch_kernel(5), 100000, seed=2, max_state_bits=14)
+    assert r5["cost"] <= r5["input_cost"]

@@ -74,3 +74,36 @@ def test_dynamic_frozen_and_shortened_specs_parse(pk):
     dyn[i] = " ".join([t[0], t[2], t[1], t[3]])
     with pytest.raises(pk.PkError):
         pk.Polar("\n".join(dyn), device=None)
+
+
+def test_trellis_cost_equals_the_built_trellis(pk, tmp_path):
+    """pk_kernel_trellis_cost (rank formula, what the permutation search scores) == the branch count of the trellises
+    pk_polar_build_trellis constructs, for the natural order and for random linear column permutations."""
+    E = pk.ebch_kernel(4)
+    assert pk.kernel_trellis_cost(E) == (11712, 8)   # SURVEY.md 8a
+    for trial in range(6):
+        P, basis = pk.kernel_permute_columns(4, E, 3, trial)
+        assert sorted(P.sum(0)) == sorted(E.sum(0)) and np.array_equal(np.sort(P, axis=1), np.sort(E, axis=1))
+        cost, mb = pk.kernel_trellis_cost(P)
+        kf = tmp_path / f"k{trial}.kernel"
+        kf.write_text("16\n" + "\n".join(" ".join(str(int(v)) for v in r) for r in P) + "\n")
+        spec = "16 8 1 1 0 0\n-%s\n" % kf + "".join("1 %d\n" % i for i in range(8))
+        prof = pk.Polar(spec, L=1, device=None).trellis_profile(0)
+        assert cost == int((2 * 2 ** prof[:, :16].astype(np.int64)).sum()) and mb == prof.max()
+
+
+def test_swap_columns_restatement(pk):
+    """swapColumns (root bchCoder.cpp:478-496): columns 0..2 stay, column i <- column j+1 with fieldElements[j] == i."""
+    E = pk.ebch_kernel(4)
+    rng = np.random.default_rng(4)
+    fe = np.zeros(16, np.uint64)
+    fe[2:15] = rng.permutation(np.arange(3, 16))    # fieldElements[j] = value carried by column j+1
+    fe[15] = 2
+    S = pk.kernel_swap_columns(4, fe, E)
+    want = E.copy()
+    for i in range(3, 16):
+        j = next(j for j in range(2, 16) if fe[j] == i)
+        want[:, i] = E[:, j + 1]
+    assert np.array_equal(S[:, :3], E[:, :3]) and np.array_equal(S, want)
+    with pytest.raises(pk.PkError):   # a value nobody carries
+        pk.kernel_swap_columns(4, np.zeros(16, np.uint64), E)
