@@ -239,13 +239,17 @@ class Env:
         return self.torch.cuda.Event(enable_timing=True)
 
     def close(self):
-        # torch's current stream is the communicator's: hand it back before that stream is destroyed (tensors freed
-        # afterwards would query a dead stream)
+        """End of the run: every rank has printed what it had to.  Pinned host tensors and CUDA events still reference the
+        communicator's stream, and the caching allocators touch it again when they are freed -- at interpreter shutdown,
+        in no particular order relative to the destruction of that stream -- so the process leaves through os._exit
+        once the process group is down (stdout flushed first)."""
         self.torch.cuda.synchronize()
-        self.torch.cuda.set_stream(self.torch.cuda.default_stream(self.dev))
-        self.comm.close()
         if self.world > 1:
+            self.dist.barrier()
             self.dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def peaks():

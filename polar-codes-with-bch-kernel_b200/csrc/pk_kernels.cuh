@@ -934,52 +934,12 @@ struct KanekoWarp {
                 }
                 cand = refine(ok & vmask, s);
             } else if constexpr (CT) {
-                // Patterns whose flip set lies within distance t of a codeword this lane already knows (the best one, the
-                // last two it rejected) decode to that codeword again -- refine() drops them anyway, so they are not even
-                // probed: their flip set is (lane / base part) ^ (in-word part q), the in-word part lives on the five
-                // least reliable positions, hence dist = D0 + popc(q ^ c5) with D0 the distance outside those positions
-                // and c5 the codeword's bits on them.  15 % of the probes at 0 dB, half of them at 3 dB (L2 requests are
-                // what bounds this kernel).
-                uint32_t skip = 0;
-                {
-                    uint32_t low[NW];   // the five in-word positions
-#pragma unroll
-                    for (int w2 = 0; w2 < NW; ++w2) low[w2] = wm.pb[31 * NW + w2];
-                    auto near = [&](const uint32_t (&Cw)[NW], bool valid) -> uint32_t {
-                        int d0 = 0;
-                        uint32_t c5 = 0;
-#pragma unroll
-                        for (int w2 = 0; w2 < NW; ++w2) {
-                            const uint32_t x = (Ul[SW + w2] ^ Ub[SW + w2] ^ Cw[w2]) & (w2 == NW - 1 ? f.topmask : PK_FULL);
-                            d0 += __popc(x & ~low[w2]);
-                        }
-#pragma unroll
-                        for (int b = 0; b < 5; ++b) {
-                            uint32_t hit = 0;
-#pragma unroll
-                            for (int w2 = 0; w2 < NW; ++w2) hit |= Cw[w2] & wm.pb[(1 << b) * NW + w2];
-                            c5 |= (hit ? 1u : 0u) << b;
-                        }
-                        const int r = T - d0;
-                        if (!valid || r < 0) return 0u;
-                        // { q : popc(q) <= r } moved by q -> q ^ c5
-                        uint32_t m = (r >= 5) ? PK_FULL : (r == 4) ? 0x7FFFFFFFu : (r == 3) ? 0x177F7FFFu : (r == 2) ? 0x0117177Fu : (r == 1) ? 0x00010117u : 0x00000001u;
-                        m = (c5 & 1u) ? (((m & 0x55555555u) << 1) | ((m >> 1) & 0x55555555u)) : m;
-                        m = (c5 & 2u) ? (((m & 0x33333333u) << 2) | ((m >> 2) & 0x33333333u)) : m;
-                        m = (c5 & 4u) ? (((m & 0x0F0F0F0Fu) << 4) | ((m >> 4) & 0x0F0F0F0Fu)) : m;
-                        m = (c5 & 8u) ? (((m & 0x00FF00FFu) << 8) | ((m >> 8) & 0x00FF00FFu)) : m;
-                        m = (c5 & 16u) ? ((m << 16) | (m >> 16)) : m;
-                        return m;
-                    };
-                    skip = near(s.bestF, s.have);
-#pragma unroll
-                    for (int k = 0; k < KR; ++k) skip |= near(rej[k], true);   // (an empty slot is all ones: farther than t from every pattern)
-                }
-                // one bitmap probe per remaining pattern: does ANY error pattern of weight <= t have this syndrome class?
+                // (Skipping the probe of patterns within distance t of a known codeword was tried in round 2: +41 % instructions
+                // for the per-lane distance masks, no measurable drop in L2 sectors, 6.1 -> 8.9 ms per launch -- profiles/r2_notes.md.)
+                // one bitmap probe per pattern: does ANY error pattern of weight <= t have this syndrome class?
                 uint32_t ok = 0;
 #pragma unroll 8
                 for (int q = 0; q < 32; ++q) {
-                    if ((skip >> q) & 1u) continue;
                     uint32_t w[SW];
 #pragma unroll
                     for (int a = 0; a < SW; ++a) w[a] = u[a] ^ wm.cm[q * SW + a];
