@@ -312,7 +312,8 @@ int pk_kernel_swap_columns(int power, const uint64_t *field_elements /*[2^power]
 int pk_kernel_permute_columns(int power, const uint8_t *matrix, uint64_t seed, uint64_t trial, uint8_t *out, uint32_t *basis_out);
 /* randomSwapColumns (:541-699) on the GPU, one thread per candidate: ntrials <= 2^26 (the reference: 2*10^7) */
 int pk_kernel_random_search(int power, const uint8_t *matrix, long ntrials, uint64_t seed, int device, int max_state_bits,
-                            uint8_t *best_matrix, uint32_t *best_basis, uint64_t *best_cost, uint64_t *best_trial, uint64_t *input_cost);
+                            uint8_t *best_matrix, uint32_t *best_basis, uint64_t *best_cost, uint64_t *best_trial, uint64_t *input_cost,
+                            uint64_t *all_costs /*[ntrials] or NULL*/);
 
 /* Introspection for bench.py: kernels launched by this library since load / reset. */
 uint64_t pk_launch_count(void);

@@ -127,7 +127,7 @@ def _load():
     lib.pk_kernel_trellis_cost.argtypes = [i, vp, vp, ip]
     lib.pk_kernel_swap_columns.argtypes = [i, vp, vp, vp]
     lib.pk_kernel_permute_columns.argtypes = [i, vp, u64, u64, vp, vp]
-    lib.pk_kernel_random_search.argtypes = [i, vp, l, u64, i, i, vp, vp, vp, vp, vp]
+    lib.pk_kernel_random_search.argtypes = [i, vp, l, u64, i, i, vp, vp, vp, vp, vp, vp]
     lib.pk_kproc_create.argtypes = [i, i, l, i, pp]
     lib.pk_kproc_destroy.argtypes = [vp]
     lib.pk_kproc_destroy.restype = None
@@ -424,15 +424,16 @@ def kernel_permute_columns(power, matrix, seed, trial):
     return out, basis
 
 
-def kernel_random_search(power, matrix, ntrials, seed=1, device=0, max_state_bits=0):
-    """randomSwapColumns on the GPU -> dict(matrix, basis, cost, trial, input_cost)"""
+def kernel_random_search(power, matrix, ntrials, seed=1, device=0, max_state_bits=0, want_costs=False):
+    """randomSwapColumns on the GPU -> dict(matrix, basis, cost, trial, input_cost[, costs of all candidates])"""
     matrix = np.ascontiguousarray(matrix, np.uint8)
     out = np.zeros_like(matrix)
     basis = np.zeros(power, np.uint32)
     v = np.zeros(3, np.uint64)
+    costs = np.zeros(ntrials, np.uint64) if want_costs else None
     _check(lib.pk_kernel_random_search(int(power), _np_ptr(matrix), int(ntrials), int(seed), int(device), int(max_state_bits), _np_ptr(out), _np_ptr(basis),
-                                       v[0:1].ctypes.data_as(C.c_void_p), v[1:2].ctypes.data_as(C.c_void_p), v[2:3].ctypes.data_as(C.c_void_p)))
-    return dict(matrix=out, basis=basis, cost=int(v[0]), trial=int(v[1]), input_cost=int(v[2]))
+                                       v[0:1].ctypes.data_as(C.c_void_p), v[1:2].ctypes.data_as(C.c_void_p), v[2:3].ctypes.data_as(C.c_void_p), _np_ptr(costs)))
+    return dict(matrix=out, basis=basis, cost=int(v[0]), trial=int(v[1]), input_cost=int(v[2]), costs=costs)
 
 
 class KanekoKernelProc:

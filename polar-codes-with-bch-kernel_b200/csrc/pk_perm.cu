@@ -121,7 +121,7 @@ __host__ __device__ inline void permute_rows(int power, const unsigned long long
 
 __global__ void __launch_bounds__(128)
 k_perm_search(int power, const unsigned long long *rows, unsigned long long seed, unsigned long long first, long ntrials, int max_bits_allowed,
-              unsigned long long *best) {
+              unsigned long long *best, unsigned long long *costs_out) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ntrials) return;
     const int n = 1 << power;
@@ -132,6 +132,7 @@ k_perm_search(int power, const unsigned long long *rows, unsigned long long seed
     permute_rows(power, base, basis, cand);
     int mb = 0;
     const unsigned long long cost = trellis_cost(cand, n, &mb);
+    if (costs_out) costs_out[i] = cost;
     if (mb > max_bits_allowed) return;
     atomicMin(best, (cost << 26) | ((first + (unsigned long long)i) & 0x3FFFFFFull));
 }
@@ -196,7 +197,8 @@ int pk_kernel_permute_columns(int power, const uint8_t *matrix, uint64_t seed, u
 // trial that produced it and the cost of the input.  Candidates whose trellis would exceed max_state_bits (<= 22, the
 // default) are discarded.
 int pk_kernel_random_search(int power, const uint8_t *matrix, long ntrials, uint64_t seed, int device, int max_state_bits,
-                            uint8_t *best_matrix, uint32_t *best_basis, uint64_t *best_cost, uint64_t *best_trial, uint64_t *input_cost) {
+                            uint8_t *best_matrix, uint32_t *best_basis, uint64_t *best_cost, uint64_t *best_trial, uint64_t *input_cost,
+                            uint64_t *all_costs /*[ntrials] or NULL: the cost of every candidate (tests)*/) {
     if (power < 2 || power > 6 || !matrix || ntrials < 1 || ntrials > (1L << 26)) return pk_set_error(PK_ERR_ARG, "bad arguments (power in [2,6], 1 <= ntrials <= 2^26)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return pk_set_error(PK_ERR_CUDA, "no CUDA device: libpkb200 has no CPU path");
@@ -205,20 +207,23 @@ int pk_kernel_random_search(int power, const uint8_t *matrix, long ntrials, uint
     std::vector<unsigned long long> rows;
     rows_from_matrix(n, matrix, rows);
     if (input_cost) *input_cost = trellis_cost(rows.data(), n, nullptr);
-    unsigned long long *d_rows = nullptr, *d_best = nullptr, h_best = ~0ull;
+    unsigned long long *d_rows = nullptr, *d_best = nullptr, *d_costs = nullptr, h_best = ~0ull;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc(&d_rows, (size_t)n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d_best, 8);
     if (e == cudaSuccess) e = cudaMemcpy(d_rows, rows.data(), (size_t)n * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_best, &h_best, 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && all_costs) e = cudaMalloc(&d_costs, (size_t)ntrials * 8);
     if (e == cudaSuccess) {
-        k_perm_search<<<(unsigned)((ntrials + 127) / 128), 128>>>(power, d_rows, seed, 0ull, ntrials, (max_state_bits > 0 && max_state_bits <= 22) ? max_state_bits : 22, d_best);
+        k_perm_search<<<(unsigned)((ntrials + 127) / 128), 128>>>(power, d_rows, seed, 0ull, ntrials, (max_state_bits > 0 && max_state_bits <= 22) ? max_state_bits : 22, d_best, d_costs);
         ++g_pk_launches;
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(&h_best, d_best, 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && all_costs) e = cudaMemcpy(all_costs, d_costs, (size_t)ntrials * 8, cudaMemcpyDeviceToHost);
     cudaFree(d_rows);
     cudaFree(d_best);
+    cudaFree(d_costs);
     if (e != cudaSuccess) return pk_set_error(PK_ERR_CUDA, std::string("pk_kernel_random_search: ") + cudaGetErrorString(e));
     if (h_best == ~0ull) return pk_set_error(PK_ERR_UNSUPPORTED, "no candidate within the state-bit limit");
     const uint64_t trial = h_best & 0x3FFFFFFull;

@@ -175,15 +175,15 @@ def test_random_column_permutation_search(pk):
     """randomSwapColumns (root bchCoder.cpp:541-699) on the GPU: the winner's cost is what the host evaluates for the
     same trial, it does not exceed the natural order's, and every candidate is a column permutation of the kernel."""
     E = pk.ebch_kernel(4)
+    few = pk.kernel_random_search(4, E, 500, seed=5, want_costs=True)
+    host = np.array([pk.kernel_trellis_cost(pk.kernel_permute_columns(4, E, 5, t)[0])[0] for t in range(500)], np.uint64)
+    assert np.array_equal(few["costs"], host), f"device and host disagree on candidates {np.nonzero(few['costs'] != host)[0][:8]}"
+    assert (few["cost"], few["trial"]) == (int(host.min()), int(np.argmin(host)))
     r = pk.kernel_random_search(4, E, 300000, seed=5)
     assert r["input_cost"] == 11712 and r["cost"] <= r["input_cost"]
     again, basis = pk.kernel_permute_columns(4, E, 5, r["trial"])
     assert np.array_equal(again, r["matrix"]) and np.array_equal(basis, r["basis"])
     assert pk.kernel_trellis_cost(r["matrix"])[0] == r["cost"]
     assert sorted(map(tuple, r["matrix"].T.tolist())) == sorted(map(tuple, E.T.tolist()))
-    # brute force over the first trials on the host agrees with the device's minimum over the same range
-    few = pk.kernel_random_search(4, E, 500, seed=5)
-    host = min((pk.kernel_trellis_cost(pk.kernel_permute_columns(4, E, 5, t)[0])[0], t) for t in range(500))
-    assert (few["cost"], few["trial"]) == host
     r5 = pk.kernel_random_search(5, pk.ebch_kernel(5), 100000, seed=2, max_state_bits=14)
     assert r5["cost"] <= r5["input_cost"]
