@@ -87,35 +87,38 @@ __host__ __device__ inline void candidate_basis(int power, unsigned long long se
     }
     bits[0] = c0; bits[1] = c1; bits[2] = c2; bits[3] = c3;
 #endif
-    unsigned char L[8][8], U[8][8];
+    // row i of L (unit lower triangular) and column j of U (unit upper triangular) as bit masks over the inner index
+    unsigned int Lrow[8], Ucol[8];
+    for (int i = 0; i < 8; ++i) { Lrow[i] = 1u << i; Ucol[i] = 1u << i; }
     int q = 0;
-    for (int i = 0; i < power; ++i)
-        for (int j = 0; j < power; ++j) {
-            L[i][j] = (i == j);
-            U[i][j] = (i == j);
-        }
     for (int i = 0; i < power; ++i) {
-        for (int j = 0; j < i; ++j) { L[i][j] = (bits[q >> 5] >> (q & 31)) & 1u; ++q; }
-        for (int j = i + 1; j < power; ++j) { U[i][j] = (bits[q >> 5] >> (q & 31)) & 1u; ++q; }
+        for (int j = 0; j < i; ++j) { Lrow[i] |= ((bits[q >> 5] >> (q & 31)) & 1u) << j; ++q; }
+        for (int j = i + 1; j < power; ++j) { Ucol[j] |= ((bits[q >> 5] >> (q & 31)) & 1u) << i; ++q; }
     }
     for (int j = 0; j < power; ++j) {
         unsigned int col = 0;   // newBasis[j] = sum_k e_k b[k][j], b = L U
         for (int k = 0; k < power; ++k) {
-            unsigned char b = 0;
-            for (int x = 0; x < power; ++x) b ^= L[k][x] & U[x][j];
-            col |= (unsigned int)b << k;
+            unsigned int x = Lrow[k] & Ucol[j];
+            x ^= x >> 4; x ^= x >> 2; x ^= x >> 1;
+            col |= (x & 1u) << k;
         }
         basis[j] = col;
     }
 }
 __host__ __device__ inline void permute_rows(int power, const unsigned long long *rows, const unsigned int *basis, unsigned long long *out) {
     const int n = 1 << power;
-    for (int r = 0; r < n; ++r) out[r] = 0;
+    unsigned char src[64];   // column j of the new kernel is column src[j] = B j of the old one
     for (int j = 0; j < n; ++j) {
-        unsigned int src = 0;
+        unsigned int s = 0;
         for (int k = 0; k < power; ++k)
-            if ((j >> k) & 1) src ^= basis[k];
-        for (int r = 0; r < n; ++r) out[r] |= ((rows[r] >> src) & 1ull) << j;
+            if ((j >> k) & 1) s ^= basis[k];
+        src[j] = (unsigned char)(s & (unsigned int)(n - 1));
+    }
+    for (int r = 0; r < n; ++r) {
+        const unsigned long long w = rows[r];
+        unsigned long long o = 0;
+        for (int j = 0; j < n; ++j) o |= ((w >> src[j]) & 1ull) << j;
+        out[r] = o;
     }
 }
 
@@ -125,11 +128,10 @@ k_perm_search(int power, const unsigned long long *rows, unsigned long long seed
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ntrials) return;
     const int n = 1 << power;
-    unsigned long long base[64], cand[64];
-    for (int r = 0; r < n; ++r) base[r] = rows[r];
+    unsigned long long cand[64];
     unsigned int basis[8];
     candidate_basis(power, seed, first + (unsigned long long)i, basis);
-    permute_rows(power, base, basis, cand);
+    permute_rows(power, rows, basis, cand);
     int mb = 0;
     const unsigned long long cost = trellis_cost(cand, n, &mb);
     if (costs_out) costs_out[i] = cost;
