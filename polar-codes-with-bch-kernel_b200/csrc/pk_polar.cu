@@ -622,189 +622,7 @@ k_polar_decode(PkPolarDev d, int L, int FPC, const float *__restrict__ llr_in, l
 }
 
 
-// ------------------------------------------------------------------ SC decoder, frames across lanes (L = 1)
-// Plain successive cancellation has no list, so every frame walks the same phases, the same kernel trellises and the
-// same sections: only the numbers differ.  k_polar_sc therefore puts FRAMES ACROSS LANES -- a warp decodes FPW = 32 / G
-// frames in lock step, G lanes per frame sharing the states of a section -- instead of one warp per frame with lanes
-// across trellis states (k_polar_decode), where the 2..16-state sections at both ends of every Viterbi pass leave most
-// lanes idle and every section pays ~20 instructions of bookkeeping for one frame.  Here a state update is ~16
-// instructions for 32 (frame, state) pairs whatever the section size.  Same fp32 operations in the same order per
-// state as k_polar_decode / the reference (one add per branch, one min per state), so LLRs and metrics are bit-identical.
-//   shared memory per warp : path metrics [2][2^max_ab + 1][FPW] floats, LLR arrays of the inner layers [..][FPW]
-//   global scratch per warp: channel LLRs transposed [N0][FPW], partial-sum / offset bytes [..][FPW], decided bits
-// (all indexed [element][frame] so that the lanes of a warp touch consecutive addresses).
-template <int G>
-__global__ void __launch_bounds__(512)
-k_polar_sc(PkPolarDev d, const float *__restrict__ llr_in, long B, int *__restrict__ count, uint8_t *__restrict__ inf_out,
-           uint8_t *__restrict__ cw_out, float *__restrict__ metric_out, float *__restrict__ scr_f, uint8_t *__restrict__ scr_b,
-           uint32_t *__restrict__ scr_u) {
-    constexpr int FPW = 32 / G;
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ PkPolarKernelDev sk[PK_POLAR_MAX_LAYERS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int f = lane % FPW, g = lane / FPW;
-    const PathLayout pl = path_layout(d);
-    unsigned char *sm = smem;
-    stage_polar_tables(d, sk, sm);
-    const int NS = 1 << d.max_ab;
-    const size_t per_warp = ((size_t)2 * (NS + 1) + (size_t)pl.floats) * FPW * sizeof(float);
-    float *met = reinterpret_cast<float *>(sm + (size_t)warp * per_warp);
-    float *S = met + (size_t)2 * (NS + 1) * FPW;                                  // [pl.floats][FPW]
-    const long gw = (long)blockIdx.x * nwarps + warp, tw = (long)gridDim.x * nwarps;
-    float *chanT = scr_f + (size_t)gw * d.N0 * FPW;                               // [N0][FPW]
-    uint8_t *Bb = scr_b + (size_t)gw * pl.bytes * FPW;                            // [pl.bytes][FPW] (C arrays, offsets)
-    uint32_t *U = scr_u + (size_t)gw * d.nw * FPW;                                // [nw][FPW] decided symbols
-    const int last = d.layers - 1, lsz = d.ksize[last];
-
-    // one Viterbi pass (TrellisKernelProcessor.cpp:260-293) for stride element i of every frame of the warp
-    auto viterbi_x = [&](const PkPolarKernelDev &k, int phase, int stride, int i, const float *src, const uint8_t *offs) -> float {
-        const uint32_t *pred = k.pred, *sec = k.off + phase * k.size;
-        const int dummy = 1 << k.max_ab;
-        float *m0 = met, *m1 = met + (size_t)(NS + 1) * FPW;
-        if (g == 0) { m0[f] = 0.0f; m0[dummy * FPW + f] = HUGE_VALF; m1[dummy * FPW + f] = HUGE_VALF; }
-        __syncwarp();
-        for (int j = 0; j < k.size; ++j) {
-            float y = src[(size_t)(j * stride + i) * FPW + f];
-            if (offs[(size_t)(j * stride + i) * FPW + f]) y = -y;
-            const bool hd = y < 0.0f;
-            const float ay = fabsf(y);
-            const float c0 = hd ? ay : 0.0f, c1 = hd ? 0.0f : ay;   // cost of a branch labelled 0 / 1
-            const uint32_t sj = sec[j];
-            const uint32_t *tab = pred + (sj & 0xFFFFFFu);
-            const int ns = 1 << (sj >> 24);
-#pragma unroll 4
-            for (int s1 = g; s1 < ns; s1 += G) {
-                const uint32_t e = tab[s1];
-                const float va = m0[(e & 0x7FFFu) * FPW + f] + (((e >> 15) & 1u) ? c1 : c0);
-                const float vb = m0[((e >> 16) & 0x7FFFu) * FPW + f] + ((e >> 31) ? c1 : c0);
-                m1[s1 * FPW + f] = vb < va ? vb : va;
-            }
-            __syncwarp();
-            float *t = m0; m0 = m1; m1 = t;
-        }
-        const float r = m0[FPW + f] - m0[f];   // :292
-        __syncwarp();
-        return r;
-    };
-
-    for (long grp = gw; grp * FPW < B; grp += tw) {
-        const long fr = grp * FPW + f;
-        const bool live = fr < B;
-        // ---- LoadLLRs (MixedKernelEncoder.cpp:179-203), transposed
-        for (int i0 = 0; i0 < d.N0; i0 += G) {
-            const int i = i0 + g;
-            if (i < d.N0) {
-                float v = 0.0f;
-                if (live) {
-                    if (!d.symtype) v = llr_in[fr * d.N + i];
-                    else if (d.symtype[i] == 1) v = PKP_UPPER;
-                    else if (d.symtype[i] == 2) v = 0.0f;
-                    else v = llr_in[fr * d.N + d.compact[i]];
-                }
-                chanT[(size_t)i * FPW + f] = v;
-            }
-        }
-        for (int w = g; w < d.nw; w += G) U[(size_t)w * FPW + f] = 0;
-        float R = 0.0f;
-        __syncwarp();
-        for (int phi = 0; phi < d.N0; ++phi) {
-            // ---- LLR of symbol phi (IterativelyCalcS, KernelListEngine.cpp:370-447)
-            int pv = phi, mm = last;
-            while (mm > 0 && (pv % d.ksize[mm]) == 0) { pv /= d.ksize[mm]; --mm; }
-            const float *src = (mm == 0) ? chanT : S + (size_t)pl.s_off[mm] * FPW;
-            for (int j = mm; j <= last; ++j) {
-                const PkPolarKernelDev &k = sk[j];
-                const int stride = d.outer[j + 1], phase = pv % d.ksize[j], l = k.size;
-                float *dest = S + (size_t)pl.s_off[j + 1] * FPW;
-                uint8_t *offs = Bb + (size_t)pl.o_off[j] * FPW;
-                const uint8_t *known = Bb + (size_t)pl.c_off[j + 1] * FPW;
-                // offset update for the newly known input phase-1 (TrellisKernelProcessor.cpp:245-259)
-                if (phase == 0) {
-                    for (int e = g; e < l * stride; e += G) offs[(size_t)e * FPW + f] = 0;
-                } else {
-                    const uint8_t *row = k.mat + (phase - 1) * l;
-                    for (int c = 0; c < l; ++c) {
-                        if (!row[c]) continue;
-                        for (int i = g; i < stride; i += G)
-                            offs[(size_t)(c * stride + i) * FPW + f] ^= known[(size_t)((phase - 1) * stride + i) * FPW + f];
-                    }
-                }
-                __syncwarp();
-                for (int i = 0; i < stride; ++i) {
-                    const float v = viterbi_x(k, phase, stride, i, src, offs);
-                    if (g == 0) dest[(size_t)i * FPW + f] = v;
-                }
-                __syncwarp();
-                pv = 0;
-                src = dest;
-            }
-            const float v = S[(size_t)pl.s_off[d.layers] * FPW + f];
-            // ---- decision: frozen symbols follow their constraint (ContinuePathsFrozen :61-98), information symbols the
-            // better of the two candidates in std::greater<pair<float,unsigned>> order (ContinuePathsUnfrozen :100-185
-            // with one path: a zero LLR ties the metrics and the larger index, the flipped decision 1, wins)
-            uint32_t bit;
-            if (d.frozen[phi]) {
-                uint32_t par = 0;
-                if (!d.all_static)
-                    for (int w = 0; w < d.nw; ++w) par ^= __popc(U[(size_t)w * FPW + f] & d.cmask[phi * d.nw + w]) & 1u;
-                if ((par != 0) ^ (v < 0.0f)) R -= fabsf(v);
-                bit = par;
-            } else {
-                bit = (v < 0.0f || v == 0.0f) ? 1u : 0u;
-            }
-            __syncwarp();
-            if (g == 0) {
-                Bb[(size_t)(pl.c_off[d.layers] + (phi % lsz)) * FPW + f] = (uint8_t)bit;
-                if (bit) U[(size_t)(phi >> 5) * FPW + f] |= 1u << (phi & 31);
-            }
-            __syncwarp();
-            // ---- propagate completed kernel blocks (IterativelyUpdateC, KernelListEngine.cpp:266-315)
-            int lambda = d.layers, stride = 1;
-            pv = phi;
-            while (lambda > 0 && ((pv + 1) % d.ksize[lambda - 1]) == 0) {
-                const int psi = pv / d.ksize[lambda - 1];
-                const int next = stride * d.ksize[lambda - 1];
-                const int phi0 = (lambda > 1) ? (psi % d.ksize[lambda - 2]) * next : 0;
-                if (lambda > 1 || cw_out) {   // the outermost product is the codeword: only needed when it is asked for
-                    const PkPolarKernelDev &k = sk[lambda - 1];
-                    const uint8_t *csrc = Bb + (size_t)pl.c_off[lambda] * FPW;
-                    uint8_t *cdst = Bb + (size_t)(pl.c_off[lambda - 1] + phi0) * FPW;
-                    const int l = k.size;
-                    for (int e = g; e < l * stride; e += G) {
-                        const int c = e / stride, i = e - c * stride;
-                        uint8_t x = 0;
-                        for (int r = 0; r < l; ++r) x ^= k.mat[r * l + c] & csrc[(size_t)(r * stride + i) * FPW + f];
-                        cdst[(size_t)e * FPW + f] = x;
-                    }
-                    __syncwarp();
-                }
-                stride = next;
-                pv = psi;
-                --lambda;
-            }
-        }
-        // ---- outputs (one list entry)
-        if (live) {
-            if (inf_out)
-                for (int q = g; q < d.K; q += G) {
-                    const int pos = d.info_pos[q];
-                    inf_out[fr * d.K + q] = (uint8_t)((U[(size_t)(pos >> 5) * FPW + f] >> (pos & 31)) & 1u);
-                }
-            if (cw_out) {
-                const uint8_t *c0 = Bb + (size_t)pl.c_off[0] * FPW;
-                for (int i = g; i < d.N0; i += G) {
-                    if (!d.symtype) cw_out[fr * d.N + i] = c0[(size_t)i * FPW + f];
-                    else if (d.symtype[i] == 0) cw_out[fr * d.N + d.compact[i]] = c0[(size_t)i * FPW + f];
-                }
-            }
-            if (g == 0) {
-                if (metric_out) metric_out[fr] = R;
-                if (count) count[fr] = 1;
-            }
-        }
-        __syncwarp();
-    }
-}
+#include "pk_polar_lanes.cuh"
 
 // ------------------------------------------------------------------ host handle + C ABI
 struct pk_polar {
@@ -815,12 +633,11 @@ struct pk_polar {
     cudaStream_t stream = nullptr;
     size_t smem_decode = 0;
     int fpc = 1;   // frames per CTA
-    // SC decoder with frames across lanes (L = 1)
-    int sc_g = 0, sc_warps = 0, sc_grid = 0;     // lanes per frame (0 = not used), warps per CTA, CTAs
-    size_t sc_smem = 0;
-    float *sc_f = nullptr;
-    uint8_t *sc_b = nullptr;
-    uint32_t *sc_u = nullptr;
+    // decoder with paths across lanes (pk_polar_lanes.cuh); ln_g = 0: not applicable, k_polar_decode runs
+    PkLanesDev lanes{};
+    int ln_g = 0, ln_warps = 0, ln_grid = 0;     // lanes per slot, warps per CTA, CTAs
+    size_t ln_smem = 0;
+    float *ln_chan = nullptr;                    // transposed channel LLRs, one block per warp of the grid
     // generation-mode workspaces (one chunk of frames)
     long gen_cap = 0;
     uint8_t *g_info = nullptr, *g_inf = nullptr;
@@ -840,6 +657,100 @@ cudaError_t up(pk_polar *h, const std::vector<Tp> &v, const Tp **d) {
     h->allocs.push_back(p);
     *d = static_cast<const Tp *>(p);
     return cudaMemcpy(p, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice);
+}
+
+// ---- lanes decoder set-up: tables in the kernel's format, shared-memory budget, scratch
+#define PK_LANES_CASES(X) X(1, 1) X(1, 2) X(1, 4) X(2, 1) X(2, 2) X(2, 4) X(4, 1) X(4, 2) X(4, 4) X(8, 1) X(8, 2) X(8, 4) X(16, 1) X(16, 2) X(32, 1)
+
+cudaError_t lanes_launch(pk_polar *h, const float *d_llr, long B, int *d_count, uint8_t *d_inf, uint8_t *d_cw, float *d_metric, cudaStream_t st) {
+#define X(LL, GG)                                                                                                                       \
+    if (h->L == LL && h->ln_g == GG) {                                                                                                    \
+        k_polar_lanes<LL, GG><<<h->ln_grid, 32 * h->ln_warps, h->ln_smem, st>>>(h->dev, h->lanes, d_llr, B, d_count, d_inf, d_cw, d_metric, h->ln_chan); \
+        return cudaGetLastError();                                                                                                        \
+    }
+    PK_LANES_CASES(X)
+#undef X
+    return cudaErrorInvalidConfiguration;
+}
+cudaError_t lanes_attr(pk_polar *h) {
+#define X(LL, GG) \
+    if (h->L == LL && h->ln_g == GG) return cudaFuncSetAttribute(k_polar_lanes<LL, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ln_smem);
+    PK_LANES_CASES(X)
+#undef X
+    return cudaErrorInvalidConfiguration;
+}
+
+// Leaves h->ln_g = 0 (k_polar_decode runs instead) when the code does not fit the scheme: list size not a power of two,
+// a kernel trellis that is not biproper (two branches with the same label into a state) or too wide for shared memory.
+cudaError_t lanes_setup(pk_polar *h) {
+    const pk_polar_code &c = h->code;
+    const PkPolarDev &d = h->dev;
+    const int L = h->L;
+    const char *off = getenv("PK_POLAR_LANES");
+    if (off && atoi(off) == 0) return cudaSuccess;
+    if (L & (L - 1)) return cudaSuccess;
+    const char *env = getenv("PK_POLAR_LANES_G");
+    int G = env ? atoi(env) : 2;
+    if (G != 1 && G != 2 && G != 4) G = 2;
+    while (L * G > 32) G >>= 1;
+    const int nslot = 32 / G;
+    PkLanesDev &ld = h->lanes;
+    ld.nk = (int)c.kernels.size();
+    ld.ns_rows = std::max(4, 1 << d.max_ab);
+    if ((size_t)(ld.ns_rows + 1) * nslot * 4 > 65535) return cudaSuccess;
+    const uint32_t dummy = (uint32_t)ld.ns_rows * nslot * 4;
+    for (int j = 0; j < c.layers; ++j) ld.kidx[j] = c.kid[j];
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < ld.nk && e == cudaSuccess; ++i) {
+        const PkKernelTrellis &k = c.kernels[i];
+        const int l = k.size;
+        std::vector<uint32_t> tab, sec((size_t)l * l);
+        for (int p = 0; p < l; ++p)
+            for (int j = 0; j < l; ++j) {
+                const int nsb = k.ab[(size_t)p * (l + 1) + j + 1], ns = 1 << nsb;
+                sec[(size_t)p * l + j] = (uint32_t)tab.size() | ((uint32_t)nsb << 24);
+                const uint32_t *src = &k.pred[k.off[(size_t)p * l + j]];
+                for (int s = 0; s < std::max(4, ns); ++s) {
+                    uint32_t lo = dummy, hi = dummy;   // predecessor rows of the branches labelled 0 / 1
+                    if (s < ns) {
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const uint32_t v = (src[s] >> (16 * hf)) & 0xFFFFu;
+                            if (v == 0xFFFFu) continue;
+                            uint32_t &slot = (v >> 15) ? hi : lo;
+                            if (slot != dummy) return cudaSuccess;   // not biproper
+                            slot = (v & 0x7FFFu) * (uint32_t)nslot * 4u;
+                        }
+                    }
+                    tab.push_back(lo | (hi << 16));
+                }
+            }
+        std::vector<unsigned long long> masks((size_t)2 * l, 0);
+        for (int r = 0; r < l; ++r)
+            for (int cc = 0; cc < l; ++cc)
+                if (k.matrix[(size_t)r * l + cc]) { masks[cc] |= 1ull << r; masks[l + r] |= 1ull << cc; }
+        ld.k[i].ntab = (int)tab.size();
+        ld.k[i].size = l;
+        e = up(h, tab, &ld.k[i].tab);
+        if (e == cudaSuccess) e = up(h, sec, &ld.k[i].sec);
+        if (e == cudaSuccess) e = up(h, masks, &ld.k[i].masks);
+    }
+    if (e != cudaSuccess) return e;
+    const PathLayout pl = path_layout(d);
+    const LanesLayout ly = lanes_layout(d, ld, pl, L, nslot);
+    int smax = 0, sms = 0;
+    cudaDeviceGetAttribute(&smax, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const long fit = ((long)smax - (long)ly.tables) / (long)ly.per_warp;
+    const char *wenv = getenv("PK_POLAR_LANES_WARPS");
+    const int warps = (int)std::min<long>(wenv ? atoi(wenv) : 8, fit);
+    if (warps < 1) return cudaSuccess;
+    h->ln_warps = warps;
+    h->ln_grid = sms;
+    h->ln_smem = (size_t)ly.tables + (size_t)warps * ly.per_warp;
+    e = cudaMalloc(&h->ln_chan, (size_t)h->ln_grid * warps * d.N0 * (nslot / L) * sizeof(float));
+    if (e != cudaSuccess) return e;
+    h->ln_g = G;
+    return lanes_attr(h);
 }
 }  // namespace
 
@@ -938,33 +849,7 @@ int pk_polar_create(const char *spec_text, int L, int device, pk_polar **out) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_polar_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_decode);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_polar_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2 * d.N0);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_polar_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * d.N0);
-        if (e == cudaSuccess && L == 1) {
-            // frames across lanes: G = 2 lanes per frame; as many warps per CTA as the 227 KB of shared memory hold next to the tables
-            const char *env = getenv("PK_POLAR_SC_G");
-            const int G = env ? atoi(env) : 2;
-            if (G == 1 || G == 2 || G == 4) {
-                const int FPW = 32 / G;
-                const size_t per_warp = ((size_t)2 * ((1u << d.max_ab) + 1) + (size_t)pl.floats) * FPW * sizeof(float);
-                const size_t tables = polar_table_bytes(d);
-                int smax = 0, sms = 0;
-                cudaDeviceGetAttribute(&smax, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-                const long fit = ((long)smax - 1024 - (long)tables) / (long)per_warp;
-                const int warps = (int)std::min<long>(16, fit);
-                if (warps >= 1) {
-                    h->sc_g = G; h->sc_warps = warps; h->sc_grid = sms;
-                    h->sc_smem = tables + (size_t)warps * per_warp;
-                    const size_t tw = (size_t)h->sc_grid * warps;
-                    e = cudaMalloc(&h->sc_f, tw * d.N0 * FPW * sizeof(float));
-                    if (e == cudaSuccess) e = cudaMalloc(&h->sc_b, tw * pl.bytes * FPW);
-                    if (e == cudaSuccess) e = cudaMalloc(&h->sc_u, tw * d.nw * FPW * sizeof(uint32_t));
-                    if (e == cudaSuccess) e = cudaMemset(h->sc_b, 0, tw * pl.bytes * FPW);
-                    if (e == cudaSuccess) e = G == 1 ? cudaFuncSetAttribute(k_polar_sc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sc_smem)
-                                            : G == 2 ? cudaFuncSetAttribute(k_polar_sc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sc_smem)
-                                                     : cudaFuncSetAttribute(k_polar_sc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sc_smem);
-                }
-            }
-        }
+        if (e == cudaSuccess) e = lanes_setup(h);
     }
     if (e != cudaSuccess) {
         std::string msg = std::string("pk_polar_create: ") + cudaGetErrorString(e);
@@ -983,7 +868,7 @@ void pk_polar_destroy(pk_polar *h) {
         if (h->stream) cudaStreamDestroy(h->stream);
         for (void *p : h->allocs) cudaFree(p);
         cudaFree(h->g_info); cudaFree(h->g_inf); cudaFree(h->g_llr); cudaFree(h->g_cnt); cudaFree(h->g_tot);
-        cudaFree(h->sc_f); cudaFree(h->sc_b); cudaFree(h->sc_u);
+        cudaFree(h->ln_chan);
         if (h->h_tot) cudaFreeHost(h->h_tot);
     }
     delete h;
@@ -1083,14 +968,10 @@ int pk_polar_decode_batch_dev(pk_polar *h, const float *d_llr, long B, int *d_co
     if (!B) return PK_OK;
     if (cudaSetDevice(h->device) != cudaSuccess) return pk_set_error(PK_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    if (h->sc_g) {
-        // plain SC: frames across lanes (one launch in flight per handle: the scratch belongs to the handle)
-        const int thr = 32 * h->sc_warps;
-        if (h->sc_g == 1) k_polar_sc<1><<<h->sc_grid, thr, h->sc_smem, st>>>(h->dev, d_llr, B, d_count, d_inf, d_cw, d_metric, h->sc_f, h->sc_b, h->sc_u);
-        else if (h->sc_g == 2) k_polar_sc<2><<<h->sc_grid, thr, h->sc_smem, st>>>(h->dev, d_llr, B, d_count, d_inf, d_cw, d_metric, h->sc_f, h->sc_b, h->sc_u);
-        else k_polar_sc<4><<<h->sc_grid, thr, h->sc_smem, st>>>(h->dev, d_llr, B, d_count, d_inf, d_cw, d_metric, h->sc_f, h->sc_b, h->sc_u);
+    if (h->ln_g) {
+        // paths across lanes (one launch in flight per handle: the channel scratch belongs to the handle)
+        const cudaError_t e = lanes_launch(h, d_llr, B, d_count, d_inf, d_cw, d_metric, st);
         ++g_pk_launches;
-        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return pk_set_error(PK_ERR_CUDA, cudaGetErrorString(e));
         return PK_OK;
     }

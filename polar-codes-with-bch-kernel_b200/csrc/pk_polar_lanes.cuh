@@ -1,0 +1,426 @@
+// pk_polar_lanes.cuh -- SC / SC-list decoder with LIST PATHS (AND FRAMES) ACROSS LANES.  Included by pk_polar.cu.
+//
+// Every path of every frame walks the same phases, the same kernel trellises and the same sections: only the numbers
+// differ.  k_polar_lanes therefore gives every (frame, path) pair one of NSLOT = 32 / G slots of a warp -- FPW = NSLOT / L
+// frames of L paths each -- and runs the Viterbi recursion of CTrellisKernelProcessor::GetLLRs
+// (TrellisKernelProcessor.cpp:260-293) with control flow that is uniform over the warp: a section is a loop over its
+// states in groups of four, the G lanes of a slot taking 4 / G states each; the predecessor entries are the same for all
+// slots (one broadcast shared-memory load), the path metrics live in shared memory as [state][slot] so every access of a
+// warp is one conflict-free wavefront.  (k_polar_decode, the general fall-back, spends one warp per path with lanes across
+// trellis states: the 2..16-state sections at both ends of every pass leave it mostly idle.)
+//
+// Bits are packed ACROSS SLOTS: the partial-sum arrays C, the kernel-processor offsets and the decided symbols are one
+// 32-bit word per element whose bit s belongs to slot s, so IterativelyUpdateC (KernelListEngine.cpp:266-315) and the
+// offset update (TrellisKernelProcessor.cpp:245-259) are word-wide XORs, one element per lane.
+//
+// List management (MixedKernelListDecoder.cpp:100-185) runs in registers: both candidates of a path are ranked against
+// the 2 L candidates of its frame with shuffles, the path-index stack (TVMemoryEngine.cpp:85-141, misc.h:206-226) is
+// replayed with ranks inside the kill / clone masks.  Cloning copies the innermost arrays at once (two words per kernel
+// row) and defers everything else: `cmap` names the slot whose column still holds a path's copy of the outer arrays; the
+// columns are brought home (`normalise`) when an innermost block completes, which is the only time outer arrays are written.
+//
+// Same fp32 operations in the same order per state as the reference (one add per branch, one min per state; the list
+// metrics as in :83, :121, :170), so LLRs, metrics and lists are bit-identical.
+#pragma once
+
+struct PkLanesKernel {
+    const uint32_t *tab;                // predecessor entries: lo16 / hi16 = byte offset of the metric row of the label-0 / label-1 predecessor
+    const uint32_t *sec;                // [l][l]: entry offset | state bits after the section << 24
+    const unsigned long long *masks;    // [2 l]: column masks (bit r: K[r][c]), then row masks (bit c: K[r][c])
+    int ntab, size;
+};
+struct PkLanesDev {
+    PkLanesKernel k[PK_POLAR_MAX_LAYERS];   // distinct kernels
+    int kidx[PK_POLAR_MAX_LAYERS];          // layer -> distinct kernel
+    int nk, ns_rows;                        // metric rows per buffer = ns_rows + 1 (row ns_rows is the DUMMY state, +inf)
+};
+struct LanesLayout {
+    int tab[PK_POLAR_MAX_LAYERS], sec[PK_POLAR_MAX_LAYERS], masks[PK_POLAR_MAX_LAYERS];   // byte offsets of the staged tables
+    int tables;                                                                           // bytes of all tables
+    int met, S, W, U, st, par, per_warp;                                                  // byte offsets inside a warp's region
+    int nwords;
+};
+__host__ __device__ inline LanesLayout lanes_layout(const PkPolarDev &d, const PkLanesDev &ld, const PathLayout &pl, int L, int nslot) {
+    LanesLayout y;
+    int o = 0;
+    for (int k = 0; k < ld.nk; ++k) {
+        const int l = ld.k[k].size;
+        y.tab[k] = o; o += ld.k[k].ntab * 4;
+        y.sec[k] = o; o += l * l * 4;
+        o = (o + 7) & ~7;
+        y.masks[k] = o; o += 2 * l * 8;
+        o = (o + 15) & ~15;
+    }
+    y.tables = o;
+    int w = 0;
+    y.met = w; w += 2 * (ld.ns_rows + 1) * nslot * 4;
+    y.S = w; w += (pl.floats + 1) * nslot * 4;
+    y.nwords = pl.u_off;
+    y.W = w; w += y.nwords * 4;
+    y.U = w; w += d.N0 * 4;
+    y.st = w; w += (nslot / L) * (L + 1) * 4;
+    y.par = w; w += 32 * 4;
+    y.per_warp = (w + 15) & ~15;
+    return y;
+}
+
+// One Viterbi pass for stride element i of every slot of the warp; returns M[1] - M[0] (:292) in all lanes of the slot.
+//   tab/sec: staged tables (shared); src: the slot's value of section 0 (then + step per section); offw: offset words.
+template <int G, bool SRC_GLOBAL>
+__device__ __forceinline__ float lanes_viterbi(const unsigned char *__restrict__ tab, const uint32_t *__restrict__ sec, int l,
+                                               const float *src, int src_step, const uint32_t *offw,
+                                               int off_step, int slot, int g, float *__restrict__ met_col, int bufrows) {
+    constexpr int NSLOT = 32 / G, CH = 4 / G;
+    float *m0 = met_col, *m1 = met_col + bufrows * NSLOT;
+    if (g == 0) m0[0] = 0.0f;
+    if (G > 1) __syncwarp();
+    float y = src[0];   // (plain loads: the transposed channel LLRs were written by this warp)
+    uint32_t ow = offw[0];
+    uint32_t sj = sec[0];
+    for (int j = 0; j < l; ++j) {
+        if ((ow >> slot) & 1u) y = -y;
+        const float ay = fabsf(y);
+        const bool hd = y < 0.0f;
+        const float c0 = hd ? ay : 0.0f, c1 = hd ? 0.0f : ay;   // cost of a branch labelled 0 / 1
+        const unsigned char *tb = tab + (size_t)(sj & 0xFFFFFFu) * 4 + g * CH * 4;
+        const int nit = max(1, (1 << (sj >> 24)) >> 2);
+        if (j + 1 < l) {   // next section's operands while this one runs
+            y = src[(size_t)(j + 1) * src_step];
+            ow = offw[(size_t)(j + 1) * off_step];
+            sj = sec[j + 1];
+        }
+        const unsigned char *mb = reinterpret_cast<const unsigned char *>(m0);
+        float *o = m1 + g * CH * NSLOT;
+        int it = 0;
+        for (; it + 1 < nit; it += 2) {
+            uint32_t e[2 * CH];
+            if constexpr (CH == 4) {
+                const uint4 q0 = *reinterpret_cast<const uint4 *>(tb), q1 = *reinterpret_cast<const uint4 *>(tb + 16);
+                e[0] = q0.x; e[1] = q0.y; e[2] = q0.z; e[3] = q0.w; e[CH] = q1.x; e[CH + 1] = q1.y; e[CH + 2] = q1.z; e[CH + 3] = q1.w;
+            } else if constexpr (CH == 2) {
+                const uint2 q0 = *reinterpret_cast<const uint2 *>(tb), q1 = *reinterpret_cast<const uint2 *>(tb + 16);
+                e[0] = q0.x; e[1] = q0.y; e[CH] = q1.x; e[CH + 1] = q1.y;
+            } else {
+                e[0] = *reinterpret_cast<const uint32_t *>(tb); e[CH] = *reinterpret_cast<const uint32_t *>(tb + 16);
+            }
+            float a[2 * CH], b[2 * CH];
+#pragma unroll
+            for (int u = 0; u < 2 * CH; ++u) {
+                a[u] = *reinterpret_cast<const float *>(mb + (e[u] & 0xFFFFu));
+                b[u] = *reinterpret_cast<const float *>(mb + (e[u] >> 16));
+            }
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                o[u * NSLOT] = fminf(a[u] + c0, b[u] + c1);
+                o[(4 + u) * NSLOT] = fminf(a[CH + u] + c0, b[CH + u] + c1);
+            }
+            tb += 32;
+            o += 8 * NSLOT;
+        }
+        if (it < nit) {
+            uint32_t e[CH];
+            if constexpr (CH == 4) {
+                const uint4 q0 = *reinterpret_cast<const uint4 *>(tb);
+                e[0] = q0.x; e[1] = q0.y; e[2] = q0.z; e[3] = q0.w;
+            } else if constexpr (CH == 2) {
+                const uint2 q0 = *reinterpret_cast<const uint2 *>(tb);
+                e[0] = q0.x; e[1] = q0.y;
+            } else {
+                e[0] = *reinterpret_cast<const uint32_t *>(tb);
+            }
+            float a[CH], b[CH];
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                a[u] = *reinterpret_cast<const float *>(mb + (e[u] & 0xFFFFu));
+                b[u] = *reinterpret_cast<const float *>(mb + (e[u] >> 16));
+            }
+#pragma unroll
+            for (int u = 0; u < CH; ++u) o[u * NSLOT] = fminf(a[u] + c0, b[u] + c1);
+        }
+        if (G > 1) __syncwarp();
+        float *t = m0; m0 = m1; m1 = t;
+    }
+    const float r = m0[NSLOT] - m0[0];   // :292
+    if (G > 1) __syncwarp();
+    return r;
+}
+
+template <int L, int G>
+__global__ void __launch_bounds__(256)
+k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, long B, int *__restrict__ count,
+              uint8_t *__restrict__ inf_out, uint8_t *__restrict__ cw_out, float *__restrict__ metric_out, float *__restrict__ scr_chan) {
+    constexpr int NSLOT = 32 / G, FPW = NSLOT / L;
+    static_assert(L * G <= 32 && (L & (L - 1)) == 0 && (G == 1 || G == 2 || G == 4), "slots");
+    constexpr uint32_t SLOTS = NSLOT == 32 ? 0xFFFFFFFFu : ((1u << NSLOT) - 1u);   // the g = 0 lanes: lane == slot
+    constexpr uint32_t GM = L == 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane / NSLOT, slot = lane % NSLOT, fslot = slot / L, p = slot % L, gs = fslot * L;
+    const PathLayout pl = path_layout(d);
+    const LanesLayout ly = lanes_layout(d, ld, pl, L, NSLOT);
+    // ---- stage the tables of every distinct kernel
+    for (int k = 0; k < ld.nk; ++k) {
+        const int l = ld.k[k].size;
+        uint32_t *t = reinterpret_cast<uint32_t *>(smem + ly.tab[k]);
+        for (int i = threadIdx.x; i < ld.k[k].ntab; i += blockDim.x) t[i] = ld.k[k].tab[i];
+        uint32_t *s = reinterpret_cast<uint32_t *>(smem + ly.sec[k]);
+        for (int i = threadIdx.x; i < l * l; i += blockDim.x) s[i] = ld.k[k].sec[i];
+        unsigned long long *m = reinterpret_cast<unsigned long long *>(smem + ly.masks[k]);
+        for (int i = threadIdx.x; i < 2 * l; i += blockDim.x) m[i] = ld.k[k].masks[i];
+    }
+    __syncthreads();
+    unsigned char *wb = smem + ly.tables + (size_t)warp * ly.per_warp;
+    float *met = reinterpret_cast<float *>(wb + ly.met);
+    float *S = reinterpret_cast<float *>(wb + ly.S);
+    uint32_t *W = reinterpret_cast<uint32_t *>(wb + ly.W);
+    uint32_t *U = reinterpret_cast<uint32_t *>(wb + ly.U);
+    uint32_t *st = reinterpret_cast<uint32_t *>(wb + ly.st) + fslot * (L + 1);
+    uint32_t *par = reinterpret_cast<uint32_t *>(wb + ly.par);
+    const int bufrows = ld.ns_rows + 1;
+    if (g == 0) { met[ld.ns_rows * NSLOT + slot] = HUGE_VALF; met[(bufrows + ld.ns_rows) * NSLOT + slot] = HUGE_VALF; }
+    __syncwarp();
+    const long gw = (long)blockIdx.x * nwarps + warp, tw = (long)gridDim.x * nwarps;
+    float *chanT = scr_chan + (size_t)gw * d.N0 * FPW;   // [N0][FPW]
+    const int last = d.layers - 1, lsz = d.ksize[last];
+    const int cm_off = pl.c_off[d.layers], ol_off = pl.o_off[last];   // innermost C array and offsets: copied eagerly
+
+    for (long grp = gw; grp * FPW < B; grp += tw) {
+        const long fr = grp * FPW + fslot;
+        const bool live = fr < B;
+        // ---- LoadLLRs (MixedKernelEncoder.cpp:179-203), transposed: chanT[i][frame slot]
+        for (int idx = lane; idx < d.N0 * FPW; idx += 32) {
+            const int i = idx / FPW, fs = idx - i * FPW;
+            const long f2 = grp * FPW + fs;
+            float v = 0.0f;
+            if (f2 < B) {
+                if (!d.symtype) v = llr_in[f2 * d.N + i];
+                else if (d.symtype[i] == 1) v = PKP_UPPER;
+                else if (d.symtype[i] == 2) v = 0.0f;
+                else v = llr_in[f2 * d.N + d.compact[i]];
+            }
+            chanT[idx] = v;
+        }
+        // ---- Cleanup + AssignInitialPath (TVMemoryEngine.cpp:58-94): the first Pop of the lazily initialised stack is L - 1
+        bool act = live && p == L - 1;
+        float R = 0.0f;
+        int cnt = L - 1;        // free path indices on the stack (positions 0 .. cnt-1)
+        int cmap = slot;        // column holding this path's copy of the outer arrays
+        if (L > 1) {
+            if (g == 0) st[p] = (uint32_t)p;
+        }
+        __syncwarp();
+
+        for (int phi = 0; phi < d.N0; ++phi) {
+            // ---- LLR of symbol phi (IterativelyCalcS, KernelListEngine.cpp:370-447)
+            int pv = phi, mm = last;
+            while (mm > 0 && (pv % d.ksize[mm]) == 0) { pv /= d.ksize[mm]; --mm; }
+            float v = 0.0f;
+            for (int j = mm; j <= last; ++j) {
+                const int kx = ld.kidx[j], l = d.ksize[j];
+                const int stride = d.outer[j + 1], phase = pv % l;
+                uint32_t *offs = W + pl.o_off[j];
+                // offset update for the newly known input phase-1 (TrellisKernelProcessor.cpp:245-259)
+                if (phase == 0) {
+                    for (int e = lane; e < l * stride; e += 32) offs[e] = 0;
+                } else {
+                    const unsigned long long row = reinterpret_cast<const unsigned long long *>(smem + ly.masks[kx])[l + phase - 1];
+                    const uint32_t *known = W + pl.c_off[j + 1] + (phase - 1) * stride;
+                    for (int e = lane; e < l * stride; e += 32) {
+                        const int c = e / stride, i = e - c * stride;
+                        if ((row >> c) & 1ull) offs[e] ^= known[i];
+                    }
+                }
+                __syncwarp();
+                const unsigned char *tab = smem + ly.tab[kx];
+                const uint32_t *sec = reinterpret_cast<const uint32_t *>(smem + ly.sec[kx]) + phase * l;
+                float *dest = S + (size_t)pl.s_off[j + 1] * NSLOT;
+                for (int i = 0; i < stride; ++i) {
+                    if (j == 0)
+                        v = lanes_viterbi<G, true>(tab, sec, l, chanT + (size_t)i * FPW + fslot, stride * FPW, offs + i, stride, slot, g, met + slot, bufrows);
+                    else
+                        v = lanes_viterbi<G, false>(tab, sec, l, S + (size_t)(pl.s_off[j] + i) * NSLOT + cmap, stride * NSLOT, offs + i, stride, slot, g, met + slot, bufrows);
+                    if (g == 0) dest[(size_t)i * NSLOT + slot] = v;
+                }
+                __syncwarp();
+                pv = 0;
+            }
+            // ---- decision
+            const bool frozen = d.frozen[phi] != 0;
+            uint32_t bit = 0;
+            int from = slot;   // slot this path was cloned from in this phase
+            if (frozen) {
+                // ContinuePathsFrozen (MixedKernelListDecoder.cpp:61-98)
+                if (!d.all_static) {
+                    const int blk0 = phi - phi % lsz;
+                    for (int w = 0; w < d.nw; ++w) {
+                        uint32_t m = d.cmask[phi * d.nw + w];
+                        while (m) {
+                            const int t = 32 * w + __ffs(m) - 1;
+                            m &= m - 1;
+                            bit ^= t >= blk0 ? (W[cm_off + t - blk0] >> slot) : (U[t] >> cmap);
+                        }
+                    }
+                    bit &= 1u;
+                }
+                if (act && ((bit != 0) ^ (v < 0.0f))) R -= fabsf(v);
+            } else if (L == 1) {
+                // one path: a zero LLR ties the two candidates and the larger index, the flipped decision 1, wins
+                bit = (v < 0.0f || v == 0.0f) ? 1u : 0u;
+            } else {
+                // ContinuePathsUnfrozen (:100-185)
+                const uint32_t amask = __ballot_sync(PKP_FULL, act);
+                const uint32_t D = v < 0.0f ? 1u : 0u;
+                const float ma = R, mb = R - fabsf(v);
+                const uint32_t sa = 2u * p + D, sb = 2u * p + (D ^ 1u);
+                int ra = 0, rb = 0;
+                for (int k = 0; k < L; ++k) {
+                    const float Rk = __shfl_sync(PKP_FULL, R, gs + k), vk = __shfl_sync(PKP_FULL, v, gs + k);
+                    if (!((amask >> (gs + k)) & 1u)) continue;
+                    const uint32_t Dk = vk < 0.0f ? 1u : 0u;
+                    const float m1 = Rk, m2 = Rk - fabsf(vk);
+                    const uint32_t s1 = 2u * k + Dk, s2 = 2u * k + (Dk ^ 1u);
+                    ra += (m1 > ma || (m1 == ma && s1 > sa)) ? 1 : 0;
+                    ra += (m2 > ma || (m2 == ma && s2 > sa)) ? 1 : 0;
+                    rb += (m1 > mb || (m1 == mb && s1 > sb)) ? 1 : 0;
+                    rb += (m2 > mb || (m2 == mb && s2 > sb)) ? 1 : 0;
+                }
+                const int J = 2 * __popc((amask >> gs) & GM), keep = J < L ? J : L;
+                const bool ka = act && ra < keep, kb = act && rb < keep;
+                const bool kill = act && !ka && !kb, clone = ka && kb;
+                bit = ka ? D : (D ^ 1u);   // the one continuation, or the better one of two (C = LLR < 0, :165)
+                const uint32_t km = (__ballot_sync(PKP_FULL, kill) >> gs) & GM, cm = (__ballot_sync(PKP_FULL, clone) >> gs) & GM;
+                const int nk = __popc(km), nc = __popc(cm);
+                const uint32_t below = (1u << p) - 1u;
+                if (g == 0) par[slot] = 0xFFu;
+                // KillPath pushes in ascending path order, then ClonePath pops (:137-176)
+                if (kill && g == 0) st[cnt + __popc(km & below)] = (uint32_t)p;
+                __syncwarp();
+                if (clone && g == 0) par[gs + st[cnt + nk - 1 - __popc(cm & below)]] = (uint32_t)slot;
+                cnt += nk - nc;
+                __syncwarp();
+                const uint32_t pr = par[slot];
+                if (kill) act = false;
+                const float Rb = __shfl_sync(PKP_FULL, mb, pr & 31u);
+                const uint32_t bp = __shfl_sync(PKP_FULL, bit, pr & 31u);
+                const int cp = __shfl_sync(PKP_FULL, cmap, pr & 31u);
+                if (pr != 0xFFu) {   // a new path: the other continuation of path pr
+                    from = (int)pr;
+                    act = true;
+                    R = Rb;
+                    bit = bp ^ 1u;
+                    cmap = cp;
+                }
+                // clones take their parent's innermost arrays now
+                const uint32_t newm = __ballot_sync(PKP_FULL, from != slot) & SLOTS;
+                if (newm) {
+                    for (int i0 = 0; i0 < 2 * lsz; i0 += 32) {   // uniform trip count: every lane takes part in the shuffles
+                        const int idx = i0 + lane;
+                        const bool mine = idx < 2 * lsz;
+                        uint32_t *wp = idx < lsz ? W + cm_off + idx : W + ol_off + idx - lsz;
+                        uint32_t w = mine ? *wp : 0u;
+                        for (uint32_t m = newm; m; m &= m - 1) {
+                            const int dd = __ffs(m) - 1;
+                            const int ss = __shfl_sync(PKP_FULL, from, dd);
+                            w = (w & ~(1u << dd)) | (((w >> ss) & 1u) << dd);
+                        }
+                        if (mine) *wp = w;
+                    }
+                    __syncwarp();
+                }
+            }
+            if (!act) bit = 0;
+            const uint32_t bw = __ballot_sync(PKP_FULL, bit != 0) & SLOTS;
+            if (lane == 0) W[cm_off + phi % lsz] = bw;
+            __syncwarp();
+            // ---- an innermost block is complete: bring the outer arrays home, file the block's decided symbols
+            if ((phi + 1) % lsz == 0) {
+                if (L > 1) {
+                    const uint32_t nonid = __ballot_sync(PKP_FULL, cmap != slot) & SLOTS;
+                    if (nonid) {
+                        const int nrows = pl.floats - 1;   // S arrays of layers 1 .. last
+                        for (int r0 = 0; r0 < nrows; r0 += 8) {
+                            float t[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) t[u] = r0 + u < nrows ? S[(size_t)(r0 + u) * NSLOT + cmap] : 0.0f;
+                            __syncwarp();
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (r0 + u < nrows && g == 0) S[(size_t)(r0 + u) * NSLOT + slot] = t[u];
+                            __syncwarp();
+                        }
+                        const int ufirst = phi + 1 - lsz;   // decided symbols filed so far
+                        const int total = ly.nwords + ufirst;
+                        for (int i0 = 0; i0 < total; i0 += 32) {
+                            const int idx = i0 + lane;
+                            const bool mine = idx < total && !(idx >= cm_off && idx < cm_off + lsz) && !(idx >= ol_off && idx < ol_off + lsz) &&
+                                              idx >= pl.c_off[1];
+                            uint32_t *wp = idx < ly.nwords ? W + idx : U + (idx - ly.nwords);
+                            uint32_t w = mine ? *wp : 0u, nw2 = w & ~nonid;
+                            for (uint32_t m = nonid; m; m &= m - 1) {
+                                const int dd = __ffs(m) - 1;
+                                const int ss = __shfl_sync(PKP_FULL, cmap, dd);
+                                nw2 |= ((w >> ss) & 1u) << dd;
+                            }
+                            if (mine) *wp = nw2;
+                        }
+                        cmap = slot;
+                        __syncwarp();
+                    }
+                }
+                for (int t = lane; t < lsz; t += 32) U[phi + 1 - lsz + t] = W[cm_off + t];
+                __syncwarp();
+            }
+            // ---- propagate completed kernel blocks (IterativelyUpdateC, KernelListEngine.cpp:266-315)
+            int lambda = d.layers, stride = 1;
+            pv = phi;
+            while (lambda > 0 && ((pv + 1) % d.ksize[lambda - 1]) == 0) {
+                const int psi = pv / d.ksize[lambda - 1];
+                const int next = stride * d.ksize[lambda - 1];
+                const int phi0 = (lambda > 1) ? (psi % d.ksize[lambda - 2]) * next : 0;
+                if (lambda > 1 || cw_out) {   // the outermost product is the codeword: only needed when it is asked for
+                    const int l = d.ksize[lambda - 1];
+                    const unsigned long long *cmk = reinterpret_cast<const unsigned long long *>(smem + ly.masks[ld.kidx[lambda - 1]]);
+                    const uint32_t *csrc = W + pl.c_off[lambda];
+                    uint32_t *cdst = W + pl.c_off[lambda - 1] + phi0;
+                    for (int e = lane; e < l * stride; e += 32) {
+                        const int c = e / stride, i = e - c * stride;
+                        uint32_t x = 0;
+                        for (unsigned long long m = cmk[c]; m; m &= m - 1) x ^= csrc[(__ffsll((long long)m) - 1) * stride + i];
+                        cdst[e] = x;
+                    }
+                    __syncwarp();
+                }
+                stride = next;
+                pv = psi;
+                --lambda;
+            }
+        }
+
+        // ---- final ordering (MixedKernelListDecoder.cpp:253-266): active paths by (R, index) descending
+        const uint32_t amask = __ballot_sync(PKP_FULL, act) & SLOTS;
+        int rank = 0;
+        if (L > 1) {
+            for (int k = 0; k < L; ++k) {
+                const float Rk = __shfl_sync(PKP_FULL, R, gs + k);
+                if (((amask >> (gs + k)) & 1u) && (Rk > R || (Rk == R && k > p))) ++rank;
+            }
+        }
+        for (uint32_t m = amask; m; m &= m - 1) {
+            const int s = __ffs(m) - 1;
+            const int rk = __shfl_sync(PKP_FULL, rank, s);
+            const long row = (grp * FPW + s / L) * L + rk;
+            if (inf_out)
+                for (int q = lane; q < d.K; q += 32) inf_out[row * d.K + q] = (uint8_t)((U[d.info_pos[q]] >> s) & 1u);
+            if (cw_out) {
+                const uint32_t *c0 = W + pl.c_off[0];
+                for (int i = lane; i < d.N0; i += 32) {
+                    if (!d.symtype) cw_out[row * d.N + i] = (uint8_t)((c0[i] >> s) & 1u);
+                    else if (d.symtype[i] == 0) cw_out[row * d.N + d.compact[i]] = (uint8_t)((c0[i] >> s) & 1u);
+                }
+            }
+        }
+        if (act && g == 0 && metric_out) metric_out[fr * L + rank] = R;
+        if (live && p == 0 && g == 0 && count) count[fr] = __popc((amask >> gs) & GM);
+        __syncwarp();
+    }
+}
