@@ -680,8 +680,8 @@ cudaError_t lanes_attr(pk_polar *h) {
     return cudaErrorInvalidConfiguration;
 }
 
-// Leaves h->ln_g = 0 (k_polar_decode runs instead) when the code does not fit the scheme: list size not a power of two,
-// a kernel trellis that is not biproper (two branches with the same label into a state) or too wide for shared memory.
+// Leaves h->ln_g = 0 (k_polar_decode runs instead) when the code does not fit the scheme: list size not a power of two
+// or a kernel trellis too wide for the 16-bit row offsets / the shared memory of an SM.
 cudaError_t lanes_setup(pk_polar *h) {
     const pk_polar_code &c = h->code;
     const PkPolarDev &d = h->dev;
@@ -696,33 +696,26 @@ cudaError_t lanes_setup(pk_polar *h) {
     const int nslot = 32 / G;
     PkLanesDev &ld = h->lanes;
     ld.nk = (int)c.kernels.size();
-    ld.ns_rows = std::max(4, 1 << d.max_ab);
-    if ((size_t)(ld.ns_rows + 1) * nslot * 4 > 65535) return cudaSuccess;
-    const uint32_t dummy = (uint32_t)ld.ns_rows * nslot * 4;
+    ld.ns_rows = 1;
+    for (const PkKernelTrellis &k : c.kernels) ld.ns_rows = std::max(ld.ns_rows, 1 << k.ip_bits);
+    if ((size_t)ld.ns_rows * nslot * 4 > 65534) return cudaSuccess;
     for (int j = 0; j < c.layers; ++j) ld.kidx[j] = c.kid[j];
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < ld.nk && e == cudaSuccess; ++i) {
         const PkKernelTrellis &k = c.kernels[i];
         const int l = k.size;
-        std::vector<uint32_t> tab, sec((size_t)l * l);
+        // entries: state index -> byte offset of its metric row, label bit in bit 0; two entries per word
+        std::vector<uint32_t> tab((k.ip_x.size() + 1) / 2 + 8, 0xFFFFFFFFu), sec(k.ip_sec);
+        for (size_t x = 0; x < k.ip_x.size(); ++x) {
+            const uint32_t v = k.ip_x[x];
+            const uint32_t ent = v == 0xFFFFu ? 0xFFFFu : (((v & 0x7FFFu) * (uint32_t)nslot * 4u) | (v >> 15));
+            tab[x / 2] = (x & 1) ? ((tab[x / 2] & 0x0000FFFFu) | (ent << 16)) : ((tab[x / 2] & 0xFFFF0000u) | ent);
+        }
         for (int p = 0; p < l; ++p)
-            for (int j = 0; j < l; ++j) {
-                const int nsb = k.ab[(size_t)p * (l + 1) + j + 1], ns = 1 << nsb;
-                sec[(size_t)p * l + j] = (uint32_t)tab.size() | ((uint32_t)nsb << 24);
-                const uint32_t *src = &k.pred[k.off[(size_t)p * l + j]];
-                for (int s = 0; s < std::max(4, ns); ++s) {
-                    uint32_t lo = dummy, hi = dummy;   // predecessor rows of the branches labelled 0 / 1
-                    if (s < ns) {
-                        for (int hf = 0; hf < 2; ++hf) {
-                            const uint32_t v = (src[s] >> (16 * hf)) & 0xFFFFu;
-                            if (v == 0xFFFFu) continue;
-                            uint32_t &slot = (v >> 15) ? hi : lo;
-                            if (slot != dummy) return cudaSuccess;   // not biproper
-                            slot = (v & 0x7FFFu) * (uint32_t)nslot * 4u;
-                        }
-                    }
-                    tab.push_back(lo | (hi << 16));
-                }
+            for (int j = 0; j <= l; ++j) {
+                uint32_t *w = &sec[((size_t)p * (l + 1) + j) * 2];
+                w[0] = ((w[0] & 0xFFFFFFu) * 2u) | (w[0] & 0xFF000000u);
+                w[1] = (((1u << (w[1] & 0xFFu)) * (uint32_t)nslot * 4u) & 0xFFFFu) | ((w[1] >> 8) << 16);
             }
         std::vector<unsigned long long> masks((size_t)2 * l, 0);
         for (int r = 0; r < l; ++r)
@@ -742,7 +735,7 @@ cudaError_t lanes_setup(pk_polar *h) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const long fit = ((long)smax - (long)ly.tables) / (long)ly.per_warp;
     const char *wenv = getenv("PK_POLAR_LANES_WARPS");
-    const int warps = (int)std::min<long>(wenv ? atoi(wenv) : 8, fit);
+    const int warps = (int)std::min<long>(wenv ? std::min(16, atoi(wenv)) : 16, fit);
     if (warps < 1) return cudaSuccess;
     h->ln_warps = warps;
     h->ln_grid = sms;

@@ -21,6 +21,17 @@ struct PkKernelTrellis {
     //   two 16-bit halves, each = previous state | (branch bit << 15), 0xFFFF = no such branch
     std::vector<uint32_t> pred;
     std::vector<uint32_t> off;                 // [l*l]
+    // The same trellises for IN-PLACE evaluation (k_polar_lanes): every generator row keeps ONE bit position of the state
+    // index for its whole span (a row that starts where another ends inherits its position), so a section only ever
+    // combines the state pairs (x, x | 1 << q) and writes its results back over them.
+    //   ip_x: per section the states x (bit q clear) | t << 15, t = label of the branch leaving x with the starting
+    //         row's coefficient 0; padded with 0xFFFF to a multiple of 4.
+    //   ip_sec[p][j], j < l: {entry offset | groups of 4 << 24, q | type << 8}; type 0: no row starts or ends (or one does
+    //         both: nothing to do, 0 groups), 1: a row starts at q, 2: a row ends at q, 3: both (butterfly).
+    //   ip_sec[p][l]: {0, position of the tagged row}: the LLR is M[1 << q] - M[0].
+    std::vector<uint16_t> ip_x;
+    std::vector<uint32_t> ip_sec;              // [l][l+1][2]
+    int ip_bits = 0;                           // state index bits used by the in-place numbering
 };
 
 struct pk_polar_code {

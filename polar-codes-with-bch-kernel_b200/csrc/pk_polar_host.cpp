@@ -44,6 +44,9 @@ std::string pk_polar_build_trellis(PkKernelTrellis &k) {
     k.off.assign((size_t)l * l, 0);
     k.pred.clear();
     k.max_ab = 0;
+    k.ip_x.clear();
+    k.ip_sec.assign((size_t)l * (l + 1) * 2, 0);
+    k.ip_bits = 0;
     for (int p = 0; p < l; ++p) {
         // extended generator: rows p..l-1, row p tagged in column l (TrellisKernelProcessor.cpp:88-98)
         std::vector<Row> g;
@@ -112,6 +115,46 @@ std::string pk_polar_build_trellis(PkKernelTrellis &k) {
             k.max_ab = std::max(k.max_ab, nb_next);
         }
         if (active.size() != 1 || last_col(g[active[0]]) != l) return "internal error: tagged row is not the last active one";
+        // ---- in-place numbering of the same trellis
+        {
+            std::vector<int> pos(g.size(), -1);   // bit position of every row while it is active
+            std::vector<int> act;                 // active rows
+            uint32_t used = 0;                    // positions in use
+            for (int j = 0; j < l; ++j) {
+                int starting = -1, ending = -1;
+                for (size_t i = 0; i < g.size(); ++i) {
+                    if (first_col(g[i]) == j) starting = (int)i;
+                    if (last_col(g[i]) == j) ending = (int)i;
+                }
+                uint32_t *sw = &k.ip_sec[((size_t)p * (l + 1) + j) * 2];
+                sw[0] = (uint32_t)k.ip_x.size();
+                if (starting >= 0 && starting == ending) { sw[1] = 0; continue; }   // min(M + c0, M + c1) = M: nothing to do
+                int type = 0, q = 0;
+                if (starting >= 0 && ending >= 0) { type = 3; q = pos[ending]; }
+                else if (ending >= 0) { type = 2; q = pos[ending]; }
+                else if (starting >= 0) { type = 1; q = 0; while ((used >> q) & 1u) ++q; }
+                if (q > 14) return "Kernel trellis has too many states";
+                // states over the active rows except the ending one
+                std::vector<int> free_rows;
+                for (int r : act)
+                    if (r != ending) free_rows.push_back(r);
+                size_t n = 0;
+                for (uint32_t sc = 0; sc < (1u << free_rows.size()); ++sc) {
+                    uint32_t x = 0, t = 0;
+                    for (size_t b = 0; b < free_rows.size(); ++b)
+                        if ((sc >> b) & 1u) { x |= 1u << pos[free_rows[b]]; t ^= (uint32_t)((g[free_rows[b]] >> j) & 1); }
+                    k.ip_x.push_back((uint16_t)(x | (t << 15)));
+                    ++n;
+                }
+                while (n % 4) { k.ip_x.push_back(0xFFFFu); ++n; }
+                sw[0] |= (uint32_t)(n / 4) << 24;
+                sw[1] = (uint32_t)q | ((uint32_t)type << 8);
+                if (ending >= 0) { used &= ~(1u << pos[ending]); act.erase(std::find(act.begin(), act.end(), ending)); pos[ending] = -1; }
+                if (starting >= 0) { pos[starting] = q; used |= 1u << q; act.push_back(starting); k.ip_bits = std::max(k.ip_bits, q + 1); }
+            }
+            if (act.size() != 1) return "internal error: tagged row is not the last active one";
+            k.ip_sec[((size_t)p * (l + 1) + l) * 2 + 1] = (uint32_t)pos[act[0]];
+        }
     }
     return "";
 }

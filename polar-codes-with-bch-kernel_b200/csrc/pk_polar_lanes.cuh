@@ -24,15 +24,15 @@
 #pragma once
 
 struct PkLanesKernel {
-    const uint32_t *tab;                // predecessor entries: lo16 / hi16 = byte offset of the metric row of the label-0 / label-1 predecessor
-    const uint32_t *sec;                // [l][l]: entry offset | state bits after the section << 24
+    const uint32_t *tab;                // in-place entries, two per word: byte offset of the metric row of state x | t (pk_polar.h), 0xFFFF = padding
+    const uint32_t *sec;                // [l][l+1][2]: {byte offset of the entries | groups of 4 << 24, byte offset of row 1 << q | type << 16}
     const unsigned long long *masks;    // [2 l]: column masks (bit r: K[r][c]), then row masks (bit c: K[r][c])
     int ntab, size;
 };
 struct PkLanesDev {
     PkLanesKernel k[PK_POLAR_MAX_LAYERS];   // distinct kernels
     int kidx[PK_POLAR_MAX_LAYERS];          // layer -> distinct kernel
-    int nk, ns_rows;                        // metric rows per buffer = ns_rows + 1 (row ns_rows is the DUMMY state, +inf)
+    int nk, ns_rows;                        // metric rows (states of the widest section)
 };
 struct LanesLayout {
     int tab[PK_POLAR_MAX_LAYERS], sec[PK_POLAR_MAX_LAYERS], masks[PK_POLAR_MAX_LAYERS];   // byte offsets of the staged tables
@@ -46,14 +46,15 @@ __host__ __device__ inline LanesLayout lanes_layout(const PkPolarDev &d, const P
     for (int k = 0; k < ld.nk; ++k) {
         const int l = ld.k[k].size;
         y.tab[k] = o; o += ld.k[k].ntab * 4;
-        y.sec[k] = o; o += l * l * 4;
+        o = (o + 7) & ~7;
+        y.sec[k] = o; o += l * (l + 1) * 8;
         o = (o + 7) & ~7;
         y.masks[k] = o; o += 2 * l * 8;
         o = (o + 15) & ~15;
     }
     y.tables = o;
     int w = 0;
-    y.met = w; w += 2 * (ld.ns_rows + 1) * nslot * 4;
+    y.met = w; w += ld.ns_rows * nslot * 4;
     y.S = w; w += (pl.floats + 1) * nslot * 4;
     y.nwords = pl.u_off;
     y.W = w; w += y.nwords * 4;
@@ -64,89 +65,102 @@ __host__ __device__ inline LanesLayout lanes_layout(const PkPolarDev &d, const P
     return y;
 }
 
-// One Viterbi pass for stride element i of every slot of the warp; returns M[1] - M[0] (:292) in all lanes of the slot.
+// One section of the in-place recursion: the lane's share of the state pairs (x, x + q) of the section, in batches of
+// CH * UNR pairs whose loads are all issued before the first store (the pairs of a section are disjoint, so the order
+// inside a section is free).  `ay` = |LLR| of the section's symbol, `hd` = its hard decision: a branch labelled like the
+// hard decision costs nothing, the other one `ay` (x + 0.0f = x: the reference's add of a zero cost is skipped, same value).
+//   TYPE 0: M[x]  = M[x] + c(t)                                  (no generator row starts or ends)
+//   TYPE 1: M[x], M[x+q] = M[x] + c(t), M[x] + c(!t)             (a row starts)
+//   TYPE 2: M[x]  = min(M[x] + c(t), M[x+q] + c(!t))             (a row ends)
+//   TYPE 3: M[x]  = min(M[x] + c(t), M[x+q] + c(!t)), M[x+q] = min(M[x] + c(!t), M[x+q] + c(t))   (both: butterfly)
+template <int G, int TYPE>
+__device__ __forceinline__ void lanes_section(const unsigned char *__restrict__ tb, int ng, unsigned char *mcol, uint32_t qoff, float ay, uint32_t hd) {
+    constexpr int CH = 4 / G, UNR = G == 4 ? 4 : 2, NP = CH * UNR;
+    for (int it = 0; it < ng; it += UNR, tb += 8 * UNR) {
+        uint32_t e[NP];
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            if constexpr (CH == 4) {
+                const uint2 q = *reinterpret_cast<const uint2 *>(tb + 8 * k);
+                e[4 * k] = q.x & 0xFFFFu; e[4 * k + 1] = q.x >> 16; e[4 * k + 2] = q.y & 0xFFFFu; e[4 * k + 3] = q.y >> 16;
+            } else if constexpr (CH == 2) {
+                const uint32_t q = *reinterpret_cast<const uint32_t *>(tb + 8 * k);
+                e[2 * k] = q & 0xFFFFu; e[2 * k + 1] = q >> 16;
+            } else {
+                e[k] = *reinterpret_cast<const uint16_t *>(tb + 8 * k);
+            }
+            if (it + k >= ng) {   // past the section: nothing to do
+#pragma unroll
+                for (int u = 0; u < CH; ++u) e[CH * k + u] = 0xFFFFu;
+            }
+        }
+        float a[NP], b[NP];
+        bool ok[NP], sw[NP];
+        float *px[NP];
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            ok[u] = e[u] != 0xFFFFu;
+            sw[u] = ((e[u] ^ hd) & 1u) != 0;
+            px[u] = reinterpret_cast<float *>(mcol + (ok[u] ? (e[u] & 0xFFFEu) : 0u));
+            a[u] = *px[u];
+            if (TYPE >= 2) b[u] = *reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(px[u]) + qoff);
+        }
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            float *pq = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(px[u]) + qoff);
+            if (TYPE == 0) {
+                if (ok[u]) *px[u] = sw[u] ? a[u] + ay : a[u];
+            } else if (TYPE == 1) {
+                const float P = a[u] + ay;
+                if (ok[u]) { *px[u] = sw[u] ? P : a[u]; *pq = sw[u] ? a[u] : P; }
+            } else if (TYPE == 2) {
+                const float lo = sw[u] ? b[u] : a[u], hi = sw[u] ? a[u] : b[u];
+                if (ok[u]) *px[u] = fminf(lo, hi + ay);
+            } else {
+                const float r0 = fminf(a[u], b[u] + ay), r1 = fminf(a[u] + ay, b[u]);
+                if (ok[u]) { *px[u] = sw[u] ? r1 : r0; *pq = sw[u] ? r0 : r1; }
+            }
+        }
+    }
+}
+
+// One Viterbi pass (TrellisKernelProcessor.cpp:260-293) for stride element i of every slot of the warp, on the in-place
+// numbering of the trellis (pk_polar.h); returns M[tag = 1] - M[tag = 0] (:292) in all lanes of the slot.
 //   tab/sec: staged tables (shared); src: the slot's value of section 0 (then + step per section); offw: offset words.
-template <int G, bool SRC_GLOBAL>
-__device__ __forceinline__ float lanes_viterbi(const unsigned char *__restrict__ tab, const uint32_t *__restrict__ sec, int l,
+template <int G>
+__device__ __forceinline__ float lanes_viterbi(const unsigned char *__restrict__ tab, const uint2 *__restrict__ sec, int l,
                                                const float *src, int src_step, const uint32_t *offw,
-                                               int off_step, int slot, int g, float *__restrict__ met_col, int bufrows) {
-    constexpr int NSLOT = 32 / G, CH = 4 / G;
-    float *m0 = met_col, *m1 = met_col + bufrows * NSLOT;
-    if (g == 0) m0[0] = 0.0f;
+                                               int off_step, int slot, int g, unsigned char *mcol) {
+    constexpr int CH = 4 / G;
+    if (g == 0) *reinterpret_cast<float *>(mcol) = 0.0f;
     if (G > 1) __syncwarp();
     float y = src[0];   // (plain loads: the transposed channel LLRs were written by this warp)
     uint32_t ow = offw[0];
-    uint32_t sj = sec[0];
+    uint2 sj = sec[0];
     for (int j = 0; j < l; ++j) {
         if ((ow >> slot) & 1u) y = -y;
         const float ay = fabsf(y);
-        const bool hd = y < 0.0f;
-        const float c0 = hd ? ay : 0.0f, c1 = hd ? 0.0f : ay;   // cost of a branch labelled 0 / 1
-        const unsigned char *tb = tab + (size_t)(sj & 0xFFFFFFu) * 4 + g * CH * 4;
-        const int nit = max(1, (1 << (sj >> 24)) >> 2);
-        if (j + 1 < l) {   // next section's operands while this one runs
-            y = src[(size_t)(j + 1) * src_step];
-            ow = offw[(size_t)(j + 1) * off_step];
-            sj = sec[j + 1];
-        }
-        const unsigned char *mb = reinterpret_cast<const unsigned char *>(m0);
-        float *o = m1 + g * CH * NSLOT;
-        int it = 0;
-        for (; it + 1 < nit; it += 2) {
-            uint32_t e[2 * CH];
-            if constexpr (CH == 4) {
-                const uint4 q0 = *reinterpret_cast<const uint4 *>(tb), q1 = *reinterpret_cast<const uint4 *>(tb + 16);
-                e[0] = q0.x; e[1] = q0.y; e[2] = q0.z; e[3] = q0.w; e[CH] = q1.x; e[CH + 1] = q1.y; e[CH + 2] = q1.z; e[CH + 3] = q1.w;
-            } else if constexpr (CH == 2) {
-                const uint2 q0 = *reinterpret_cast<const uint2 *>(tb), q1 = *reinterpret_cast<const uint2 *>(tb + 16);
-                e[0] = q0.x; e[1] = q0.y; e[CH] = q1.x; e[CH + 1] = q1.y;
-            } else {
-                e[0] = *reinterpret_cast<const uint32_t *>(tb); e[CH] = *reinterpret_cast<const uint32_t *>(tb + 16);
-            }
-            float a[2 * CH], b[2 * CH];
-#pragma unroll
-            for (int u = 0; u < 2 * CH; ++u) {
-                a[u] = *reinterpret_cast<const float *>(mb + (e[u] & 0xFFFFu));
-                b[u] = *reinterpret_cast<const float *>(mb + (e[u] >> 16));
-            }
-#pragma unroll
-            for (int u = 0; u < CH; ++u) {
-                o[u * NSLOT] = fminf(a[u] + c0, b[u] + c1);
-                o[(4 + u) * NSLOT] = fminf(a[CH + u] + c0, b[CH + u] + c1);
-            }
-            tb += 32;
-            o += 8 * NSLOT;
-        }
-        if (it < nit) {
-            uint32_t e[CH];
-            if constexpr (CH == 4) {
-                const uint4 q0 = *reinterpret_cast<const uint4 *>(tb);
-                e[0] = q0.x; e[1] = q0.y; e[2] = q0.z; e[3] = q0.w;
-            } else if constexpr (CH == 2) {
-                const uint2 q0 = *reinterpret_cast<const uint2 *>(tb);
-                e[0] = q0.x; e[1] = q0.y;
-            } else {
-                e[0] = *reinterpret_cast<const uint32_t *>(tb);
-            }
-            float a[CH], b[CH];
-#pragma unroll
-            for (int u = 0; u < CH; ++u) {
-                a[u] = *reinterpret_cast<const float *>(mb + (e[u] & 0xFFFFu));
-                b[u] = *reinterpret_cast<const float *>(mb + (e[u] >> 16));
-            }
-#pragma unroll
-            for (int u = 0; u < CH; ++u) o[u * NSLOT] = fminf(a[u] + c0, b[u] + c1);
-        }
+        const uint32_t hd = y < 0.0f ? 1u : 0u;
+        const unsigned char *tb = tab + (sj.x & 0xFFFFFFu) + g * CH * 2;
+        const int ng = (int)(sj.x >> 24);
+        const uint32_t qoff = sj.y & 0xFFFFu, type = sj.y >> 16;
+        // next section's operands while this one runs
+        y = src[(size_t)(j + 1 < l ? j + 1 : j) * src_step];
+        ow = offw[(size_t)(j + 1 < l ? j + 1 : j) * off_step];
+        sj = sec[j + 1];   // (sec[l] holds the position of the tagged row)
+        if (type == 3) lanes_section<G, 3>(tb, ng, mcol, qoff, ay, hd);
+        else if (type == 2) lanes_section<G, 2>(tb, ng, mcol, qoff, ay, hd);
+        else if (type == 1) lanes_section<G, 1>(tb, ng, mcol, qoff, ay, hd);
+        else lanes_section<G, 0>(tb, ng, mcol, qoff, ay, hd);
         if (G > 1) __syncwarp();
-        float *t = m0; m0 = m1; m1 = t;
     }
-    const float r = m0[NSLOT] - m0[0];   // :292
+    const float r = *reinterpret_cast<const float *>(mcol + (sj.y & 0xFFFFu)) - *reinterpret_cast<const float *>(mcol);
     if (G > 1) __syncwarp();
     return r;
 }
 
 template <int L, int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512, 1)
 k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, long B, int *__restrict__ count,
               uint8_t *__restrict__ inf_out, uint8_t *__restrict__ cw_out, float *__restrict__ metric_out, float *__restrict__ scr_chan) {
     constexpr int NSLOT = 32 / G, FPW = NSLOT / L;
@@ -164,7 +178,7 @@ k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, lon
         uint32_t *t = reinterpret_cast<uint32_t *>(smem + ly.tab[k]);
         for (int i = threadIdx.x; i < ld.k[k].ntab; i += blockDim.x) t[i] = ld.k[k].tab[i];
         uint32_t *s = reinterpret_cast<uint32_t *>(smem + ly.sec[k]);
-        for (int i = threadIdx.x; i < l * l; i += blockDim.x) s[i] = ld.k[k].sec[i];
+        for (int i = threadIdx.x; i < l * (l + 1) * 2; i += blockDim.x) s[i] = ld.k[k].sec[i];
         unsigned long long *m = reinterpret_cast<unsigned long long *>(smem + ly.masks[k]);
         for (int i = threadIdx.x; i < 2 * l; i += blockDim.x) m[i] = ld.k[k].masks[i];
     }
@@ -176,9 +190,6 @@ k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, lon
     uint32_t *U = reinterpret_cast<uint32_t *>(wb + ly.U);
     uint32_t *st = reinterpret_cast<uint32_t *>(wb + ly.st) + fslot * (L + 1);
     uint32_t *par = reinterpret_cast<uint32_t *>(wb + ly.par);
-    const int bufrows = ld.ns_rows + 1;
-    if (g == 0) { met[ld.ns_rows * NSLOT + slot] = HUGE_VALF; met[(bufrows + ld.ns_rows) * NSLOT + slot] = HUGE_VALF; }
-    __syncwarp();
     const long gw = (long)blockIdx.x * nwarps + warp, tw = (long)gridDim.x * nwarps;
     float *chanT = scr_chan + (size_t)gw * d.N0 * FPW;   // [N0][FPW]
     const int last = d.layers - 1, lsz = d.ksize[last];
@@ -232,13 +243,13 @@ k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, lon
                 }
                 __syncwarp();
                 const unsigned char *tab = smem + ly.tab[kx];
-                const uint32_t *sec = reinterpret_cast<const uint32_t *>(smem + ly.sec[kx]) + phase * l;
+                const uint2 *sec = reinterpret_cast<const uint2 *>(smem + ly.sec[kx]) + phase * (l + 1);
                 float *dest = S + (size_t)pl.s_off[j + 1] * NSLOT;
                 for (int i = 0; i < stride; ++i) {
                     if (j == 0)
-                        v = lanes_viterbi<G, true>(tab, sec, l, chanT + (size_t)i * FPW + fslot, stride * FPW, offs + i, stride, slot, g, met + slot, bufrows);
+                        v = lanes_viterbi<G>(tab, sec, l, chanT + (size_t)i * FPW + fslot, stride * FPW, offs + i, stride, slot, g, reinterpret_cast<unsigned char *>(met + slot));
                     else
-                        v = lanes_viterbi<G, false>(tab, sec, l, S + (size_t)(pl.s_off[j] + i) * NSLOT + cmap, stride * NSLOT, offs + i, stride, slot, g, met + slot, bufrows);
+                        v = lanes_viterbi<G>(tab, sec, l, S + (size_t)(pl.s_off[j] + i) * NSLOT + cmap, stride * NSLOT, offs + i, stride, slot, g, reinterpret_cast<unsigned char *>(met + slot));
                     if (g == 0) dest[(size_t)i * NSLOT + slot] = v;
                 }
                 __syncwarp();
