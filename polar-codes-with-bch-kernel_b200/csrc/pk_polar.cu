@@ -704,19 +704,33 @@ cudaError_t lanes_setup(pk_polar *h) {
     for (int i = 0; i < ld.nk && e == cudaSuccess; ++i) {
         const PkKernelTrellis &k = c.kernels[i];
         const int l = k.size;
-        // entries: state index -> byte offset of its metric row, label bit in bit 0; two entries per word
-        std::vector<uint32_t> tab((k.ip_x.size() + 1) / 2 + 8, 0xFFFFFFFFu), sec(k.ip_sec);
-        for (size_t x = 0; x < k.ip_x.size(); ++x) {
-            const uint32_t v = k.ip_x[x];
-            const uint32_t ent = v == 0xFFFFu ? 0xFFFFu : (((v & 0x7FFFu) * (uint32_t)nslot * 4u) | (v >> 15));
-            tab[x / 2] = (x & 1) ? ((tab[x / 2] & 0x0000FFFFu) | (ent << 16)) : ((tab[x / 2] & 0xFFFF0000u) | ent);
-        }
+        // entries: state index -> byte offset of its metric row | PAD << 1 | label bit; 16 bits each.  The G lanes of a slot
+        // take the entries of a group of four interleaved (lane g: entries g, g + G, ..), so that the lanes of a slot read
+        // neighbouring rows, which lie in different banks: the table stores every group in lane order.
+        std::vector<uint16_t> ent;
+        std::vector<uint32_t> sec(k.ip_sec);
         for (int p = 0; p < l; ++p)
             for (int j = 0; j <= l; ++j) {
                 uint32_t *w = &sec[((size_t)p * (l + 1) + j) * 2];
-                w[0] = ((w[0] & 0xFFFFFFu) * 2u) | (w[0] & 0xFF000000u);
-                w[1] = (((1u << (w[1] & 0xFFu)) * (uint32_t)nslot * 4u) & 0xFFFFu) | ((w[1] >> 8) << 16);
+                const uint32_t first = w[0] & 0xFFFFFFu, ngroups = w[0] >> 24, q = w[1] & 0xFFu, type = w[1] >> 8;
+                const uint32_t qoff = (((1u << q) * (uint32_t)nslot * 4u) & 0xFFFFu);
+                if (j == l || ngroups == 0) { w[0] = 0; w[1] = qoff; continue; }
+                uint32_t n = 0;
+                for (uint32_t x = 0; x < 4 * ngroups; ++x) n += k.ip_x[first + x] != 0xFFFFu;
+                const bool tiny = n < 8;   // n is a power of two
+                w[0] = (uint32_t)(ent.size() * 2) | ((tiny ? 0u : n / 8) << 24);
+                w[1] = qoff | ((type | (tiny ? 4u : 0u) | 8u) << 16);
+                for (uint32_t gr = 0; gr < ngroups; ++gr)
+                    for (int gg = 0; gg < G; ++gg)
+                        for (int u = 0; u < 4 / G; ++u) {
+                            const uint32_t v = k.ip_x[first + 4 * gr + gg + G * u];
+                            ent.push_back(v == 0xFFFFu ? (uint16_t)2u : (uint16_t)(((v & 0x7FFFu) * (uint32_t)nslot * 4u) | (v >> 15)));
+                        }
             }
+        ent.resize((ent.size() + 1) & ~(size_t)1, 2u);
+        ent.resize(ent.size() + 16, 2u);
+        std::vector<uint32_t> tab(ent.size() / 2);
+        for (size_t x = 0; x < tab.size(); ++x) tab[x] = (uint32_t)ent[2 * x] | ((uint32_t)ent[2 * x + 1] << 16);
         std::vector<unsigned long long> masks((size_t)2 * l, 0);
         for (int r = 0; r < l; ++r)
             for (int cc = 0; cc < l; ++cc)

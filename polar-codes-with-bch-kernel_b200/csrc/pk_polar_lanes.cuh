@@ -24,8 +24,8 @@
 #pragma once
 
 struct PkLanesKernel {
-    const uint32_t *tab;                // in-place entries, two per word: byte offset of the metric row of state x | t (pk_polar.h), 0xFFFF = padding
-    const uint32_t *sec;                // [l][l+1][2]: {byte offset of the entries | groups of 4 << 24, byte offset of row 1 << q | type << 16}
+    const uint32_t *tab;                // in-place entries, two per word: byte offset of the metric row of state x | PAD << 1 | t (pk_polar.h)
+    const uint32_t *sec;                // [l][l+1][2]: {byte offset of the entries | batches of 8 << 24, byte offset of row 1 << q | (type | TINY << 2 | 8) << 16}
     const unsigned long long *masks;    // [2 l]: column masks (bit r: K[r][c]), then row masks (bit c: K[r][c])
     int ntab, size;
 };
@@ -65,60 +65,58 @@ __host__ __device__ inline LanesLayout lanes_layout(const PkPolarDev &d, const P
     return y;
 }
 
-// One section of the in-place recursion: the lane's share of the state pairs (x, x + q) of the section, in batches of
-// CH * UNR pairs whose loads are all issued before the first store (the pairs of a section are disjoint, so the order
-// inside a section is free).  `ay` = |LLR| of the section's symbol, `hd` = its hard decision: a branch labelled like the
-// hard decision costs nothing, the other one `ay` (x + 0.0f = x: the reference's add of a zero cost is skipped, same value).
+// One section of the in-place recursion: the lane's share of the state pairs (x, x + q) of the section.  The number of
+// pairs is a power of two: sections of 8 and more run in batches of 8 pairs per slot (2 CH per lane) whose loads are all
+// issued before the first store (the pairs of a section are disjoint, so the order inside a section is free); sections of
+// 1, 2 or 4 pairs are one group of four entries padded with PAD entries whose stores are suppressed (TINY).
+// `ay` = |LLR| of the section's symbol, `hd` = its hard decision: a branch labelled like the hard decision costs nothing,
+// the other one `ay` (x + 0.0f = x: the reference's add of a zero cost is skipped, same value).  sw = t ^ hd.
 //   TYPE 0: M[x]  = M[x] + c(t)                                  (no generator row starts or ends)
 //   TYPE 1: M[x], M[x+q] = M[x] + c(t), M[x] + c(!t)             (a row starts)
 //   TYPE 2: M[x]  = min(M[x] + c(t), M[x+q] + c(!t))             (a row ends)
 //   TYPE 3: M[x]  = min(M[x] + c(t), M[x+q] + c(!t)), M[x+q] = min(M[x] + c(!t), M[x+q] + c(t))   (both: butterfly)
-template <int G, int TYPE>
-__device__ __forceinline__ void lanes_section(const unsigned char *__restrict__ tb, int ng, unsigned char *mcol, uint32_t qoff, float ay, uint32_t hd) {
-    constexpr int CH = 4 / G, UNR = G == 4 ? 4 : 2, NP = CH * UNR;
-    for (int it = 0; it < ng; it += UNR, tb += 8 * UNR) {
+// Entry (16 bits): byte offset of the metric row of x (a multiple of 32) | PAD << 1 | t.
+template <int G, int TYPE, bool TINY>
+__device__ __forceinline__ void lanes_section(const unsigned char *__restrict__ tb, int nbatch, unsigned char *mcol, uint32_t qoff, float ay, uint32_t hd) {
+    constexpr int CH = 4 / G, NP = TINY ? CH : 2 * CH;
+    for (int it = 0; it < (TINY ? 1 : nbatch); ++it, tb += 16) {
         uint32_t e[NP];
 #pragma unroll
-        for (int k = 0; k < UNR; ++k) {
+        for (int k = 0; k < NP / CH; ++k) {
             if constexpr (CH == 4) {
                 const uint2 q = *reinterpret_cast<const uint2 *>(tb + 8 * k);
-                e[4 * k] = q.x & 0xFFFFu; e[4 * k + 1] = q.x >> 16; e[4 * k + 2] = q.y & 0xFFFFu; e[4 * k + 3] = q.y >> 16;
+                e[4 * k] = q.x; e[4 * k + 1] = q.x >> 16; e[4 * k + 2] = q.y; e[4 * k + 3] = q.y >> 16;
             } else if constexpr (CH == 2) {
                 const uint32_t q = *reinterpret_cast<const uint32_t *>(tb + 8 * k);
-                e[2 * k] = q & 0xFFFFu; e[2 * k + 1] = q >> 16;
+                e[2 * k] = q; e[2 * k + 1] = q >> 16;
             } else {
                 e[k] = *reinterpret_cast<const uint16_t *>(tb + 8 * k);
             }
-            if (it + k >= ng) {   // past the section: nothing to do
-#pragma unroll
-                for (int u = 0; u < CH; ++u) e[CH * k + u] = 0xFFFFu;
-            }
         }
         float a[NP], b[NP];
-        bool ok[NP], sw[NP];
         float *px[NP];
 #pragma unroll
         for (int u = 0; u < NP; ++u) {
-            ok[u] = e[u] != 0xFFFFu;
-            sw[u] = ((e[u] ^ hd) & 1u) != 0;
-            px[u] = reinterpret_cast<float *>(mcol + (ok[u] ? (e[u] & 0xFFFEu) : 0u));
+            px[u] = reinterpret_cast<float *>(mcol + (e[u] & 0xFFE0u));
             a[u] = *px[u];
             if (TYPE >= 2) b[u] = *reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(px[u]) + qoff);
         }
 #pragma unroll
         for (int u = 0; u < NP; ++u) {
             float *pq = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(px[u]) + qoff);
+            const bool sw = ((e[u] ^ hd) & 1u) != 0, ok = !TINY || !(e[u] & 2u);
             if (TYPE == 0) {
-                if (ok[u]) *px[u] = sw[u] ? a[u] + ay : a[u];
+                const float P = a[u] + ay;
+                if (ok) *px[u] = sw ? P : a[u];
             } else if (TYPE == 1) {
                 const float P = a[u] + ay;
-                if (ok[u]) { *px[u] = sw[u] ? P : a[u]; *pq = sw[u] ? a[u] : P; }
+                if (ok) { *px[u] = sw ? P : a[u]; *pq = sw ? a[u] : P; }
             } else if (TYPE == 2) {
-                const float lo = sw[u] ? b[u] : a[u], hi = sw[u] ? a[u] : b[u];
-                if (ok[u]) *px[u] = fminf(lo, hi + ay);
+                const float r0 = fminf(a[u], b[u] + ay), r1 = fminf(a[u] + ay, b[u]);
+                if (ok) *px[u] = sw ? r1 : r0;
             } else {
                 const float r0 = fminf(a[u], b[u] + ay), r1 = fminf(a[u] + ay, b[u]);
-                if (ok[u]) { *px[u] = sw[u] ? r1 : r0; *pq = sw[u] ? r0 : r1; }
+                if (ok) { *px[u] = sw ? r1 : r0; *pq = sw ? r0 : r1; }
             }
         }
     }
@@ -142,16 +140,23 @@ __device__ __forceinline__ float lanes_viterbi(const unsigned char *__restrict__
         const float ay = fabsf(y);
         const uint32_t hd = y < 0.0f ? 1u : 0u;
         const unsigned char *tb = tab + (sj.x & 0xFFFFFFu) + g * CH * 2;
-        const int ng = (int)(sj.x >> 24);
-        const uint32_t qoff = sj.y & 0xFFFFu, type = sj.y >> 16;
+        const int nb = (int)(sj.x >> 24);
+        const uint32_t qoff = sj.y & 0xFFFFu, type = sj.y >> 16;   // type | TINY << 2 | something to do << 3
         // next section's operands while this one runs
         y = src[(size_t)(j + 1 < l ? j + 1 : j) * src_step];
         ow = offw[(size_t)(j + 1 < l ? j + 1 : j) * off_step];
         sj = sec[j + 1];   // (sec[l] holds the position of the tagged row)
-        if (type == 3) lanes_section<G, 3>(tb, ng, mcol, qoff, ay, hd);
-        else if (type == 2) lanes_section<G, 2>(tb, ng, mcol, qoff, ay, hd);
-        else if (type == 1) lanes_section<G, 1>(tb, ng, mcol, qoff, ay, hd);
-        else lanes_section<G, 0>(tb, ng, mcol, qoff, ay, hd);
+        switch (type) {
+        case 8 + 0: lanes_section<G, 0, false>(tb, nb, mcol, qoff, ay, hd); break;
+        case 8 + 1: lanes_section<G, 1, false>(tb, nb, mcol, qoff, ay, hd); break;
+        case 8 + 2: lanes_section<G, 2, false>(tb, nb, mcol, qoff, ay, hd); break;
+        case 8 + 3: lanes_section<G, 3, false>(tb, nb, mcol, qoff, ay, hd); break;
+        case 12 + 0: lanes_section<G, 0, true>(tb, nb, mcol, qoff, ay, hd); break;
+        case 12 + 1: lanes_section<G, 1, true>(tb, nb, mcol, qoff, ay, hd); break;
+        case 12 + 2: lanes_section<G, 2, true>(tb, nb, mcol, qoff, ay, hd); break;
+        case 12 + 3: lanes_section<G, 3, true>(tb, nb, mcol, qoff, ay, hd); break;
+        default: break;
+        }
         if (G > 1) __syncwarp();
     }
     const float r = *reinterpret_cast<const float *>(mcol + (sj.y & 0xFFFFu)) - *reinterpret_cast<const float *>(mcol);
