@@ -6,15 +6,17 @@
 //   CTrellisKernelProcessor::GetLLRs          TrellisKernelProcessor.cpp:234-295          -> get_llrs() / viterbi()
 //   CListKernelEngine::IterativelyCalcS / IterativelyUpdateC   KernelListEngine.cpp:370-447,266-315 -> calc_s() / update_c()
 //   CMixedKernelListDecoder::Decode / ContinuePathsFrozen / ContinuePathsUnfrozen
-//                                             MixedKernelListDecoder.cpp:211-269,61-98,100-185 -> k_polar_decode
+//                                             MixedKernelListDecoder.cpp:211-269,61-98,100-185 -> k_polar_lanes, k_polar_decode
 //   CTVMemoryEngine path stack (Pop / Push, lazily initialised)   TVMemoryEngine.cpp:85-141, misc.h:212-226 -> PathStack
 //
-// One CTA per frame, ONE WARP PER LIST PATH (L warps).  The per-path arrays of the reference's Tal-Vardy memory
-// engine (LLR arrays S, partial-sum arrays C, kernel-processor offsets) live in shared memory and are copied
-// eagerly on a clone (a few hundred bytes), which is observably identical to the reference's copy-on-write.
-// Kernel LLRs are min-sum Viterbi over the per-phase minimal trellis in GATHER form (each next state takes the
-// minimum over its <= 2 incoming branches), lanes across trellis states; every value is a single fp32 add or
-// min of the reference's operands, so kernel LLRs and path metrics are bit-identical to the reference's floats.
+// Two decoders share this file's set-up and C ABI:
+//   k_polar_lanes (pk_polar_lanes.cuh) -- list paths AND frames across the lanes of a warp, in-place Viterbi on the
+//     fixed-bit-position numbering of the kernel trellises, bits packed across slots.  Runs whenever the list size is a
+//     power of two and the trellises fit (every code the reference's trellis processor accepts at L <= 32 so far).
+//   k_polar_decode (below) -- one CTA per frame group, ONE WARP PER LIST PATH, lanes across trellis states in gather
+//     form; the general fall-back (any L <= 32) and the decoder the lanes kernel is tested against.
+// In both, every value is a single fp32 add or min of the reference's operands in the reference's order, so kernel
+// LLRs and path metrics are bit-identical to the reference's floats (tests/test_gpu_polar.py).
 #include <cuda_runtime.h>
 
 #include <algorithm>

@@ -61,6 +61,11 @@ def _check_curve(pk, name, kan, points, trials_ref, J):
         tr_ratio = (r["trials"] / n) / trials_ref[si] if trials_ref else 1.0
         tol = (0.6, 1.6) if J >= 0 else (0.2, 5.0)
         ok_tr = tol[0] <= tr_ratio <= tol[1]
+        # An uncapped search of an n = 63 code can run to the wrapped bound, 2^31 - 1 trials; ONE such frame among
+        # the reference's few hundred is most of its published mean (63_39_9 at 0.5 dB: 1.02e7 trials/frame over 254 frames =
+        # one 2^31 frame + 1.7e6), so the mean is not a statistic there: FER only.
+        if J < 0 and trials_ref and trials_ref[si] * n_ref > 0.25 * 2 ** 31:
+            ok_tr = True
         RESULTS.append((name, snr, not out[0.95], not out[0.9999]))
         miss95 += not out[0.95]
         report.append(f"{snr:.1f} dB: ref {k_ref}/{n_ref} = {k_ref / n_ref:.3e}, ours {k}/{n} = {k / n:.3e}, trials x{tr_ratio:.2f}"
