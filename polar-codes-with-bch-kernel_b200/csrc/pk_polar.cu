@@ -751,7 +751,8 @@ cudaError_t lanes_setup(pk_polar *h) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const long fit = ((long)smax - (long)ly.tables) / (long)ly.per_warp;
     const char *wenv = getenv("PK_POLAR_LANES_WARPS");
-    const int warps = (int)std::min<long>(wenv ? std::min(16, atoi(wenv)) : 16, fit);
+    const int wmax = G == 1 ? 8 : 16;   // __launch_bounds__ of k_polar_lanes
+    const int warps = (int)std::min<long>(wenv ? std::min(wmax, atoi(wenv)) : wmax, fit);
     if (warps < 1) return cudaSuccess;
     h->ln_warps = warps;
     h->ln_grid = sms;

@@ -82,10 +82,13 @@ __host__ __device__ inline LanesLayout lanes_layout(const PkPolarDev &d, const P
 //   TYPE 2: M[x]  = min(M[x] + c(t), M[x+q] + c(!t))             (a row ends)
 //   TYPE 3: M[x]  = min(M[x] + c(t), M[x+q] + c(!t)), M[x+q] = min(M[x] + c(!t), M[x+q] + c(t))   (both: butterfly)
 // Entry (16 bits): byte offset of the metric row of x (a multiple of 32) | PAD << 1 | t.
-template <int G, int TYPE, bool TINY>
+#ifndef PK_LANES_UNRB
+#define PK_LANES_UNRB(G) 1   // batches of 8 pairs in flight per step of a wide section (2: measured 7-15 % slower, r2t)
+#endif
+template <int G, int TYPE, bool TINY, int UNRB = 1>
 __device__ __forceinline__ void lanes_section(const unsigned char *__restrict__ tb, int nbatch, unsigned char *mcol, uint32_t qoff, float ay, uint32_t hd) {
-    constexpr int CH = 4 / G, NP = TINY ? CH : 2 * CH;
-    for (int it = 0; it < (TINY ? 1 : nbatch); ++it, tb += 16) {
+    constexpr int CH = 4 / G, NP = TINY ? CH : 2 * CH * UNRB;
+    for (int it = 0; it < (TINY ? 1 : nbatch); it += UNRB, tb += 16 * UNRB) {
         uint32_t e[NP];
 #pragma unroll
         for (int k = 0; k < NP / CH; ++k) {
@@ -149,19 +152,30 @@ __device__ __forceinline__ float lanes_viterbi(const unsigned char *__restrict__
         const int nb = (int)(sj.x >> 24);
         const uint32_t qoff = sj.y & 0xFFFFu, type = sj.y >> 16;   // type | TINY << 2 | something to do << 3
         // next section's operands while this one runs
-        y = src[(size_t)(j + 1 < l ? j + 1 : j) * src_step];
-        ow = offw[(size_t)(j + 1 < l ? j + 1 : j) * off_step];
+        if (j + 1 < l) { src += src_step; offw += off_step; }
+        y = *src;
+        ow = *offw;
         sj = sec[j + 1];   // (sec[l] holds the position of the tagged row)
-        switch (type) {
-        case 8 + 0: lanes_section<G, 0, false>(tb, nb, mcol, qoff, ay, hd); break;
-        case 8 + 1: lanes_section<G, 1, false>(tb, nb, mcol, qoff, ay, hd); break;
-        case 8 + 2: lanes_section<G, 2, false>(tb, nb, mcol, qoff, ay, hd); break;
-        case 8 + 3: lanes_section<G, 3, false>(tb, nb, mcol, qoff, ay, hd); break;
-        case 12 + 0: lanes_section<G, 0, true>(tb, nb, mcol, qoff, ay, hd); break;
-        case 12 + 1: lanes_section<G, 1, true>(tb, nb, mcol, qoff, ay, hd); break;
-        case 12 + 2: lanes_section<G, 2, true>(tb, nb, mcol, qoff, ay, hd); break;
-        case 12 + 3: lanes_section<G, 3, true>(tb, nb, mcol, qoff, ay, hd); break;
-        default: break;
+        constexpr int UB = PK_LANES_UNRB(G);   // nb is a power of two: one batch, or whole steps of UB batches
+        if (UB > 1 && nb >= UB) {
+            switch (type) {
+            case 8 + 0: lanes_section<G, 0, false, UB>(tb, nb, mcol, qoff, ay, hd); break;
+            case 8 + 1: lanes_section<G, 1, false, UB>(tb, nb, mcol, qoff, ay, hd); break;
+            case 8 + 2: lanes_section<G, 2, false, UB>(tb, nb, mcol, qoff, ay, hd); break;
+            default: lanes_section<G, 3, false, UB>(tb, nb, mcol, qoff, ay, hd); break;
+            }
+        } else {
+            switch (type) {
+            case 8 + 0: lanes_section<G, 0, false>(tb, nb, mcol, qoff, ay, hd); break;
+            case 8 + 1: lanes_section<G, 1, false>(tb, nb, mcol, qoff, ay, hd); break;
+            case 8 + 2: lanes_section<G, 2, false>(tb, nb, mcol, qoff, ay, hd); break;
+            case 8 + 3: lanes_section<G, 3, false>(tb, nb, mcol, qoff, ay, hd); break;
+            case 12 + 0: lanes_section<G, 0, true>(tb, nb, mcol, qoff, ay, hd); break;
+            case 12 + 1: lanes_section<G, 1, true>(tb, nb, mcol, qoff, ay, hd); break;
+            case 12 + 2: lanes_section<G, 2, true>(tb, nb, mcol, qoff, ay, hd); break;
+            case 12 + 3: lanes_section<G, 3, true>(tb, nb, mcol, qoff, ay, hd); break;
+            default: break;
+            }
         }
         if (G > 1) __syncwarp();
     }
@@ -171,7 +185,7 @@ __device__ __forceinline__ float lanes_viterbi(const unsigned char *__restrict__
 }
 
 template <int L, int G>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(G == 1 ? 256 : 512, 1)
 k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, long B, int *__restrict__ count,
               uint8_t *__restrict__ inf_out, uint8_t *__restrict__ cw_out, float *__restrict__ metric_out, float *__restrict__ scr_chan) {
     constexpr int NSLOT = 32 / G, FPW = NSLOT / L;
