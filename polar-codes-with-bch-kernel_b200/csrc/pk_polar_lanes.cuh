@@ -270,11 +270,12 @@ k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, lon
                 const unsigned char *tab = smem + ly.tab[kx];
                 const uint2 *sec = reinterpret_cast<const uint2 *>(smem + ly.sec[kx]) + phase * (l + 1);
                 float *dest = S + (size_t)pl.s_off[j + 1] * NSLOT;
+                // one call site (the recursion is inlined once): layer 0 reads the transposed channel LLRs, the others the
+                // S array of the layer above through the path's column
+                const float *src = j == 0 ? chanT + fslot : S + (size_t)pl.s_off[j] * NSLOT + cmap;
+                const int unit = j == 0 ? FPW : NSLOT;
                 for (int i = 0; i < stride; ++i) {
-                    if (j == 0)
-                        v = lanes_viterbi<G>(tab, sec, l, chanT + (size_t)i * FPW + fslot, stride * FPW, offs + i, stride, slot, g, reinterpret_cast<unsigned char *>(met + slot));
-                    else
-                        v = lanes_viterbi<G>(tab, sec, l, S + (size_t)(pl.s_off[j] + i) * NSLOT + cmap, stride * NSLOT, offs + i, stride, slot, g, reinterpret_cast<unsigned char *>(met + slot));
+                    v = lanes_viterbi<G>(tab, sec, l, src + (size_t)i * unit, stride * unit, offs + i, stride, slot, g, reinterpret_cast<unsigned char *>(met + slot));
                     if (g == 0) dest[(size_t)i * NSLOT + slot] = v;
                 }
                 __syncwarp();

@@ -9,11 +9,13 @@ identical decoders, so the per-curve test demands the 99.99 % intervals for ever
 95 %, and the summary test bounds the overall 95 % miss rate (396 points) at 9 % (expected 5 % + 3.6 sigma).
 The average number of algebraic trials per frame (column 3/4 of the files) is heavy-tailed; it is compared loosely.
 
-FOUR published files cannot be reproduced by the reference itself: for the three BCH(63,16,23) files (J = 9, 10, 11) and the
-uncapped BCH(63,51,5) file the reference COMPILED HERE (its own generator, its own decoder, 10^5..10^6 frames per point:
+FIVE published files cannot be reproduced by the reference itself: for the three BCH(63,16,23) files (J = 9, 10, 11) and the
+uncapped BCH(63,51,5) and BCH(63,39,9) files the reference COMPILED HERE (its own generator, its own decoder, 10^5..10^6 frames per point:
 tests/golden/make_ref_fer_recomputed.py -> ref_fer_recomputed.json) gives the GPU's FER, not the published one (e.g.
 (63,16,23) J=9 at 3.5 dB: published 6.66e-3, compiled reference 4.8e-3, GPU 4.85e-3) -- those files come from another
-revision of the program.  For them the check runs against the recomputed reference points (same 95 % criterion)."""
+revision of the program (the uncapped n = 63 searches of this one stop early whenever T >= 32, the bound `(1 << T) - 1`
+wraps: its uncapped (63,39,9) curve is WORSE than its J = 9 curve, 1.05e-1 vs 8.6e-2 at 2 dB, where the published uncapped file
+says 6.4e-2; make_ref_fer_recomputed_budget.py).  For them the check runs against the recomputed reference points (same 95 % criterion)."""
 import json
 import os
 
@@ -86,6 +88,8 @@ def test_fer_curve_within_reference_interval(pk, name):
         assert (rc["m"], rc["t"], rc["J"]) == (c["m"], c["t"], c["J"])
         pts = [(p["ebn0_db"], int(round(2 * p["ebn0_db"])), p["frame_errors"], p["frames"]) for p in rc["points"]]
         trials_ref = {int(round(2 * p["ebn0_db"])): p["trials"] / p["frames"] for p in rc["points"]}
+        if rc.get("trials_unreliable"):   # recomputed with a time budget: the frames with the longest searches are missing
+            trials_ref = None
         report = _check_curve(pk, name + " (recomputed reference)", kan, pts, trials_ref, c["J"])
     else:
         pts = []
