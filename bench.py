@@ -483,7 +483,7 @@ def run_b200(a):
     roofline = {
         "bound": "l2_request_port", "unit": "Gsector/s",
         "achieved": tps0 * spt / 1e9, "peak": 148 * sm_hz / 1e9, "frac": tps0 * spt / (148 * sm_hz),
-        "traffic": NCU.get("dram_bytes_per_launch"),
+        "traffic": NCU.get("dram_bytes_per_launch"), "traffic_note": NCU.get("dram_note"), "l2_hit_rate_pct_ncu": NCU.get("l2_hit_rate_pct"),
         "kernel": f"k_phase_b<{dom_code.m},{dom_code.t},{mode},generation> (wide search; {NCU.get('phase_b_share_pct', 92)} % of this code's kernel time)",
         "launch": f"0 dB point of {CODES[dom][3]}: {sweep.count} frames per GPU in {launches_per_point} launch pairs",
         "avg_launch_ms": ms0 / launches_per_point, "trials_per_s": tps0, "l2_sectors_per_trial_ncu": spt,

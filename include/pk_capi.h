@@ -259,6 +259,9 @@ int pk_polar_kernel_llrs(pk_polar *p, int layer, const float *chan /*[B][l]*/, c
  * best first; inf [B][L][K]; cw [B][L][N] and metric [B][L] may be NULL */
 int pk_polar_decode_batch(pk_polar *p, const float *llr /*[B][N]*/, long B, int *count, uint8_t *inf, uint8_t *cw,
                           float *metric);
+/* The same with device buffers, asynchronous on `stream` (NULL = the handle's own stream).  A handle owns one set of
+ * decoder scratch (transposed channel LLRs): launches of ONE handle must be ordered on one stream; use one handle per
+ * stream for concurrent decoding. */
 int pk_polar_decode_batch_dev(pk_polar *p, const float *d_llr, long B, int *d_count, uint8_t *d_inf, uint8_t *d_cw,
                               float *d_metric, void *stream);
 

@@ -1249,7 +1249,7 @@ __device__ __forceinline__ void pk_load_frame(const PkIo &io, const PkDevTables 
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             const int p = lane + 32 * w;
-            yv[w] = (p < NE) ? __ldg(io.y + f * NE + p) : 0.0;
+            yv[w] = (p < NE) ? __ldcs(io.y + f * NE + p) : 0.0;   // streamed once (evict-first): L2 belongs to the 64 MB of class tables
             CW[w] = 0;
         }
     } else {
@@ -1344,10 +1344,10 @@ __device__ __forceinline__ void pk_emit(const PkIo &io, long f, const uint32_t (
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const int p = lane + 32 * w;
-                if (p < N) io.decided[f * N + p] = (uint8_t)(((YH[w] ^ bestF[w]) >> lane) & 1u);
+                if (p < N) __stcs(io.decided + f * N + p, (uint8_t)(((YH[w] ^ bestF[w]) >> lane) & 1u));
             }
         }
-        if (lane == 0 && io.trials) io.trials[f] = trials;
+        if (lane == 0 && io.trials) __stcs(io.trials + f, trials);
     } else {
         if (!(flags & PK_FLAG_NO_DECISION)) {
 #pragma unroll
