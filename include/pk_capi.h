@@ -247,6 +247,9 @@ void pk_polar_destroy(pk_polar *p);
 int pk_polar_info(const pk_polar *p, int *N, int *K, int *N0, int *layers, int *list_size);
 /* m_ppNumOfActiveBits of the kernel of `layer` (TrellisKernelProcessor.cpp:105,154): out[l][l+1] */
 int pk_polar_trellis_profile(const pk_polar *p, int layer, int *size, uint8_t *out);
+/* Host check of the two trellis table forms of a layer's kernel against each other (the in-place numbering of the lanes
+ * decoder vs the gather form of the warp-per-path decoder) on random integer costs; works on host-only handles. */
+int pk_polar_trellis_selfcheck(const pk_polar *p, int layer, uint64_t seed, int ntests, int *state_bits);
 /* (2^m) x (2^m) extended-BCH polarisation kernel, makeMatrix of the root bchCoder.cpp:356-389; m in [3,6] */
 int pk_make_ebch_kernel(int m, uint8_t *out /*[2^m][2^m]*/);
 /* CBinaryEncoder::Encode (Codec.h:52; MixedKernelEncoder.cpp:142-176) */

@@ -34,7 +34,7 @@ SYMBOLS = (
     "pk_kaneko_destroy pk_kaneko_set_variant pk_kaneko_set_frames_per_grab pk_kaneko_set_phase_a_limit pk_kaneko_launch_geometry pk_kaneko_decode_batch "
     "pk_kaneko_decode_batch_async pk_kaneko_wait pk_kaneko_decode_batch_dev pk_kaneko_run_frames_dev pk_kaneko_run_frames pk_generate_frames pk_generate_frames_dev "
     "pk_kaneko_run_point pk_make_kernel_matrix pk_launch_count pk_launch_count_reset "
-    "pk_polar_create pk_polar_destroy pk_polar_info pk_polar_trellis_profile pk_make_ebch_kernel pk_polar_encode_batch "
+    "pk_polar_create pk_polar_destroy pk_polar_info pk_polar_trellis_profile pk_polar_trellis_selfcheck pk_make_ebch_kernel pk_polar_encode_batch "
     "pk_polar_kernel_llrs pk_polar_decode_batch pk_polar_decode_batch_dev "
     "pk_comm_create pk_comm_unique_id pk_comm_create_rank pk_comm_destroy pk_comm_size pk_comm_rank pk_comm_local_devices pk_comm_stream "
     "pk_allreduce_point pk_comm_sync pk_comm_kaneko_create pk_comm_kaneko_destroy pk_comm_kaneko_local pk_comm_run_point "
@@ -97,6 +97,7 @@ def _load():
     lib.pk_polar_destroy.restype = None
     lib.pk_polar_info.argtypes = [vp, ip, ip, ip, ip, ip]
     lib.pk_polar_trellis_profile.argtypes = [vp, i, ip, vp]
+    lib.pk_polar_trellis_selfcheck.argtypes = [vp, i, u64, i, ip]
     lib.pk_make_ebch_kernel.argtypes = [i, vp]
     lib.pk_polar_encode_batch.argtypes = [vp, vp, l, vp]
     lib.pk_polar_kernel_llrs.argtypes = [vp, i, vp, vp, l, vp]
@@ -526,6 +527,12 @@ class Polar:
         out = np.zeros((sz.value, sz.value + 1), np.uint8)
         _check(lib.pk_polar_trellis_profile(self.h, layer, C.byref(sz), _np_ptr(out)))
         return out
+
+    def trellis_selfcheck(self, layer=0, seed=1, ntests=50):
+        """in-place vs gather-form trellis tables of the layer's kernel on the host -> state index bits of the in-place numbering"""
+        bits = C.c_int()
+        _check(lib.pk_polar_trellis_selfcheck(self.h, layer, int(seed), int(ntests), C.byref(bits)))
+        return bits.value
 
     def encode(self, info):
         info = np.ascontiguousarray(info, np.uint8)

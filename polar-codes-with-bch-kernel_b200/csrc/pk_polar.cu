@@ -699,7 +699,10 @@ cudaError_t lanes_setup(pk_polar *h) {
     PkLanesDev &ld = h->lanes;
     ld.nk = (int)c.kernels.size();
     ld.ns_rows = 1;
-    for (const PkKernelTrellis &k : c.kernels) ld.ns_rows = std::max(ld.ns_rows, 1 << k.ip_bits);
+    for (const PkKernelTrellis &k : c.kernels) {
+        if (!k.ip_ok || k.ip_bits > 14) return cudaSuccess;
+        ld.ns_rows = std::max(ld.ns_rows, 1 << k.ip_bits);
+    }
     if ((size_t)ld.ns_rows * nslot * 4 > 65534) return cudaSuccess;
     for (int j = 0; j < c.layers; ++j) ld.kidx[j] = c.kid[j];
     cudaError_t e = cudaSuccess;
@@ -901,6 +904,18 @@ int pk_polar_trellis_profile(const pk_polar *h, int layer, int *size, uint8_t *o
     const PkKernelTrellis &k = h->code.kernels[h->code.kid[layer]];
     if (size) *size = k.size;
     if (out) std::memcpy(out, k.ab.data(), k.ab.size());
+    return PK_OK;
+}
+
+// Host self-check of the trellis tables of the kernel of `layer`: the in-place numbering k_polar_lanes runs on against the
+// gather form k_polar_decode runs on, `ntests` random cost vectors, all phases.  *state_bits = index bits of the in-place
+// numbering.  PK_OK, or PK_ERR_UNSUPPORTED with the first difference in pk_last_error().
+int pk_polar_trellis_selfcheck(const pk_polar *h, int layer, uint64_t seed, int ntests, int *state_bits) {
+    if (!h || layer < 0 || layer >= h->code.layers || ntests < 1) return pk_set_error(PK_ERR_ARG, "bad arguments");
+    const PkKernelTrellis &k = h->code.kernels[h->code.kid[layer]];
+    if (state_bits) *state_bits = k.ip_ok ? k.ip_bits : -1;
+    const std::string err = pk_polar_check_inplace(k, seed, ntests);
+    if (!err.empty()) return pk_set_error(PK_ERR_UNSUPPORTED, err);
     return PK_OK;
 }
 

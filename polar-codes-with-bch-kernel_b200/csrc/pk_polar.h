@@ -32,6 +32,7 @@ struct PkKernelTrellis {
     std::vector<uint16_t> ip_x;
     std::vector<uint32_t> ip_sec;              // [l][l+1][2]
     int ip_bits = 0;                           // state index bits used by the in-place numbering
+    bool ip_ok = true;                         // false: a section has more groups than the 8-bit count holds (k_polar_lanes is not used)
 };
 
 struct pk_polar_code {
@@ -52,5 +53,7 @@ struct pk_polar_code {
 std::string pk_polar_parse(pk_polar_code &c, const std::string &spec_text);
 // Builds the per-phase trellises of one kernel.
 std::string pk_polar_build_trellis(PkKernelTrellis &k);
+// Gather-form and in-place tables of a kernel against each other on random integer costs (host, tests).
+std::string pk_polar_check_inplace(const PkKernelTrellis &k, unsigned long long seed, int ntests);
 // (2^m) x (2^m) extended BCH kernel of the reference's newer makeMatrix (root bchCoder.cpp:356-389).
 void pk_polar_ebch_kernel(int m, std::vector<uint8_t> &out);

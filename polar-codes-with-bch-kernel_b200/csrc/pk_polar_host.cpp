@@ -47,6 +47,7 @@ std::string pk_polar_build_trellis(PkKernelTrellis &k) {
     k.ip_x.clear();
     k.ip_sec.assign((size_t)l * (l + 1) * 2, 0);
     k.ip_bits = 0;
+    k.ip_ok = true;
     for (int p = 0; p < l; ++p) {
         // extended generator: rows p..l-1, row p tagged in column l (TrellisKernelProcessor.cpp:88-98)
         std::vector<Row> g;
@@ -147,13 +148,71 @@ std::string pk_polar_build_trellis(PkKernelTrellis &k) {
                     ++n;
                 }
                 while (n % 4) { k.ip_x.push_back(0xFFFFu); ++n; }
-                sw[0] |= (uint32_t)(n / 4) << 24;
+                if (n / 4 > 255) k.ip_ok = false;
+                sw[0] |= (uint32_t)std::min<size_t>(n / 4, 255) << 24;
                 sw[1] = (uint32_t)q | ((uint32_t)type << 8);
                 if (ending >= 0) { used &= ~(1u << pos[ending]); act.erase(std::find(act.begin(), act.end(), ending)); pos[ending] = -1; }
                 if (starting >= 0) { pos[starting] = q; used |= 1u << q; act.push_back(starting); k.ip_bits = std::max(k.ip_bits, q + 1); }
             }
             if (act.size() != 1) return "internal error: tagged row is not the last active one";
             k.ip_sec[((size_t)p * (l + 1) + l) * 2 + 1] = (uint32_t)pos[act[0]];
+        }
+    }
+    return "";
+}
+
+// Host check of the two table forms against each other: the gather-form recursion (k_polar_decode, pinned to the
+// reference) and the in-place recursion (k_polar_lanes) on integer costs -- one label of every section costs nothing,
+// the other `ay`, as in the kernels -- for `ntests` random cost vectors and every phase.  Returns "" or what differs.
+std::string pk_polar_check_inplace(const PkKernelTrellis &k, unsigned long long seed, int ntests) {
+    const int l = k.size;
+    if (!k.ip_ok) return "";
+    const long long INF = 1ll << 60;
+    unsigned long long s = seed * 6364136223846793005ull + 1442695040888963407ull;
+    auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (unsigned)(s >> 33); };
+    for (int test = 0; test < ntests; ++test) {
+        std::vector<long long> ay(l);
+        std::vector<int> hd(l);
+        for (int j = 0; j < l; ++j) { ay[j] = rnd() % 1000; hd[j] = rnd() & 1; }
+        for (int p = 0; p < l; ++p) {
+            // gather form
+            std::vector<long long> m0(1, 0), m1;
+            for (int j = 0; j < l; ++j) {
+                const int ns = 1 << k.ab[(size_t)p * (l + 1) + j + 1];
+                m1.assign(ns, INF);
+                const uint32_t *tab = &k.pred[k.off[(size_t)p * l + j]];
+                for (int s1 = 0; s1 < ns; ++s1)
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const uint32_t v = (tab[s1] >> (16 * hf)) & 0xFFFFu;
+                        if (v == 0xFFFFu) continue;
+                        const long long c = (((v >> 15) & 1u) ^ (uint32_t)hd[j]) ? ay[j] : 0;
+                        m1[s1] = std::min(m1[s1], m0[v & 0x7FFFu] + c);
+                    }
+                m0.swap(m1);
+            }
+            const long long want = m0[1] - m0[0];
+            // in-place form
+            std::vector<long long> M((size_t)1 << std::max(1, k.ip_bits), INF);
+            M[0] = 0;
+            for (int j = 0; j < l; ++j) {
+                const uint32_t *sw = &k.ip_sec[((size_t)p * (l + 1) + j) * 2];
+                const uint32_t first = sw[0] & 0xFFFFFFu, ngroups = sw[0] >> 24, q = sw[1] & 0xFFu, type = sw[1] >> 8;
+                const size_t Q = (size_t)1 << q;
+                for (uint32_t e = 0; e < 4 * ngroups; ++e) {
+                    const uint32_t v = k.ip_x[first + e];
+                    if (v == 0xFFFFu) continue;
+                    const size_t x = v & 0x7FFFu;
+                    const bool swp = ((v >> 15) ^ (uint32_t)hd[j]) & 1u;
+                    const long long a = M[x], b = M[x | Q];
+                    if (type == 0) M[x] = swp ? a + ay[j] : a;
+                    else if (type == 1) { M[x] = swp ? a + ay[j] : a; M[x | Q] = swp ? a : a + ay[j]; }
+                    else if (type == 2) M[x] = swp ? std::min(a + ay[j], b) : std::min(a, b + ay[j]);
+                    else { const long long r0 = std::min(a, b + ay[j]), r1 = std::min(a + ay[j], b); M[x] = swp ? r1 : r0; M[x | Q] = swp ? r0 : r1; }
+                }
+            }
+            const size_t tq = (size_t)1 << (k.ip_sec[((size_t)p * (l + 1) + l) * 2 + 1] & 0xFFu);
+            const long long got = M[tq] - M[0];
+            if (got != want) return "in-place trellis of phase " + std::to_string(p) + " gives " + std::to_string(got) + ", gather form " + std::to_string(want);
         }
     }
     return "";

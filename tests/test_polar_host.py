@@ -107,3 +107,28 @@ def test_swap_columns_restatement(pk):
     assert np.array_equal(S[:, :3], E[:, :3]) and np.array_equal(S, want)
     with pytest.raises(pk.PkError):   # a value nobody carries
         pk.kernel_swap_columns(4, np.zeros(16, np.uint64), E)
+
+
+def test_inplace_trellis_tables_equal_the_gather_form(pk, tmp_path):
+    """The lanes decoder runs the kernel-trellis Viterbi in place on a renumbered trellis (pk_polar.h: one bit position of
+    the state index per generator row); on the host, with integer costs, that recursion gives the gather-form recursion's
+    LLR for every phase -- for the 16 x 16 and 8 x 8 eBCH kernels, column-permuted 16 x 16 kernels and
+    random invertible kernels (rows that start and end in the same section, single-state phases)."""
+    assert pk.Polar(pk.load_spec(), L=1, device=None).trellis_selfcheck(0, seed=3, ntests=200) == 8
+    rng = np.random.default_rng(4)
+    kernels = [pk.ebch_kernel(3)]   # (the 32 x 32 kernel's trellis has more than 2^14 states: no trellis processor, see pk_bridge.cu)
+    E = pk.ebch_kernel(4)
+    kernels += [E[:, rng.permutation(16)] for _ in range(6)]
+    while len(kernels) < 20:
+        n = int(rng.integers(2, 13))
+        K = rng.integers(0, 2, (n, n), dtype=np.uint8)
+        if round(abs(np.linalg.det(K.astype(float)))) % 2 == 1:   # invertible over GF(2)
+            kernels.append(K)
+    for i, K in enumerate(kernels):
+        n = K.shape[0]
+        kf = tmp_path / f"k{i}.kernel"
+        kf.write_text(f"{n}\n" + "\n".join(" ".join(str(int(v)) for v in r) for r in K) + "\n")
+        spec = f"{n} {n // 2} 1 1 0 0\n-{kf}\n" + "".join("1 %d\n" % j for j in range(n - n // 2))
+        p = pk.Polar(spec, L=1, device=None)
+        bits = p.trellis_selfcheck(0, seed=10 + i, ntests=40)
+        assert bits == int(p.trellis_profile(0).max()), (i, bits)
