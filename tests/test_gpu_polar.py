@@ -163,3 +163,61 @@ def test_lanes_decoder_equals_warp_per_path_decoder(pk, name, L, G, monkeypatch)
     assert np.array_equal(n_cnt, o_cnt)
     assert np.array_equal(n_met.view(np.uint32), o_met.view(np.uint32)), "path metrics differ"
     assert np.array_equal(n_inf, o_inf) and np.array_equal(n_cw, o_cw)
+
+
+def _make_spec(tmp_path, sizes, K, seed, dyn=0):
+    """A specification with the given kernel sizes per layer (eBCH kernels of size 8 / 16), K information symbols at the
+    positions of largest index weight, the others frozen to zero (the first `dyn` frozen symbols after an information
+    symbol get a dynamic constraint on earlier information symbols)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import pkb200
+    pk = pkb200.pk
+    files = {}
+    for n in set(sizes):
+        Kn = pk.ebch_kernel({8: 3, 16: 4}[n])
+        f = tmp_path / f"ebch{n}.kernel"
+        f.write_text(f"{n}\n" + "\n".join(" ".join(str(int(v)) for v in r) for r in Kn) + "\n")
+        files[n] = f
+    N0 = int(np.prod(sizes))
+    rng = np.random.default_rng(seed)
+    score = np.array([bin(i).count("1") for i in range(N0)]) + rng.random(N0) * 0.5
+    info = set(np.argsort(-score)[:K].tolist())
+    lines = [f"{N0} {K} 1 {len(sizes)} 0 0", " ".join(f"-{files[n]}" for n in sizes)]
+    seen_info = []
+    for i in range(N0):
+        if i in info:
+            seen_info.append(i)
+            continue
+        if dyn > 0 and len(seen_info) >= 2:
+            terms = sorted(rng.choice(seen_info, size=2, replace=False).tolist()) + [i]
+            lines.append(f"{len(terms)} " + " ".join(map(str, terms)))
+            dyn -= 1
+        else:
+            lines.append(f"1 {i}")
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("sizes,K,dyn", [((16,), 8, 0), ((8,), 4, 1), ((8, 16), 64, 0), ((16, 8), 70, 5), ((8, 8, 8), 256, 0), ((8, 8), 32, 6)])
+@pytest.mark.parametrize("L", [1, 4, 32])
+def test_lanes_decoder_on_other_code_shapes(pk, oracle_mod, tmp_path, monkeypatch, sizes, K, dyn, L):
+    """One, two and three layers, different kernels per layer, dynamic frozen symbols: k_polar_lanes against
+    k_polar_decode and, where oracle/_ref is present, against the reference library itself."""
+    spec = _make_spec(tmp_path, sizes, K, 7, dyn)
+    monkeypatch.setenv("PK_POLAR_LANES", "0")
+    old = pk.Polar(spec, L=L, device=0)
+    monkeypatch.setenv("PK_POLAR_LANES", "1")
+    monkeypatch.delenv("PK_POLAR_LANES_G", raising=False)
+    new = pk.Polar(spec, L=L, device=0)
+    B = 96 // min(L, 8) + 5
+    _, _, llr = new.generate_frames(2.0, 4, 3, 0, B)
+    llr[1] = 0.0
+    o = old.decode(llr)
+    n = new.decode(llr)
+    assert np.array_equal(n[0], o[0]) and np.array_equal(n[3].view(np.uint32), o[3].view(np.uint32))
+    assert np.array_equal(n[1], o[1]) and np.array_equal(n[2], o[2])
+    if oracle_mod.polar_ref_available():
+        ref = oracle_mod.PolarReference(spec, L)
+        r = ref.decode(llr)
+        assert np.array_equal(n[0], r[0]) and np.array_equal(n[3].view(np.uint32), r[3].view(np.uint32))
+        assert np.array_equal(n[1], r[1]) and np.array_equal(n[2], r[2])
