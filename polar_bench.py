@@ -27,7 +27,7 @@ ACS_PER_PATH = 2 * 16 * 11712
 
 
 def frames_for(L, short):
-    base = {1: 1 << 18, 8: 1 << 16, 32: 1 << 14}[L]
+    base = {1: 1 << 20, 8: 1 << 17, 32: 1 << 15}[L]   # per SNR point, sharded over the GPUs (>= 4096 frames per GPU at N = 8)
     return base // 8 if short else base
 
 
