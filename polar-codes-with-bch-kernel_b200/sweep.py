@@ -70,6 +70,31 @@ class Comm:
         return np.array([int(o.item()) for o in out], np.int64)
 
 
+class PolarEngine:
+    """pk.Polar behind the engine interface: the simulator loop of the reference's vendored library (Simulator.cpp:139-335)
+    for a mixed-kernel polar code -- generate, encode, AWGN, SC / SC-list decode, compare, all on the device
+    (pk_polar_run_frames).  With want_recs the frames are drawn to the host, decoded through the batch API and compared
+    there, which yields the per-frame error flags the stop rule needs (same frames: the Philox counter is the frame index)."""
+
+    REC = np.dtype([("trials", "<u4"), ("bit_errors", "<u2"), ("flags", "<u2"), ("extra_cmp", "<u4"), ("extra_sum", "<u4")])
+
+    def __init__(self, polar):
+        self.p = polar
+
+    def run_frames(self, ebn0_db, snr_index, seed, first_frame, nframes, want_recs=False):
+        if not want_recs:
+            tot = self.p.run_frames(ebn0_db, snr_index, seed, first_frame, nframes)
+            return {f: int(tot.get(f, 0)) for f in FIELDS}, None
+        info, _, llr = self.p.generate_frames(ebn0_db, snr_index, seed, first_frame, nframes)
+        cnt, inf, _, _ = self.p.decode(llr)
+        be = (inf[:, 0, :] != info).sum(1)
+        be[cnt < 1] = self.p.K
+        recs = np.zeros(nframes, self.REC)
+        recs["bit_errors"] = be
+        recs["flags"] = np.where(be > 0, FLAG_ERR, 0)
+        return {"frames": nframes, "frame_errors": int((be > 0).sum()), "bit_errors": int(be.sum()), "trials": 0, "cmp": 0, "sum": 0}, recs
+
+
 def run_point(engine, n, comm, ebn0_db, snr_index, seed, p, e, chunk=1 << 16):
     """One SNR point; returns int64[6] totals (FIELDS order), identical on every rank."""
     W, k = comm.world, comm.rank
@@ -114,15 +139,17 @@ def format_row(stnr, tot, cum_bit_errors, n):
     return ",".join("%g" % v for v in vals)
 
 
-def sweep(engine, n, comm, p, e, seed=1, max_snr=5.0, out_path=None, chunk=1 << 16, log=None):
+def sweep(engine, n, comm, p, e, seed=1, max_snr=5.0, out_path=None, chunk=1 << 16, log=None, cumulative_ber=True, min_snr=0.0):
+    """cumulative_ber: the reference's BER* column never resets its bit-error count (dataForPlot.cpp:20,71,95); the polar
+    sweep divides the point's own information-bit errors by frames * K (pass n = K)."""
     rows, raw = [], []
     cum_be = 0
     t0 = time.perf_counter()
-    idx, stnr = 0, 0.0
+    idx, stnr = int(round(2 * min_snr)), float(min_snr)
     fout = open(out_path + ".csv", "w") if (out_path and comm.rank == 0) else None
     while stnr <= max_snr:
         tot = run_point(engine, n, comm, stnr, idx, seed, p, e, chunk)
-        cum_be += int(tot[2])       # BER* is cumulative over the sweep (dataForPlot.cpp:20,71,95)
+        cum_be = cum_be + int(tot[2]) if cumulative_ber else int(tot[2])   # BER* is cumulative over the sweep (dataForPlot.cpp:20,71,95)
         row = format_row(stnr, tot, cum_be, n)
         rows.append(row)
         raw.append(tot.copy())
@@ -143,7 +170,8 @@ def sweep(engine, n, comm, p, e, seed=1, max_snr=5.0, out_path=None, chunk=1 << 
 def main(argv=None):
     import argparse
 
-    ap = argparse.ArgumentParser(description="kaneko <m> <t> <file> <p> <e> on 1..8 B200s (torchrun for > 1)")
+    ap = argparse.ArgumentParser(description="kaneko <m> <t> <file> <p> <e> on 1..8 B200s (torchrun for > 1); with --polar SPEC: "
+                                             "the FER sweep of a mixed-kernel polar code (m = list size, t ignored)")
     ap.add_argument("m", type=int)
     ap.add_argument("t", type=int)
     ap.add_argument("file")
@@ -152,6 +180,8 @@ def main(argv=None):
     ap.add_argument("--J", type=int, default=-1)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--max-snr", type=float, default=5.0)
+    ap.add_argument("--min-snr", type=float, default=0.0)
+    ap.add_argument("--polar", default=None, metavar="SPEC", help="code specification file (MixedKernelEncoder.cpp:10-93 format); m = list size")
     a = ap.parse_args(argv)
     import torch
 
@@ -165,6 +195,18 @@ def main(argv=None):
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
     comm = Comm(dev)
+    if a.polar:
+        if os.path.exists(a.polar):
+            txt = open(a.polar).read().replace("@KERNEL@", os.path.join(pk.SPEC_DIR, "ebch16.kernel"))
+        else:
+            txt = pk.load_spec(a.polar)   # a specification committed under specs/
+        pol = pk.Polar(txt, L=a.m, device=local)
+        if comm.rank == 0:
+            print(f"polar ({pol.N}, {pol.K}), {pol.layers} layers, L = {pol.L}")
+        sweep(PolarEngine(pol), pol.K, comm, a.p, a.e, seed=a.seed, max_snr=a.max_snr, min_snr=a.min_snr, out_path=a.file, cumulative_ber=False, chunk=1 << 14)
+        if comm.world > 1:
+            torch.distributed.destroy_process_group()
+        return
     code = pk.Code(a.m, a.t, device=local)
     kan = pk.Kaneko(code, J=a.J)
     if comm.rank == 0:

@@ -187,3 +187,35 @@ def test_random_column_permutation_search(pk):
     assert sorted(map(tuple, r["matrix"].T.tolist())) == sorted(map(tuple, E.T.tolist()))
     r5 = pk.kernel_random_search(5, pk.ebch_kernel(5), 100000, seed=2, max_state_bits=14)
     assert r5["cost"] <= r5["input_cost"]
+
+
+@pytest.mark.parametrize("L", [1, 8])
+def test_polar_sweep_engine_and_stop_rule(pk, tmp_path, L):
+    """sweep.py --polar: the polar simulator loop behind the same point driver -- fixed frame count = pk_polar_run_frames,
+    the stop rule `count < p && countErr < e` = a sequential pass over the same frames cut right after the e-th error, and the
+    CLI writes one CSV row per SNR point."""
+    import sweep
+
+    pol = pk.Polar(pk.load_spec(), L=L, device=0)
+    eng = sweep.PolarEngine(pol)
+    snr, si, seed = 1.5, 3, 9
+    tot = sweep.run_point(eng, pol.K, sweep.Comm(), snr, si, seed, 5000, 0)
+    ref = pol.run_frames(snr, si, seed, 0, 5000)
+    assert (int(tot[0]), int(tot[1]), int(tot[2])) == (ref["frames"], ref["frame_errors"], ref["bit_errors"])
+    # stop rule against a sequential pass
+    e = 25
+    got = sweep.run_point(eng, pol.K, sweep.Comm(), snr, si, seed, 20000, e, chunk=1 << 10)
+    info, _, llr = pol.generate_frames(snr, si, seed, 0, int(got[0]) + 500)
+    cnt, inf, _, _ = pol.decode(llr)
+    be = (inf[:, 0, :] != info).sum(1)
+    cut = int(np.nonzero(np.cumsum(be > 0) == e)[0][0]) + 1
+    assert (int(got[0]), int(got[1]), int(got[2])) == (cut, e, int(be[:cut].sum()))
+    # CLI
+    out = tmp_path / f"polar_L{L}"
+    sweep.main([str(L), "0", str(out), "3000", "0", "--polar", "polar_256_128_ebch16.spec.in", "--min-snr", "1.0", "--max-snr", "2.0", "--seed", "3"])
+    rows = open(str(out) + ".csv").read().split()
+    assert len(rows) == 3
+    fer = [float(r.split(",")[1]) for r in rows]
+    assert [r.split(",")[0] for r in rows] == ["1", "1.5", "2"] and fer[0] > fer[1] > fer[2] > 0
+    p2 = pol.run_frames(2.0, 4, 3, 0, 3000)
+    assert abs(fer[2] - p2["frame_errors"] / 3000) < 1e-9
