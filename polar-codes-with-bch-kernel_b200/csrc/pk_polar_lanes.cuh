@@ -82,13 +82,11 @@ __host__ __device__ inline LanesLayout lanes_layout(const PkPolarDev &d, const P
 //   TYPE 2: M[x]  = min(M[x] + c(t), M[x+q] + c(!t))             (a row ends)
 //   TYPE 3: M[x]  = min(M[x] + c(t), M[x+q] + c(!t)), M[x+q] = min(M[x] + c(!t), M[x+q] + c(t))   (both: butterfly)
 // Entry (16 bits): byte offset of the metric row of x (a multiple of 32) | PAD << 1 | t.
-#ifndef PK_LANES_UNRB
-#define PK_LANES_UNRB(G) 1   // batches of 8 pairs in flight per step of a wide section (2: measured 7-15 % slower, r2t)
-#endif
-template <int G, int TYPE, bool TINY, int UNRB = 1>
+// (Two batches per step, software-pipelined batches and repacked entry words were measured and dropped: profiles/r2_notes.md 3.)
+template <int G, int TYPE, bool TINY>
 __device__ __forceinline__ void lanes_section(const unsigned char *__restrict__ tb, int nbatch, unsigned char *mcol, uint32_t qoff, float ay, uint32_t hd) {
-    constexpr int CH = 4 / G, NP = TINY ? CH : 2 * CH * UNRB;
-    for (int it = 0; it < (TINY ? 1 : nbatch); it += UNRB, tb += 16 * UNRB) {
+    constexpr int CH = 4 / G, NP = TINY ? CH : 2 * CH;
+    for (int it = 0; it < (TINY ? 1 : nbatch); ++it, tb += 16) {
         uint32_t e[NP];
 #pragma unroll
         for (int k = 0; k < NP / CH; ++k) {
@@ -131,68 +129,6 @@ __device__ __forceinline__ void lanes_section(const unsigned char *__restrict__ 
     }
 }
 
-// The same for sections of 16 and more pairs (nbatch >= 2, a power of two), software-pipelined: the entries and metrics of
-// the next batch are loaded before the results of the current one are stored (legal: the pairs of a section are disjoint;
-// the compiler cannot know), so a warp always has a batch of loads in flight.
-#ifndef PK_LANES_PIPE
-#define PK_LANES_PIPE 0   // measured slower (r3b: L=1 7.12 -> 6.78e6, L=32 1.78 -> 1.60e5 frames/s): more loads in flight do not help
-#endif
-template <int G, int TYPE>
-__device__ __forceinline__ void lanes_section_pipe(const unsigned char *__restrict__ tb, int nbatch, unsigned char *mcol, uint32_t qoff, float ay, uint32_t hd) {
-    constexpr int CH = 4 / G, NP = 2 * CH;
-    auto load = [&](const unsigned char *t, uint32_t (&e)[NP], float (&a)[NP], float (&b)[NP]) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            if constexpr (CH == 4) {
-                const uint2 q = *reinterpret_cast<const uint2 *>(t + 8 * k);
-                e[4 * k] = q.x; e[4 * k + 1] = q.x >> 16; e[4 * k + 2] = q.y; e[4 * k + 3] = q.y >> 16;
-            } else if constexpr (CH == 2) {
-                const uint32_t q = *reinterpret_cast<const uint32_t *>(t + 8 * k);
-                e[2 * k] = q; e[2 * k + 1] = q >> 16;
-            } else {
-                e[k] = *reinterpret_cast<const uint16_t *>(t + 8 * k);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < NP; ++u) {
-            const unsigned char *px = mcol + (e[u] & 0xFFE0u);
-            a[u] = *reinterpret_cast<const float *>(px);
-            if (TYPE >= 2) b[u] = *reinterpret_cast<const float *>(px + qoff);
-        }
-    };
-    auto finish = [&](const uint32_t (&e)[NP], const float (&a)[NP], const float (&b)[NP]) {
-#pragma unroll
-        for (int u = 0; u < NP; ++u) {
-            float *px = reinterpret_cast<float *>(mcol + (e[u] & 0xFFE0u));
-            float *pq = reinterpret_cast<float *>(mcol + (e[u] & 0xFFE0u) + qoff);
-            const bool sw = ((e[u] ^ hd) & 1u) != 0;
-            if (TYPE == 0) {
-                const float P = a[u] + ay;
-                *px = sw ? P : a[u];
-            } else if (TYPE == 1) {
-                const float P = a[u] + ay;
-                *px = sw ? P : a[u]; *pq = sw ? a[u] : P;
-            } else if (TYPE == 2) {
-                const float r0 = fminf(a[u], b[u] + ay), r1 = fminf(a[u] + ay, b[u]);
-                *px = sw ? r1 : r0;
-            } else {
-                const float r0 = fminf(a[u], b[u] + ay), r1 = fminf(a[u] + ay, b[u]);
-                *px = sw ? r1 : r0; *pq = sw ? r0 : r1;
-            }
-        }
-    };
-    uint32_t e0[NP], e1[NP];
-    float a0[NP], b0[NP], a1[NP], b1[NP];
-    load(tb, e0, a0, b0);
-    for (int it = 0; it < nbatch; it += 2) {
-        load(tb + 16, e1, a1, b1);
-        finish(e0, a0, b0);
-        tb += 32;
-        if (it + 2 < nbatch) load(tb, e0, a0, b0);
-        finish(e1, a1, b1);
-    }
-}
-
 // One Viterbi pass (TrellisKernelProcessor.cpp:260-293) for stride element i of every slot of the warp, on the in-place
 // numbering of the trellis (pk_polar.h); returns M[tag = 1] - M[tag = 0] (:292) in all lanes of the slot.
 //   tab/sec: staged tables (shared); src: the slot's value of section 0 (then + step per section); offw: offset words.
@@ -218,33 +154,16 @@ __device__ __forceinline__ float lanes_viterbi(const unsigned char *__restrict__
         y = *src;
         ow = *offw;
         sj = sec[j + 1];   // (sec[l] holds the position of the tagged row)
-        constexpr int UB = PK_LANES_UNRB(G);   // nb is a power of two: one batch, or whole steps of UB batches
-        if (PK_LANES_PIPE && nb >= 2) {
-            switch (type) {
-            case 8 + 0: lanes_section_pipe<G, 0>(tb, nb, mcol, qoff, ay, hd); break;
-            case 8 + 1: lanes_section_pipe<G, 1>(tb, nb, mcol, qoff, ay, hd); break;
-            case 8 + 2: lanes_section_pipe<G, 2>(tb, nb, mcol, qoff, ay, hd); break;
-            default: lanes_section_pipe<G, 3>(tb, nb, mcol, qoff, ay, hd); break;
-            }
-        } else if (UB > 1 && nb >= UB) {
-            switch (type) {
-            case 8 + 0: lanes_section<G, 0, false, UB>(tb, nb, mcol, qoff, ay, hd); break;
-            case 8 + 1: lanes_section<G, 1, false, UB>(tb, nb, mcol, qoff, ay, hd); break;
-            case 8 + 2: lanes_section<G, 2, false, UB>(tb, nb, mcol, qoff, ay, hd); break;
-            default: lanes_section<G, 3, false, UB>(tb, nb, mcol, qoff, ay, hd); break;
-            }
-        } else {
-            switch (type) {
-            case 8 + 0: lanes_section<G, 0, false>(tb, nb, mcol, qoff, ay, hd); break;
-            case 8 + 1: lanes_section<G, 1, false>(tb, nb, mcol, qoff, ay, hd); break;
-            case 8 + 2: lanes_section<G, 2, false>(tb, nb, mcol, qoff, ay, hd); break;
-            case 8 + 3: lanes_section<G, 3, false>(tb, nb, mcol, qoff, ay, hd); break;
-            case 12 + 0: lanes_section<G, 0, true>(tb, nb, mcol, qoff, ay, hd); break;
-            case 12 + 1: lanes_section<G, 1, true>(tb, nb, mcol, qoff, ay, hd); break;
-            case 12 + 2: lanes_section<G, 2, true>(tb, nb, mcol, qoff, ay, hd); break;
-            case 12 + 3: lanes_section<G, 3, true>(tb, nb, mcol, qoff, ay, hd); break;
-            default: break;
-            }
+        switch (type) {
+        case 8 + 0: lanes_section<G, 0, false>(tb, nb, mcol, qoff, ay, hd); break;
+        case 8 + 1: lanes_section<G, 1, false>(tb, nb, mcol, qoff, ay, hd); break;
+        case 8 + 2: lanes_section<G, 2, false>(tb, nb, mcol, qoff, ay, hd); break;
+        case 8 + 3: lanes_section<G, 3, false>(tb, nb, mcol, qoff, ay, hd); break;
+        case 12 + 0: lanes_section<G, 0, true>(tb, nb, mcol, qoff, ay, hd); break;
+        case 12 + 1: lanes_section<G, 1, true>(tb, nb, mcol, qoff, ay, hd); break;
+        case 12 + 2: lanes_section<G, 2, true>(tb, nb, mcol, qoff, ay, hd); break;
+        case 12 + 3: lanes_section<G, 3, true>(tb, nb, mcol, qoff, ay, hd); break;
+        default: break;
         }
         if (G > 1) __syncwarp();
     }
