@@ -178,19 +178,47 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------- B200 arm: shared plumbing
+def bind_to_gpu_numa_node(local):
+    """Run this rank on the cores of the NUMA node its GPU hangs off (so that page-locked host buffers, placed by first
+    touch, and the H2D / D2H copies of the end-to-end legs stay on one socket).  Multi-GPU runs only; returns a note."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:          # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa_node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"node {node}: no allowed cores"
+        os.sched_setaffinity(0, cpus)
+        return f"node {node}, {len(cpus)} cores"
+    except Exception as exc:   # noqa: BLE001  (best effort: a box without NVML / sysfs topology runs unbound)
+        return f"unbound ({type(exc).__name__})"
+
+
 class Env:
     """One rank: torch for device memory and process-group plumbing, the C-ABI communicator for the data path."""
 
     def __init__(self, a):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.numa = bind_to_gpu_numa_node(self.local) if self.world > 1 else "single rank: not bound"
         import torch
         import torch.distributed as dist
 
         import pkb200
 
         self.torch, self.dist, self.pk = torch, dist, pkb200.pk
-        self.world = int(os.environ.get("WORLD_SIZE", "1"))
-        self.rank = int(os.environ.get("RANK", "0"))
-        self.local = int(os.environ.get("LOCAL_RANK", "0"))
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
         torch.cuda.set_device(self.local)
@@ -554,7 +582,8 @@ def run_b200(a):
                 "api": ("pk_kaneko_decode_batch_async per (code, SNR point) batch + pk_kaneko_wait per step "
                         "(pinned host y -> host decisions + trial counts; copies overlap the kernels of the neighbouring batches)"),
                 "sync_call_value": replay_frames_step * a.steps / e2e_sync_s,
-                "sync_call_api": "pk_kaneko_decode_batch, one blocking call per (code, SNR point) batch"},
+                "sync_call_api": "pk_kaneko_decode_batch, one blocking call per (code, SNR point) batch",
+                "host_binding_rank0": env.numa},
         "fun_e2e": {"value": frames_per_step * a.steps / fun_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64 * len(SNRS) * len(CODES),
                     "api": "pk_comm_run_point: one blocking host call per (code, SNR point), reduced counters back in host memory (what the drop-in fun() does)"},
         "gpu_launches": int(launches),
