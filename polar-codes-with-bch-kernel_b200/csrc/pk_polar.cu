@@ -736,6 +736,26 @@ cudaError_t lanes_setup(pk_polar *h) {
         ent.resize(ent.size() + 16, 2u);
         std::vector<uint32_t> tab(ent.size() / 2);
         for (size_t x = 0; x < tab.size(); ++x) tab[x] = (uint32_t)ent[2 * x] | ((uint32_t)ent[2 * x + 1] << 16);
+        // bounds check of everything the kernel will dereference from these tables (it has no checks of its own): every
+        // batch lies inside the table, every row offset and partner offset inside the metric buffer
+        {
+            const uint32_t met_bytes = (uint32_t)ld.ns_rows * (uint32_t)nslot * 4u;
+            for (int p = 0; p < l; ++p)
+                for (int j = 0; j <= l; ++j) {
+                    const uint32_t *w = &sec[((size_t)p * (l + 1) + j) * 2];
+                    const uint32_t off = w[0] & 0xFFFFFFu, nb = w[0] >> 24, qoff = w[1] & 0xFFFFu, ty = w[1] >> 16;
+                    if (j == l) { if (qoff >= met_bytes) return cudaErrorInvalidValue; continue; }
+                    if (!(ty & 8u)) continue;
+                    const uint32_t nent = (ty & 4u) ? 4u : 8u * nb;
+                    if ((off & 7u) || off / 2 + nent > ent.size() - 16) return cudaErrorInvalidValue;
+                    for (uint32_t x = 0; x < nent; ++x) {
+                        const uint32_t en = ent[off / 2 + x];
+                        if (en & 2u) { if (!(ty & 4u)) return cudaErrorInvalidValue; continue; }   // padding only in one-group sections
+                        const uint32_t ro = en & 0xFFE0u;
+                        if ((ro % ((uint32_t)nslot * 4u)) || ro + ((ty & 3u) ? qoff : 0u) >= met_bytes) return cudaErrorInvalidValue;
+                    }
+                }
+        }
         std::vector<unsigned long long> masks((size_t)2 * l, 0);
         for (int r = 0; r < l; ++r)
             for (int cc = 0; cc < l; ++cc)
