@@ -170,7 +170,7 @@ def run_polar(a, Env, ClockSampler):
                     "frac": acs_per_s * ipa / (148 * 4 * sm_hz) if ipa else None, "traffic": NCU.get("polar_dram_bytes_per_launch"),
                     "kernel": NCU.get("polar_kernel", "k_polar_lanes<1,2> (2 dB)"), "acs_per_s": acs_per_s, "acs_per_frame": ACS_PER_PATH, "warp_inst_per_acs_ncu": ipa,
                     "peak_source": "148 SMs x 4 schedulers x one warp instruction per clock at the sampled SM clock", "ncu_source": NCU.get("polar_source"),
-                    "ncu": {k: NCU.get(k) for k in ("polar_issue_active_pct", "polar_lsu_wavefronts_pct", "polar_shared_bank_conflict_wavefronts_pct", "polar_warp_inst_per_frame", "polar_L32_warp_inst_per_frame", "polar_L32_issue_active_pct", "polar_r1_warp_inst_per_acs")},
+                    "ncu": {k: NCU.get(k) for k in ("polar_issue_active_pct", "polar_lsu_wavefronts_pct", "polar_shared_bank_conflict_wavefronts_pct", "polar_warp_inst_per_frame", "polar_L8_warp_inst_per_frame", "polar_L8_issue_active_pct", "polar_L32_warp_inst_per_frame", "polar_L32_issue_active_pct", "polar_r1_warp_inst_per_acs")},
                     "note": "ACS = branch evaluation of the reference's Viterbi recursion (2 per trellis state, 374 784 per SC pass); the in-place recursion spends one shared-memory load and store per state and runs 0.21 warp instructions per ACS (round 1: 1.5)"}
         line = {"metric": POLAR_METRIC, "value": res["value"], "unit": "frames/s", "n_gpus": env.world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32 LLRs / path metrics, u8 bits",
