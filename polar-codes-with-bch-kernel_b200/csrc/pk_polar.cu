@@ -11,8 +11,8 @@
 //
 // Two decoders share this file's set-up and C ABI:
 //   k_polar_lanes (pk_polar_lanes.cuh) -- list paths AND frames across the lanes of a warp, in-place Viterbi on the
-//     fixed-bit-position numbering of the kernel trellises, bits packed across slots.  Runs whenever the list size is a
-//     power of two and the trellises fit (every code the reference's trellis processor accepts at L <= 32 so far).
+//     fixed-bit-position numbering of the kernel trellises, bits packed across slots.  Runs for every list size <= 32
+//     whenever the trellises fit the shared memory of an SM (every code of the tests).
 //   k_polar_decode (below) -- one CTA per frame group, ONE WARP PER LIST PATH, lanes across trellis states in gather
 //     form; the general fall-back (any L <= 32) and the decoder the lanes kernel is tested against.
 // In both, every value is a single fp32 add or min of the reference's operands in the reference's order, so kernel
@@ -637,7 +637,7 @@ struct pk_polar {
     int fpc = 1;   // frames per CTA
     // decoder with paths across lanes (pk_polar_lanes.cuh); ln_g = 0: not applicable, k_polar_decode runs
     PkLanesDev lanes{};
-    int ln_g = 0, ln_warps = 0, ln_grid = 0;     // lanes per slot, warps per CTA, CTAs
+    int ln_g = 0, ln_ls = 0, ln_warps = 0, ln_grid = 0;   // lanes per slot, slots per frame (list size rounded up to a power of two), warps per CTA, CTAs
     size_t ln_smem = 0;
     float *ln_chan = nullptr;                    // transposed channel LLRs, one block per warp of the grid
     // generation-mode workspaces (one chunk of frames)
@@ -666,8 +666,8 @@ cudaError_t up(pk_polar *h, const std::vector<Tp> &v, const Tp **d) {
 
 cudaError_t lanes_launch(pk_polar *h, const float *d_llr, long B, int *d_count, uint8_t *d_inf, uint8_t *d_cw, float *d_metric, cudaStream_t st) {
 #define X(LL, GG)                                                                                                                       \
-    if (h->L == LL && h->ln_g == GG) {                                                                                                    \
-        k_polar_lanes<LL, GG><<<h->ln_grid, 32 * h->ln_warps, h->ln_smem, st>>>(h->dev, h->lanes, d_llr, B, d_count, d_inf, d_cw, d_metric, h->ln_chan); \
+    if (h->ln_ls == LL && h->ln_g == GG) {                                                                                                \
+        k_polar_lanes<LL, GG><<<h->ln_grid, 32 * h->ln_warps, h->ln_smem, st>>>(h->dev, h->lanes, h->L, d_llr, B, d_count, d_inf, d_cw, d_metric, h->ln_chan); \
         return cudaGetLastError();                                                                                                        \
     }
     PK_LANES_CASES(X)
@@ -676,21 +676,21 @@ cudaError_t lanes_launch(pk_polar *h, const float *d_llr, long B, int *d_count, 
 }
 cudaError_t lanes_attr(pk_polar *h) {
 #define X(LL, GG) \
-    if (h->L == LL && h->ln_g == GG) return cudaFuncSetAttribute(k_polar_lanes<LL, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ln_smem);
+    if (h->ln_ls == LL && h->ln_g == GG) return cudaFuncSetAttribute(k_polar_lanes<LL, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ln_smem);
     PK_LANES_CASES(X)
 #undef X
     return cudaErrorInvalidConfiguration;
 }
 
-// Leaves h->ln_g = 0 (k_polar_decode runs instead) when the code does not fit the scheme: list size not a power of two
-// or a kernel trellis too wide for the 16-bit row offsets / the shared memory of an SM.
+// Leaves h->ln_g = 0 (k_polar_decode runs instead) when the code does not fit the scheme: a kernel trellis too wide for
+// the 16-bit row offsets / the shared memory of an SM.
 cudaError_t lanes_setup(pk_polar *h) {
     const pk_polar_code &c = h->code;
     const PkPolarDev &d = h->dev;
-    const int L = h->L;
+    int L = 1;                      // slots per frame: the list size rounded up to a power of two (the spare slots stay empty)
+    while (L < h->L) L <<= 1;
     const char *off = getenv("PK_POLAR_LANES");
     if (off && atoi(off) == 0) return cudaSuccess;
-    if (L & (L - 1)) return cudaSuccess;
     const char *env = getenv("PK_POLAR_LANES_G");
     int G = env ? atoi(env) : 2;
     if (G != 1 && G != 2 && G != 4) G = 2;
@@ -783,6 +783,7 @@ cudaError_t lanes_setup(pk_polar *h) {
     e = cudaMalloc(&h->ln_chan, (size_t)h->ln_grid * warps * d.N0 * (nslot / L) * sizeof(float));
     if (e != cudaSuccess) return e;
     h->ln_g = G;
+    h->ln_ls = L;
     return lanes_attr(h);
 }
 }  // namespace

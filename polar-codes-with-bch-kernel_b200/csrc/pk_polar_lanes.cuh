@@ -172,9 +172,10 @@ __device__ __forceinline__ float lanes_viterbi(const unsigned char *__restrict__
     return r;
 }
 
+// L = slots per frame (a power of two), Lr = the list size (<= L: the slots Lr .. L-1 of a frame are never used)
 template <int L, int G>
 __global__ void __launch_bounds__(G == 1 ? 256 : 512, 1)
-k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, long B, int *__restrict__ count,
+k_polar_lanes(PkPolarDev d, PkLanesDev ld, int Lr, const float *__restrict__ llr_in, long B, int *__restrict__ count,
               uint8_t *__restrict__ inf_out, uint8_t *__restrict__ cw_out, float *__restrict__ metric_out, float *__restrict__ scr_chan) {
     constexpr int NSLOT = 32 / G, FPW = NSLOT / L;
     static_assert(L * G <= 32 && (L & (L - 1)) == 0 && (G == 1 || G == 2 || G == 4), "slots");
@@ -225,9 +226,9 @@ k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, lon
             chanT[idx] = v;
         }
         // ---- Cleanup + AssignInitialPath (TVMemoryEngine.cpp:58-94): the first Pop of the lazily initialised stack is L - 1
-        bool act = live && p == L - 1;
+        bool act = live && p == Lr - 1;
         float R = 0.0f;
-        int cnt = L - 1;        // free path indices on the stack (positions 0 .. cnt-1)
+        int cnt = Lr - 1;       // free path indices on the stack (positions 0 .. cnt-1)
         int cmap = slot;        // column holding this path's copy of the outer arrays
         if (L > 1) {
             if (g == 0) st[p] = (uint32_t)p;
@@ -309,7 +310,7 @@ k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, lon
                     rb += (m1 > mb || (m1 == mb && s1 > sb)) ? 1 : 0;
                     rb += (m2 > mb || (m2 == mb && s2 > sb)) ? 1 : 0;
                 }
-                const int J = 2 * __popc((amask >> gs) & GM), keep = J < L ? J : L;
+                const int J = 2 * __popc((amask >> gs) & GM), keep = J < Lr ? J : Lr;
                 const bool ka = act && ra < keep, kb = act && rb < keep;
                 const bool kill = act && !ka && !kb, clone = ka && kb;
                 bit = ka ? D : (D ^ 1u);   // the one continuation, or the better one of two (C = LLR < 0, :165)
@@ -433,7 +434,7 @@ k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, lon
         for (uint32_t m = amask; m; m &= m - 1) {
             const int s = __ffs(m) - 1;
             const int rk = __shfl_sync(PKP_FULL, rank, s);
-            const long row = (grp * FPW + s / L) * L + rk;
+            const long row = (grp * FPW + s / L) * Lr + rk;
             if (inf_out)
                 for (int q = lane; q < d.K; q += 32) inf_out[row * d.K + q] = (uint8_t)((U[d.info_pos[q]] >> s) & 1u);
             if (cw_out) {
@@ -444,7 +445,7 @@ k_polar_lanes(PkPolarDev d, PkLanesDev ld, const float *__restrict__ llr_in, lon
                 }
             }
         }
-        if (act && g == 0 && metric_out) metric_out[fr * L + rank] = R;
+        if (act && g == 0 && metric_out) metric_out[fr * Lr + rank] = R;
         if (live && p == 0 && g == 0 && count) count[fr] = __popc((amask >> gs) & GM);
         __syncwarp();
     }

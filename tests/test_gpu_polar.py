@@ -143,11 +143,12 @@ def test_generation_mode_equals_decode_of_the_dumped_frames(pk, name, L):
 
 
 @pytest.mark.parametrize("name", ["polar_256_128_ebch16.spec.in", "polar_256_128_ebch16_dyn.spec.in", "polar_240_114_ebch16_sp.spec.in"])
-@pytest.mark.parametrize("L,G", [(1, 1), (1, 2), (1, 4), (2, 2), (4, 1), (4, 4), (8, 1), (8, 2), (8, 4), (16, 1), (16, 2), (32, 1)])
+@pytest.mark.parametrize("L,G", [(1, 1), (1, 2), (1, 4), (2, 2), (3, 2), (4, 1), (4, 4), (5, 4), (6, 1), (8, 1), (8, 2), (8, 4), (12, 2), (16, 1), (16, 2), (24, 1), (32, 1)])
 def test_lanes_decoder_equals_warp_per_path_decoder(pk, name, L, G, monkeypatch):
     """k_polar_lanes (paths across lanes, G lanes per path) against k_polar_decode (one warp per path, pinned to the
     reference library above) on the same LLRs: list sizes, information vectors, codewords and fp32 metrics identical,
-    for every list size and lane split the dispatcher knows; the frame count is not a multiple of the frames per warp."""
+    for every lane split the dispatcher knows and list sizes that are not powers of two (they run in the next power of
+    two of slots per frame); the frame count is not a multiple of the frames per warp."""
     spec = pk.load_spec(name)
     monkeypatch.setenv("PK_POLAR_LANES", "0")
     old = pk.Polar(spec, L=L, device=0)
@@ -199,7 +200,7 @@ def _make_spec(tmp_path, sizes, K, seed, dyn=0):
 
 
 @pytest.mark.parametrize("sizes,K,dyn", [((16,), 8, 0), ((8,), 4, 1), ((8, 16), 64, 0), ((16, 8), 70, 5), ((8, 8, 8), 256, 0), ((8, 8), 32, 6)])
-@pytest.mark.parametrize("L", [1, 4, 32])
+@pytest.mark.parametrize("L", [1, 4, 7, 32])
 def test_lanes_decoder_on_other_code_shapes(pk, oracle_mod, tmp_path, monkeypatch, sizes, K, dyn, L):
     """One, two and three layers, different kernels per layer, dynamic frozen symbols: k_polar_lanes against
     k_polar_decode and, where oracle/_ref is present, against the reference library itself."""
