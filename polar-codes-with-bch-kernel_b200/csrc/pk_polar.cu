@@ -695,7 +695,6 @@ cudaError_t lanes_setup(pk_polar *h) {
     int G = env ? atoi(env) : 2;
     if (G != 1 && G != 2 && G != 4) G = 2;
     while (L * G > 32) G >>= 1;
-    const int nslot = 32 / G;
     PkLanesDev &ld = h->lanes;
     ld.nk = (int)c.kernels.size();
     ld.ns_rows = 1;
@@ -703,6 +702,9 @@ cudaError_t lanes_setup(pk_polar *h) {
         if (!k.ip_ok || k.ip_bits > 14) return cudaSuccess;
         ld.ns_rows = std::max(ld.ns_rows, 1 << k.ip_bits);
     }
+    // wide trellises: more lanes per slot make the metric rows shorter (16-bit row offsets, shared memory per warp)
+    while ((size_t)ld.ns_rows * (32 / G) * 4 > 65534 && G < 4 && L * G * 2 <= 32) G *= 2;
+    const int nslot = 32 / G;
     if ((size_t)ld.ns_rows * nslot * 4 > 65534) return cudaSuccess;
     for (int j = 0; j < c.layers; ++j) ld.kidx[j] = c.kid[j];
     cudaError_t e = cudaSuccess;
@@ -869,10 +871,12 @@ int pk_polar_create(const char *spec_text, int L, int device, pk_polar **out) {
         const PathLayout pl = path_layout(d);
         const size_t path_sz = (((size_t)pl.floats * 4 + 15) & ~(size_t)15) + pl.bytes;
         const size_t frame_sz = ((sizeof(ListCtl) + 15) & ~(size_t)15) + (size_t)d.N0 * 4 + (size_t)L * path_sz;
-        h->fpc = std::max(1, 8 / L);   // at least 8 warps per CTA share the staged trellis tables
-        h->smem_decode = polar_table_bytes(d) + (size_t)h->fpc * frame_sz + (size_t)h->fpc * L * polar_met_floats(d.max_ab) * 4;
         int smem_max = 0;
         e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        h->fpc = std::max(1, 8 / L);   // at least 8 warps per CTA share the staged trellis tables ..
+        auto need = [&](int fpc) { return polar_table_bytes(d) + (size_t)fpc * frame_sz + (size_t)fpc * L * polar_met_floats(d.max_ab) * 4; };
+        while (h->fpc > 1 && e == cudaSuccess && need(h->fpc) > (size_t)smem_max) h->fpc /= 2;   // .. fewer where the trellises are wide
+        h->smem_decode = need(h->fpc);
         if (e == cudaSuccess && h->smem_decode > (size_t)smem_max) {
             for (void *p : h->allocs) cudaFree(p);
             cudaStreamDestroy(h->stream);

@@ -222,3 +222,36 @@ def test_lanes_decoder_on_other_code_shapes(pk, oracle_mod, tmp_path, monkeypatc
         r = ref.decode(llr)
         assert np.array_equal(n[0], r[0]) and np.array_equal(n[3].view(np.uint32), r[3].view(np.uint32))
         assert np.array_equal(n[1], r[1]) and np.array_equal(n[2], r[2])
+
+
+@pytest.mark.parametrize("n,seed", [(20, 1), (20, 2), (24, 2), (24, 5)])
+@pytest.mark.parametrize("L", [1, 4, 8, 32])
+def test_wide_random_kernels(pk, oracle_mod, tmp_path, monkeypatch, n, seed, L):
+    """Random invertible n x n kernels (single layer) whose trellises have 2^9 .. 2^12 states: the lanes decoder takes more
+    lanes per slot where the 16-bit row offsets need it (2^9: G = 2, 2^10: G = 4) and equals the warp-per-path decoder and
+    the reference library; trellis tables beyond the shared memory of an SM (2^11 and more states) are refused loudly."""
+    rng = np.random.default_rng(seed)
+    while True:
+        K = rng.integers(0, 2, (n, n), dtype=np.uint8)
+        if round(abs(np.linalg.det(K.astype(float)))) % 2 == 1:
+            break
+    kf = tmp_path / "k.kernel"
+    kf.write_text(f"{n}\n" + "\n".join(" ".join(str(int(v)) for v in r) for r in K) + "\n")
+    spec = f"{n} {n // 2} 1 1 0 0\n-{kf}\n" + "".join("1 %d\n" % j for j in range(n - n // 2))
+    bits = int(pk.Polar(spec, L=1, device=None).trellis_profile(0).max())
+    monkeypatch.setenv("PK_POLAR_LANES", "0")
+    try:
+        old = pk.Polar(spec, L=L, device=0)
+    except pk.PkError as exc:            # tables + 2^bits states x L paths do not fit the shared memory of an SM
+        assert "shared memory" in str(exc) and (bits >= 11 or L == 32)
+        pytest.skip(f"{bits} state bits at L = {L}: no decoder fits")
+    monkeypatch.setenv("PK_POLAR_LANES", "1")
+    new = pk.Polar(spec, L=L, device=0)
+    _, _, llr = new.generate_frames(2.0, 4, 3, 0, 40)
+    o, nn = old.decode(llr), new.decode(llr)
+    assert np.array_equal(nn[0], o[0]) and np.array_equal(nn[3].view(np.uint32), o[3].view(np.uint32))
+    assert np.array_equal(nn[1], o[1]) and np.array_equal(nn[2], o[2])
+    if oracle_mod.polar_ref_available():
+        r = oracle_mod.PolarReference(spec, L).decode(llr)
+        assert np.array_equal(nn[0], r[0]) and np.array_equal(nn[3].view(np.uint32), r[3].view(np.uint32))
+        assert np.array_equal(nn[1], r[1]) and np.array_equal(nn[2], r[2])
