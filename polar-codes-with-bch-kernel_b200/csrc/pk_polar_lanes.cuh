@@ -209,7 +209,10 @@ k_polar_lanes(PkPolarDev d, PkLanesDev ld, int Lr, const float *__restrict__ llr
     const int last = d.layers - 1, lsz = d.ksize[last];
     const int cm_off = pl.c_off[d.layers], ol_off = pl.o_off[last];   // innermost C array and offsets: copied eagerly
 
-    for (long grp = gw; grp * FPW < B; grp += tw) {
+    // (the trip count depends on the CTA only: control flow that is uniform over the whole CTA, not just the warp, measured
+    // 9 % faster at L = 32; a warp past the end runs one idle group)
+    for (long grp0 = (long)blockIdx.x * nwarps; grp0 * FPW < B; grp0 += tw) {
+        const long grp = grp0 + warp;
         const long fr = grp * FPW + fslot;
         const bool live = fr < B;
         // ---- LoadLLRs (MixedKernelEncoder.cpp:179-203), transposed: chanT[i][frame slot]
