@@ -182,7 +182,9 @@ k_polar_lanes(PkPolarDev d, PkLanesDev ld, int Lr, const float *__restrict__ llr
     constexpr uint32_t SLOTS = NSLOT == 32 ? 0xFFFFFFFFu : ((1u << NSLOT) - 1u);   // the g = 0 lanes: lane == slot
     constexpr uint32_t GM = L == 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
     extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // (the warp index through a shuffle: the compiler then knows it is uniform over the warp and keeps what derives from
+    // it -- the warp's shared-memory region -- in uniform registers)
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(PKP_FULL, (int)(threadIdx.x >> 5), 0), nwarps = blockDim.x >> 5;
     const int g = lane / NSLOT, slot = lane % NSLOT, fslot = slot / L, p = slot % L, gs = fslot * L;
     const PathLayout pl = path_layout(d);
     const LanesLayout ly = lanes_layout(d, ld, pl, L, NSLOT);
